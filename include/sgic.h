@@ -1,0 +1,127 @@
+/*
+ * sgic.h — C ABI of the B200-native exact inner-product k-NN path.
+ *
+ * This is the drop-in boundary for the retrieval hot path of
+ * lionl1106/Searchable-Generative-Image-Compression.  The reference has no FFI of its own:
+ * it reaches the arithmetic through the Python `faiss` module (IndexFlatIP / add / search /
+ * ntotal / d / read_index / write_index).  Each entry point below names the reference call
+ * site it replaces (paths relative to the reference root).  Plain pointers and sizes only; no
+ * torch / numpy types.  Every function returns 0 on success, non-zero on failure;
+ * sgic_last_error() returns the calling thread's last message (what the Python layer raises
+ * as RuntimeError, mirroring how faiss surfaces C++ exceptions).
+ *
+ * Buffers named host_* are ordinary host memory (pageable or pinned).  Buffers named dev_*
+ * are device pointers on the index's device; `stream` is a cudaStream_t passed as void*
+ * (NULL = the index's own stream).  *_dev calls enqueue work and do not synchronise.
+ */
+#ifndef SGIC_H_
+#define SGIC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgic_index sgic_index;
+
+enum { SGIC_F16 = 0, SGIC_BF16 = 1 };  /* storage type of the HBM-resident database */
+
+enum {
+  SGIC_RETAIN_F32 = 1, /* keep the fp32 rows given to add_f32 on the host so that
+                          sgic_index_write is bit-identical to faiss.write_index */
+};
+
+/* per-file status codes of the batched .c2df ingest; they mirror the exceptions of
+ * decode_clip_from_c2df (src/search.py:24-41 == src/build.py:26-43) and unpack_c2df
+ * (src/filemaker.py:137-173) that build.py:87-88 turns into "[SKIP] name: err". */
+enum {
+  SGIC_C2DF_OK = 0,
+  SGIC_C2DF_BAD_MAGIC = 1,     /* filemaker.py:145  assert data[:4] == b"C2DF"            */
+  SGIC_C2DF_TRUNCATED = 2,     /* struct.error / short slice while walking the TLV entries */
+  SGIC_C2DF_NO_CLIP = 3,       /* search.py:26-27   ValueError: no clip_stream / clip_meta */
+  SGIC_C2DF_BAD_DIM = 4,       /* search.py:31-33   ValueError: invalid clip_meta.dim      */
+  SGIC_C2DF_ZSTD = 5,          /* search.py:35      zstd.ZstdError                         */
+  SGIC_C2DF_DIM_MISMATCH = 6,  /* search.py:37-38   ValueError: q.size != dim              */
+  SGIC_C2DF_WRONG_D = 7,       /* row dimension differs from the index's d (np.concatenate
+                                  would raise in build.py:91)                              */
+  SGIC_C2DF_BAD_TYPE = 8,      /* filemaker.py:135  ValueError: unknown type code          */
+};
+
+const char* sgic_last_error(void);
+int sgic_version(void);
+
+/* faiss.IndexFlatIP(d) — src/build.py:93,232; src/compress.py:97.
+ * dtype: SGIC_F16 | SGIC_BF16.  device: CUDA ordinal.  capacity_rows: rows to reserve up
+ * front (0 = grow on demand).  d must be a multiple of 8 and <= 2048. */
+int sgic_index_create(int d, int dtype, int device, int64_t capacity_rows, int flags, sgic_index** out);
+int sgic_index_destroy(sgic_index* h);
+
+/* index.ntotal / index.d — src/search.py:78,114; src/build.py:101,120,240. */
+int64_t sgic_index_ntotal(const sgic_index* h);
+int sgic_index_d(const sgic_index* h);
+int sgic_index_dtype(const sgic_index* h);
+int sgic_index_device(const sgic_index* h);
+
+int sgic_index_reserve(sgic_index* h, int64_t rows);
+int sgic_index_reset(sgic_index* h);
+
+/* index.add(X) — src/build.py:94,233; src/compress.py:107.  X is (n,d) fp32 C-contiguous;
+ * rows are appended as given (no normalisation), rounded to the storage type on device. */
+int sgic_index_add_f32(sgic_index* h, int64_t n, const float* host_x);
+int sgic_index_add_f32_dev(sgic_index* h, int64_t n, const float* dev_x, void* stream);
+/* rows already in the storage type on the device (synthetic generators, shard loaders) */
+int sgic_index_add_packed_dev(sgic_index* h, int64_t n, const void* dev_rows, void* stream);
+
+/* Device-side loader for the u8 payload of clip_stream: dequantize_clip_u8 + l2n
+ * (src/search.py:16-22) run as one kernel, 1 byte/element over PCIe. */
+int sgic_index_add_u8(sgic_index* h, int64_t n, const uint8_t* host_q);
+int sgic_index_add_u8_dev(sgic_index* h, int64_t n, const uint8_t* dev_q, void* stream);
+
+/* Batched .c2df ingest — the loop of build_index_from_c2df_dir (src/build.py:80-88).
+ * blob holds n files back to back; file i is blob[offsets[i] .. offsets[i+1]) (n+1 offsets).
+ * status_out[i] gets a SGIC_C2DF_* code; files with status != 0 are skipped (as [SKIP] does)
+ * and the good ones are appended in order.  Returns the number of rows added in *n_added. */
+int sgic_index_add_c2df(sgic_index* h, const uint8_t* blob, const int64_t* offsets, int64_t n,
+                        int32_t* status_out, int64_t* n_added, int n_threads);
+
+/* Host-only half of the above: walk the TLV container, find clip_stream / clip_meta.dim,
+ * zstd-decode into out_u8 (n rows of `dim` bytes; rows of failed files are left untouched).
+ * dim_out[i] receives clip_meta.dim (or 0).  No GPU needed. */
+int sgic_c2df_parse(const uint8_t* blob, const int64_t* offsets, int64_t n, int dim, uint8_t* out_u8,
+                    int32_t* status_out, int32_t* dim_out, int n_threads);
+
+/* index.search(q, k) — src/search.py:115 (faiss search_c(n, x, k, D, I)).
+ * host_q (nq,d) fp32; D (nq,k) fp32 and I (nq,k) int64 are caller-owned host buffers.
+ * Per query: the k largest inner products sorted descending; ties ordered by ascending row;
+ * missing slots are I=-1, D=-FLT_MAX.  k >= 1. */
+int sgic_index_search(sgic_index* h, int64_t nq, const float* host_q, int64_t k, float* host_D,
+                      int64_t* host_I);
+/* Same with device-resident queries and outputs; id_base is added to every returned row
+ * number (a shard's first global row). */
+int sgic_index_search_dev(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D,
+                          int64_t* dev_I, int64_t id_base, void* stream);
+
+/* Merge of per-shard answers after the all-gather: lists laid out
+ * [n_lists][nq][k]; shard g holds rows below shard g+1.  Output (nq,k). */
+int sgic_merge_topk_dev(int device, int64_t nq, int n_lists, int64_t k, const float* dev_D_lists,
+                        const int64_t* dev_I_lists, float* dev_D, int64_t* dev_I, void* stream);
+
+/* faiss.write_index / faiss.read_index — src/build.py:95,99,235,238; src/compress.py:95,111;
+ * src/search.py:69,76.  File layout "IxFI" (SURVEY.md §8a F3): fp32 little-endian rows. */
+int sgic_index_write(sgic_index* h, const char* path);
+int sgic_index_read(const char* path, int dtype, int device, int flags, sgic_index** out);
+
+/* rows [i0, i0+n) up-cast to fp32 (faiss reconstruct_n); host buffer. */
+int sgic_index_reconstruct(sgic_index* h, int64_t i0, int64_t n, float* host_out);
+
+/* Device pointer of the packed database and timing of the last search (kernel-only, ms,
+ * measured with CUDA events on the index's stream when enabled). */
+const void* sgic_index_data_dev(const sgic_index* h);
+int sgic_index_set_option(sgic_index* h, const char* name, int64_t value);
+int64_t sgic_index_get_stat(const sgic_index* h, const char* name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGIC_H_ */

@@ -1,0 +1,372 @@
+// Batched .c2df header parser (host side of north-star item (a)).
+//
+// Replaces the per-file Python loop of build_index_from_c2df_dir (reference
+// src/build.py:80-88): for every file it walks the little-endian TLV container written by
+// pack_c2df (src/filemaker.py:75-100; reader :137-173), locates the `clip_stream` (BYTES)
+// and `clip_meta` (JSON) entries, reads clip_meta.dim, and zstd-decodes the stream into one
+// u8 row.  The rows then cross PCIe at 1 byte/element and are expanded on the device (K1).
+//
+// libzstd has no headers in the image, so the four entry points used are resolved with
+// dlopen("libzstd.so.1") and hand-declared prototypes (stable public ABI since zstd 1.0).
+#include <dlfcn.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/sgic.h"
+
+namespace sgic {
+void set_error(const std::string& msg);  // defined in sgic_api.cu
+
+namespace {
+
+struct ZstdApi {
+  void* lib = nullptr;
+  void* (*createDCtx)() = nullptr;
+  size_t (*freeDCtx)(void*) = nullptr;
+  size_t (*decompressDCtx)(void*, void*, size_t, const void*, size_t) = nullptr;
+  unsigned long long (*getFrameContentSize)(const void*, size_t) = nullptr;
+  unsigned (*isError)(size_t) = nullptr;
+  bool ok = false;
+};
+
+const ZstdApi& zstd_api() {
+  static ZstdApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libzstd.so.1", "libzstd.so"};
+    for (const char* n : names) {
+      api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+      if (api.lib) break;
+    }
+    if (!api.lib) return;
+    api.createDCtx = reinterpret_cast<void* (*)()>(dlsym(api.lib, "ZSTD_createDCtx"));
+    api.freeDCtx = reinterpret_cast<size_t (*)(void*)>(dlsym(api.lib, "ZSTD_freeDCtx"));
+    api.decompressDCtx = reinterpret_cast<size_t (*)(void*, void*, size_t, const void*, size_t)>(
+        dlsym(api.lib, "ZSTD_decompressDCtx"));
+    api.getFrameContentSize =
+        reinterpret_cast<unsigned long long (*)(const void*, size_t)>(dlsym(api.lib, "ZSTD_getFrameContentSize"));
+    api.isError = reinterpret_cast<unsigned (*)(size_t)>(dlsym(api.lib, "ZSTD_isError"));
+    api.ok = api.createDCtx && api.freeDCtx && api.decompressDCtx && api.getFrameContentSize && api.isError;
+  });
+  return api;
+}
+
+// type codes, src/filemaker.py:4-11
+enum : uint8_t { T_BYTES = 0, T_STR = 1, T_INT = 2, T_FLOAT = 3, T_JSON = 4, T_NP = 5, T_NONE = 6, T_BOOL = 7 };
+
+struct Cursor {
+  const uint8_t* p;
+  size_t n;
+  size_t off = 0;
+  bool take(size_t len, const uint8_t** out) {
+    if (len > n - off) return false;
+    *out = p + off;
+    off += len;
+    return true;
+  }
+  bool u8(uint8_t* v) {
+    const uint8_t* q;
+    if (!take(1, &q)) return false;
+    *v = q[0];
+    return true;
+  }
+  bool u16(uint16_t* v) {
+    const uint8_t* q;
+    if (!take(2, &q)) return false;
+    *v = static_cast<uint16_t>(q[0] | (q[1] << 8));
+    return true;
+  }
+  bool u32(uint32_t* v) {
+    const uint8_t* q;
+    if (!take(4, &q)) return false;
+    *v = static_cast<uint32_t>(q[0]) | (static_cast<uint32_t>(q[1]) << 8) | (static_cast<uint32_t>(q[2]) << 16) |
+         (static_cast<uint32_t>(q[3]) << 24);
+    return true;
+  }
+};
+
+// ---- a JSON skipper just big enough to read the top-level "dim" of clip_meta ----------
+struct Json {
+  const char* s;
+  size_t n;
+  size_t i = 0;
+  void ws() {
+    while (i < n && (s[i] == ' ' || s[i] == '\t' || s[i] == '\n' || s[i] == '\r')) ++i;
+  }
+  bool string(size_t* b, size_t* e) {  // raw span between the quotes
+    if (i >= n || s[i] != '"') return false;
+    ++i;
+    *b = i;
+    while (i < n && s[i] != '"') {
+      if (s[i] == '\\') ++i;
+      ++i;
+    }
+    if (i >= n) return false;
+    *e = i;
+    ++i;
+    return true;
+  }
+  bool skip_value() {
+    ws();
+    if (i >= n) return false;
+    const char c = s[i];
+    if (c == '"') {
+      size_t b, e;
+      return string(&b, &e);
+    }
+    if (c == '{' || c == '[') {
+      const char close = (c == '{') ? '}' : ']';
+      ++i;
+      ws();
+      if (i < n && s[i] == close) {
+        ++i;
+        return true;
+      }
+      for (;;) {
+        if (c == '{') {
+          ws();
+          size_t b, e;
+          if (!string(&b, &e)) return false;
+          ws();
+          if (i >= n || s[i] != ':') return false;
+          ++i;
+        }
+        if (!skip_value()) return false;
+        ws();
+        if (i >= n) return false;
+        if (s[i] == ',') {
+          ++i;
+          continue;
+        }
+        if (s[i] == close) {
+          ++i;
+          return true;
+        }
+        return false;
+      }
+    }
+    // number / true / false / null / NaN / Infinity
+    const size_t b = i;
+    while (i < n && s[i] != ',' && s[i] != '}' && s[i] != ']' && s[i] != ' ' && s[i] != '\t' && s[i] != '\n' &&
+           s[i] != '\r')
+      ++i;
+    return i > b;
+  }
+};
+
+// int(meta.get('dim', 0)) for a JSON object payload.  Returns false when Python would have
+// raised (not an object, value not convertible); *dim = 0 when the key is absent / meta falsy.
+bool clip_meta_dim(const char* s, size_t n, long long* dim) {
+  *dim = 0;
+  Json j{s, n};
+  j.ws();
+  if (j.i >= n) return false;
+  if (s[j.i] != '{') {
+    // `meta = enc_result['clip_meta'] or {}`: null / false / 0 / "" / [] become {}
+    const std::string v(s + j.i, n - j.i);
+    if (v.rfind("null", 0) == 0 || v.rfind("false", 0) == 0 || v.rfind("[]", 0) == 0 || v.rfind("\"\"", 0) == 0 ||
+        v == "0")
+      return true;
+    return false;  // a list / str / number has no .get -> AttributeError in the reference
+  }
+  ++j.i;
+  j.ws();
+  if (j.i < n && s[j.i] == '}') return true;
+  for (;;) {
+    j.ws();
+    size_t kb, ke;
+    if (!j.string(&kb, &ke)) return false;
+    j.ws();
+    if (j.i >= n || s[j.i] != ':') return false;
+    ++j.i;
+    j.ws();
+    const size_t vb = j.i;
+    if (!j.skip_value()) return false;
+    const size_t ve = j.i;
+    if (ke - kb == 3 && std::memcmp(s + kb, "dim", 3) == 0) {
+      std::string v(s + vb, ve - vb);
+      if (!v.empty() && v.front() == '"' && v.back() == '"') v = v.substr(1, v.size() - 2);  // int("512")
+      if (v == "true") {
+        *dim = 1;
+      } else if (v == "false") {
+        *dim = 0;
+      } else {
+        char* end = nullptr;
+        const double dv = std::strtod(v.c_str(), &end);
+        if (end == v.c_str() || *end != '\0' || dv != dv || dv > 9e15 || dv < -9e15) return false;
+        *dim = static_cast<long long>(dv);  // int() truncates toward zero
+      }
+    }
+    j.ws();
+    if (j.i >= n) return false;
+    if (s[j.i] == ',') {
+      ++j.i;
+      continue;
+    }
+    if (s[j.i] == '}') return true;
+    return false;
+  }
+}
+
+struct Found {
+  const uint8_t* stream = nullptr;
+  size_t stream_len = 0;
+  bool has_stream = false, stream_is_bytes = false;
+  const uint8_t* meta = nullptr;
+  size_t meta_len = 0;
+  bool has_meta = false;
+  uint8_t meta_type = T_NONE;
+};
+
+int walk_one(const uint8_t* data, size_t n, Found* f) {
+  if (n < 4 || std::memcmp(data, "C2DF", 4) != 0) return SGIC_C2DF_BAD_MAGIC;
+  Cursor c{data, n, 4};
+  uint16_t ver;
+  uint32_t hlen, n_items;
+  const uint8_t* skip;
+  if (!c.u16(&ver) || !c.u32(&hlen) || !c.take(hlen, &skip) || !c.u32(&n_items)) return SGIC_C2DF_TRUNCATED;
+  for (uint32_t it = 0; it < n_items; ++it) {
+    uint16_t klen;
+    const uint8_t* key;
+    uint8_t t;
+    if (!c.u16(&klen) || !c.take(klen, &key) || !c.u8(&t)) return SGIC_C2DF_TRUNCATED;
+    const uint8_t* payload = nullptr;
+    size_t plen = 0;
+    if (t == T_INT || t == T_FLOAT) {
+      plen = 8;
+      if (!c.take(8, &payload)) return SGIC_C2DF_TRUNCATED;
+    } else if (t == T_BOOL) {
+      plen = 1;
+      if (!c.take(1, &payload)) return SGIC_C2DF_TRUNCATED;
+    } else if (t == T_NONE) {
+      plen = 0;
+    } else {
+      uint32_t L;
+      if (!c.u32(&L) || !c.take(L, &payload)) return SGIC_C2DF_TRUNCATED;
+      plen = L;
+      if (t > T_BOOL) return SGIC_C2DF_BAD_TYPE;
+    }
+    const bool is_stream = (klen == 11 && std::memcmp(key, "clip_stream", 11) == 0);
+    const bool is_meta = (klen == 9 && std::memcmp(key, "clip_meta", 9) == 0);
+    if (!is_stream && !is_meta) continue;
+    // BYTES / STR / JSON payloads carry a second u32 length in front of the data
+    const uint8_t* inner = payload;
+    size_t inner_len = plen;
+    if (t == T_BYTES || t == T_STR || t == T_JSON) {
+      if (plen < 4) return SGIC_C2DF_TRUNCATED;
+      const uint32_t L = static_cast<uint32_t>(payload[0]) | (static_cast<uint32_t>(payload[1]) << 8) |
+                         (static_cast<uint32_t>(payload[2]) << 16) | (static_cast<uint32_t>(payload[3]) << 24);
+      inner = payload + 4;
+      inner_len = (L <= plen - 4) ? L : plen - 4;  // Python slicing clamps
+    }
+    if (is_stream) {
+      f->has_stream = true;
+      f->stream_is_bytes = (t == T_BYTES);
+      f->stream = inner;
+      f->stream_len = inner_len;
+    } else {
+      f->has_meta = true;
+      f->meta_type = t;
+      f->meta = inner;
+      f->meta_len = inner_len;
+    }
+  }
+  return SGIC_C2DF_OK;
+}
+
+int parse_one(const ZstdApi& z, void* dctx, const uint8_t* data, size_t n, int want_dim, uint8_t* out_row,
+              int32_t* dim_out, std::vector<uint8_t>& scratch) {
+  *dim_out = 0;
+  Found f;
+  int st = walk_one(data, n, &f);
+  if (st != SGIC_C2DF_OK) return st;
+  if (!f.has_stream || !f.has_meta) return SGIC_C2DF_NO_CLIP;
+  long long dim = 0;
+  if (f.meta_type == T_JSON) {
+    if (!clip_meta_dim(reinterpret_cast<const char*>(f.meta), f.meta_len, &dim)) return SGIC_C2DF_BAD_DIM;
+  } else if (f.meta_type == T_NONE) {
+    dim = 0;  // None or {} -> dim 0
+  } else {
+    return SGIC_C2DF_BAD_DIM;  // no .get on bytes / str / int / ndarray
+  }
+  if (dim <= 0 || dim > (1ll << 24)) return SGIC_C2DF_BAD_DIM;
+  *dim_out = static_cast<int32_t>(dim);
+  if (!f.stream_is_bytes) return SGIC_C2DF_ZSTD;  // decompress(str) raises
+  // python-zstandard's one-shot decompress needs the content size in the frame header
+  const unsigned long long fcs = z.getFrameContentSize(f.stream, f.stream_len);
+  if (fcs == ~0ull || fcs == ~0ull - 1) return SGIC_C2DF_ZSTD;
+  if (fcs > (1ull << 26)) return SGIC_C2DF_ZSTD;
+  if (static_cast<long long>(fcs) == dim && dim == want_dim) {
+    const size_t r = z.decompressDCtx(dctx, out_row, static_cast<size_t>(dim), f.stream, f.stream_len);
+    if (z.isError(r)) return SGIC_C2DF_ZSTD;
+    if (static_cast<long long>(r) != dim) return SGIC_C2DF_DIM_MISMATCH;
+    return SGIC_C2DF_OK;
+  }
+  // mismatching sizes: still decode (to report a corrupt frame as such), never into out_row
+  scratch.resize(static_cast<size_t>(fcs) + 1);
+  const size_t r = z.decompressDCtx(dctx, scratch.data(), scratch.size(), f.stream, f.stream_len);
+  if (z.isError(r)) return SGIC_C2DF_ZSTD;
+  if (static_cast<long long>(r) != dim) return SGIC_C2DF_DIM_MISMATCH;
+  return SGIC_C2DF_WRONG_D;
+}
+
+}  // namespace
+
+int c2df_parse_batch(const uint8_t* blob, const int64_t* offsets, int64_t n, int dim, uint8_t* out_u8,
+                     int32_t* status_out, int32_t* dim_out, int n_threads) {
+  const ZstdApi& z = zstd_api();
+  if (!z.ok) {
+    set_error("libzstd.so.1 could not be loaded (dlopen) — required for clip_stream decoding");
+    return 1;
+  }
+  if (n < 0 || dim <= 0) {
+    set_error("c2df_parse: bad arguments");
+    return 1;
+  }
+  if (n_threads <= 0) n_threads = static_cast<int>(std::thread::hardware_concurrency());
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 64) n_threads = 64;
+  if (static_cast<int64_t>(n_threads) > n) n_threads = static_cast<int>(n > 0 ? n : 1);
+  std::atomic<int64_t> next{0};
+  constexpr int64_t kGrain = 256;
+  auto work = [&]() {
+    void* dctx = z.createDCtx();
+    std::vector<uint8_t> scratch;
+    for (;;) {
+      const int64_t b = next.fetch_add(kGrain);
+      if (b >= n) break;
+      const int64_t e = (b + kGrain < n) ? b + kGrain : n;
+      for (int64_t i = b; i < e; ++i) {
+        const int64_t o0 = offsets[i], o1 = offsets[i + 1];
+        int32_t dd = 0;
+        int st;
+        if (o1 < o0) {
+          st = SGIC_C2DF_TRUNCATED;
+        } else {
+          st = parse_one(z, dctx, blob + o0, static_cast<size_t>(o1 - o0), dim,
+                         out_u8 + static_cast<size_t>(i) * dim, &dd, scratch);
+        }
+        status_out[i] = st;
+        if (dim_out) dim_out[i] = dd;
+      }
+    }
+    z.freeDCtx(dctx);
+  };
+  if (n_threads == 1) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    th.reserve(n_threads);
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work);
+    for (auto& t : th) t.join();
+  }
+  return 0;
+}
+
+}  // namespace sgic

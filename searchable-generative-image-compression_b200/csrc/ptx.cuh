@@ -1,0 +1,164 @@
+// Thin inline-PTX wrappers for sm_100a: mbarrier, bulk async copy (TMA), tcgen05.
+// Hand-written; bit layouts cross-checked against the PTX ISA 8.8 text and the
+// CuTe headers vendored in the image (cute/arch/{copy_sm90_desc,mma_sm100_desc}.hpp).
+#pragma once
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+namespace sgic {
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ---------------------------------------------------------------- L2 policies
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+// ---------------------------------------------------------------- TMA (bulk async copy)
+// 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+// 2-D tiled tensor-map copy global -> shared (SASS: UTMALDG).
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int32_t c0, int32_t c1, uint64_t* bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// ---------------------------------------------------------------- mixed-precision FMA (sm_100+)
+// d = a*b + c with a,b 16-bit and c,d fp32, single rounding (SASS: FHFMA).  The
+// product of two fp16/bf16 values is exact in fp32, so this equals an fp32 FMA on
+// the up-cast operands.
+template <typename T>
+__device__ __forceinline__ float fma_mixed_lo(uint32_t a2, uint32_t b2, float c);
+template <typename T>
+__device__ __forceinline__ float fma_mixed_hi(uint32_t a2, uint32_t b2, float c);
+
+template <>
+__device__ __forceinline__ float fma_mixed_lo<__half>(uint32_t a2, uint32_t b2, float c) {
+  float d;
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\t"
+      "mov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
+      "fma.rn.f32.f16 %0, al, bl, %3;\n\t}"
+      : "=f"(d)
+      : "r"(a2), "r"(b2), "f"(c));
+  return d;
+}
+template <>
+__device__ __forceinline__ float fma_mixed_hi<__half>(uint32_t a2, uint32_t b2, float c) {
+  float d;
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\t"
+      "mov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
+      "fma.rn.f32.f16 %0, ah, bh, %3;\n\t}"
+      : "=f"(d)
+      : "r"(a2), "r"(b2), "f"(c));
+  return d;
+}
+template <>
+__device__ __forceinline__ float fma_mixed_lo<__nv_bfloat16>(uint32_t a2, uint32_t b2, float c) {
+  float d;
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\t"
+      "mov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
+      "fma.rn.f32.bf16 %0, al, bl, %3;\n\t}"
+      : "=f"(d)
+      : "r"(a2), "r"(b2), "f"(c));
+  return d;
+}
+template <>
+__device__ __forceinline__ float fma_mixed_hi<__nv_bfloat16>(uint32_t a2, uint32_t b2, float c) {
+  float d;
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\t"
+      "mov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
+      "fma.rn.f32.bf16 %0, ah, bh, %3;\n\t}"
+      : "=f"(d)
+      : "r"(a2), "r"(b2), "f"(c));
+  return d;
+}
+
+}  // namespace ptx
+
+// ---------------------------------------------------------------- candidate keys
+// A candidate (score, local row id) is one 64-bit key whose unsigned order is
+// (score descending-is-larger, id ascending-is-larger):  hi = order-preserving map
+// of the fp32 score, lo = ~id.  key 0 is the "empty slot" sentinel (it would decode
+// to a NaN score, which no finite dot product produces).
+__host__ __device__ __forceinline__ uint32_t score_to_ord(float s) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(s);
+#else
+  union { float f; uint32_t u; } c; c.f = s; uint32_t u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord_to_score(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float s, uint32_t id) {
+  return (static_cast<uint64_t>(score_to_ord(s)) << 32) | static_cast<uint64_t>(~id);
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t k) { return ord_to_score(static_cast<uint32_t>(k >> 32)); }
+__host__ __device__ __forceinline__ uint32_t key_id(uint64_t k) { return ~static_cast<uint32_t>(k); }
+
+}  // namespace sgic

@@ -1,0 +1,221 @@
+// K3 — streaming score + top-k for 1..4 queries (replaces FAISS
+// exhaustive_inner_product_seq = fvec_inner_product + heap behind src/search.py:115).
+//
+// HBM-bound: the database is read exactly once per call (algorithmic bytes = N*d*2).
+// One persistent CTA per SM.  A producer thread streams contiguous row tiles into a
+// ring of shared-memory stages with 1-D bulk async copies (TMA, SASS UBLKCP) that
+// complete on mbarriers; 8 consumer warps read the staged rows with 128-bit LDS, form
+// the dot products with mixed-precision FMAs (fp16/bf16 x fp16/bf16 -> fp32, SASS
+// FHFMA; products exact, fp32 accumulation), reduce RB rows x NQ queries at once with a
+// transposing butterfly, and keep a warp-private sorted top-k in shared memory guarded
+// by a register threshold.  No score matrix is materialised.  At the end the CTA merges
+// its warps' lists (bitonic sort) and writes k keys per query; merge_keys_kernel
+// finishes the job.
+#pragma once
+#include "topk_common.cuh"
+
+namespace sgic {
+
+constexpr int kScanConsumerWarps = 8;
+constexpr int kScanThreads = (kScanConsumerWarps + 1) * 32;  // + producer warp
+constexpr int kScanMaxStages = 8;
+
+struct ScanSmallParams {
+  const void* db;        // [n_rows][d] 16-bit, row-major
+  const float* q;        // [nq][d] fp32 (rounded to the db dtype in-kernel)
+  uint64_t* partial;     // [NQ][gridDim.x][k] keys
+  uint32_t n_rows;
+  uint32_t d;            // multiple of 8
+  uint32_t nq;           // valid queries (<= NQ)
+  uint32_t k;
+  uint32_t kp;           // list stride (power of two >= k)
+  uint32_t n_tiles;
+  uint32_t n_stages;
+  uint32_t stage_bytes;  // R * d * 2 rounded up to 128
+  uint32_t evict_first;  // L2 policy for the database stream
+};
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <typename T, int NQ, int CPL, int RB>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanSmallParams p) {
+  constexpr int W = kScanConsumerWarps;
+  constexpr int R = W * RB;       // rows per tile
+  constexpr int V = NQ * RB;      // partial sums per lane before the butterfly
+  static_assert(V <= 32 && (V & (V - 1)) == 0, "NQ*RB must be a power of two <= 32");
+  constexpr int L = (V == 1) ? 0 : (V == 2) ? 1 : (V == 4) ? 2 : (V == 8) ? 3 : (V == 16) ? 4 : 5;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* stage_base = smem;
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.n_stages) * p.stage_bytes);
+  uint64_t* full_bar = lists + static_cast<size_t>(NQ) * W * p.kp;
+  uint64_t* empty_bar = full_bar + kScanMaxStages;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t row_bytes = p.d * 2u;
+  const uint32_t n_chunks = p.d >> 3;  // 16-byte chunks per row
+
+  for (uint32_t i = tid; i < static_cast<uint32_t>(NQ) * W * p.kp; i += kScanThreads) lists[i] = 0ull;
+  if (tid == 0) {
+    for (uint32_t s = 0; s < p.n_stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], W);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == W) {
+    // ------------------------------------------------------------ producer
+    if (lane == 0) {
+      const uint64_t pol = p.evict_first ? ptx::policy_evict_first() : ptx::policy_evict_last();
+      const uint8_t* db = static_cast<const uint8_t*>(p.db);
+      uint32_t it = 0;
+      for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it % p.n_stages, use = it / p.n_stages;
+        if (use > 0) ptx::mbar_wait(&empty_bar[s], (use - 1) & 1);
+        const uint32_t row0 = tile * R;
+        const uint32_t rows = min(static_cast<uint32_t>(R), p.n_rows - row0);
+        const uint32_t bytes = rows * row_bytes;
+        ptx::mbar_expect_tx(&full_bar[s], bytes);
+        ptx::bulk_g2s(stage_base + static_cast<size_t>(s) * p.stage_bytes,
+                      db + static_cast<size_t>(row0) * row_bytes, bytes, &full_bar[s], pol);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ consumers
+    // query fragments, rounded to the storage dtype (same rounding the dense path applies)
+    uint32_t qf[NQ][CPL][4];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const uint32_t chunk = lane + 32 * c;
+        if (qi < static_cast<int>(p.nq) && chunk < n_chunks) {
+          const float4* src = reinterpret_cast<const float4*>(p.q + static_cast<size_t>(qi) * p.d + chunk * 8);
+          const float4 a = __ldg(src), b = __ldg(src + 1);
+          qf[qi][c][0] = pack2<T>(a.x, a.y);
+          qf[qi][c][1] = pack2<T>(a.z, a.w);
+          qf[qi][c][2] = pack2<T>(b.x, b.y);
+          qf[qi][c][3] = pack2<T>(b.z, b.w);
+        } else {
+          qf[qi][c][0] = qf[qi][c][1] = qf[qi][c][2] = qf[qi][c][3] = 0u;
+        }
+      }
+    }
+    float thr[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) thr[qi] = -INFINITY;
+
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t s = it % p.n_stages, use = it / p.n_stages;
+      ptx::mbar_wait(&full_bar[s], use & 1);
+      const uint32_t row0 = tile * R;
+      const uint32_t rows = min(static_cast<uint32_t>(R), p.n_rows - row0);
+      const uint8_t* sb = stage_base + static_cast<size_t>(s) * p.stage_bytes;
+
+      uint4 v[RB][CPL];
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        const uint32_t r = warp * RB + j;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          const uint32_t chunk = lane + 32 * c;
+          if (r < rows && chunk < n_chunks)
+            v[j][c] = *reinterpret_cast<const uint4*>(sb + r * row_bytes + chunk * 16);
+          else
+            v[j][c] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      float acc[V];
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi) {
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+          float a = 0.f;
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) {
+            a = ptx::fma_mixed_lo<T>(v[j][c].x, qf[qi][c][0], a);
+            a = ptx::fma_mixed_hi<T>(v[j][c].x, qf[qi][c][0], a);
+            a = ptx::fma_mixed_lo<T>(v[j][c].y, qf[qi][c][1], a);
+            a = ptx::fma_mixed_hi<T>(v[j][c].y, qf[qi][c][1], a);
+            a = ptx::fma_mixed_lo<T>(v[j][c].z, qf[qi][c][2], a);
+            a = ptx::fma_mixed_hi<T>(v[j][c].z, qf[qi][c][2], a);
+            a = ptx::fma_mixed_lo<T>(v[j][c].w, qf[qi][c][3], a);
+            a = ptx::fma_mixed_hi<T>(v[j][c].w, qf[qi][c][3], a);
+          }
+          acc[qi * RB + j] = a;
+        }
+      }
+      // the stage's bytes are in registers now: hand the slot back to the producer
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty_bar[s]);
+
+      // transposing butterfly: V values/lane -> 1 value/lane, then finish the all-reduce
+#pragma unroll
+      for (int step = 0; step < L; ++step) {
+        const int off = 16 >> step;
+        const int half = V >> (step + 1);
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const float keep = up ? acc[i + half] : acc[i];
+          const float send = up ? acc[i] : acc[i + half];
+          acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      float val = acc[0];
+#pragma unroll
+      for (int off = 16 >> L; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
+
+      // lane holds the score of element e = lane >> (5-L):  query e / RB, row e % RB
+      const int e = lane >> (5 - L);
+      const int qi_me = e / RB, j_me = e % RB;
+      const bool rep = (lane & ((1 << (5 - L)) - 1)) == 0;
+      float t = thr[0];
+#pragma unroll
+      for (int qi = 1; qi < NQ; ++qi)
+        if (qi_me == qi) t = thr[qi];
+      const bool cand = rep && (warp * RB + j_me < rows) && (qi_me < static_cast<int>(p.nq)) && (val > t);
+      uint32_t m = __ballot_sync(0xffffffffu, cand);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const float sv = __shfl_sync(0xffffffffu, val, src);
+        const int se = src >> (5 - L);
+        const int sq = se / RB, sj = se % RB;
+        const uint32_t id = row0 + warp * RB + sj;
+        uint64_t* Lq = lists + (static_cast<size_t>(sq) * W + warp) * p.kp;
+        const uint64_t kth = warp_list_insert(Lq, static_cast<int>(p.k), make_key(sv, id), lane);
+        const float nt = (kth == 0ull) ? -INFINITY : key_score(kth);
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi)
+          if (sq == qi) thr[qi] = nt;
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- CTA merge of the W warp lists
+  __syncthreads();
+  const uint32_t m = W * p.kp;  // power of two
+  for (uint32_t qi = 0; qi < p.nq; ++qi) {
+    uint64_t* Lq = lists + static_cast<size_t>(qi) * m;
+    block_bitonic_sort_desc(Lq, m);
+    uint64_t* dst = p.partial + (static_cast<size_t>(qi) * gridDim.x + blockIdx.x) * p.k;
+    for (uint32_t i = tid; i < p.k; i += kScanThreads) dst[i] = Lq[i];
+  }
+}
+
+}  // namespace sgic

@@ -1,0 +1,852 @@
+// C-ABI implementation (include/sgic.h): index object, HBM database, ingest, search dispatch,
+// IxFI (de)serialisation.  Host logic only; the kernels live in the .cuh files next to this.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sgic.h"
+#include "ingest.cuh"
+#include "scan_small.cuh"
+#include "topk_common.cuh"
+
+namespace sgic {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+int c2df_parse_batch(const uint8_t* blob, const int64_t* offsets, int64_t n, int dim, uint8_t* out_u8,
+                     int32_t* status_out, int32_t* dim_out, int n_threads);
+
+#define SGIC_CUDA(call)                                                                         \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      set_error(std::string(#call) + " failed: " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
+                std::to_string(__LINE__) + ")");                                                \
+      return 2;                                                                                 \
+    }                                                                                           \
+  } while (0)
+
+#define SGIC_REQUIRE(cond, msg) \
+  do {                          \
+    if (!(cond)) {              \
+      set_error(msg);           \
+      return 1;                 \
+    }                           \
+  } while (0)
+
+constexpr size_t kSmemBudget = 232448;  // 227 KB opt-in maximum per CTA on sm_100
+constexpr int kMaxD = 2048;
+constexpr int64_t kMaxK = 1024;
+constexpr size_t kStageChunkBytes = 32u << 20;  // host->device staging granularity for add()
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace sgic
+
+struct sgic_index {
+  int d = 0, dtype = SGIC_F16, device = 0, flags = 0;
+  int64_t ntotal = 0, capacity = 0;
+  void* db = nullptr;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  std::mutex mu;
+  // staging (double-buffered) for add()
+  void* pin[2] = {nullptr, nullptr};
+  void* dstage[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  // search workspaces
+  void* ws = nullptr;  // partial keys
+  size_t ws_bytes = 0;
+  void* qdev = nullptr;  // queries / outputs for the host-buffer search
+  size_t qdev_bytes = 0;
+  void* odev = nullptr;
+  size_t odev_bytes = 0;
+  void* opin = nullptr;
+  size_t opin_bytes = 0;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  // retained fp32 rows (SGIC_RETAIN_F32)
+  std::vector<float> retained;
+  bool retain_ok = false;
+  // options / stats
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0;
+  int64_t stat_launches = 0, stat_last_search_us = 0, stat_last_grid = 0, stat_last_stages = 0;
+};
+
+namespace sgic {
+
+static size_t elt_rows_bytes(const sgic_index* h, int64_t rows) { return static_cast<size_t>(rows) * h->d * 2; }
+
+static int ensure_capacity(sgic_index* h, int64_t rows, cudaStream_t st) {
+  if (rows <= h->capacity) return 0;
+  int64_t cap = std::max<int64_t>(rows, std::max<int64_t>(1024, h->capacity + h->capacity / 2));
+  void* nb = nullptr;
+  cudaError_t e = cudaMalloc(&nb, elt_rows_bytes(h, cap));
+  if (e != cudaSuccess && cap > rows) {
+    cudaGetLastError();
+    cap = rows;
+    e = cudaMalloc(&nb, elt_rows_bytes(h, cap));
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaMalloc of " + std::to_string(elt_rows_bytes(h, cap)) + " bytes for the database failed: " +
+              cudaGetErrorString(e));
+    return 2;
+  }
+  if (h->ntotal > 0) {
+    SGIC_CUDA(cudaMemcpyAsync(nb, h->db, elt_rows_bytes(h, h->ntotal), cudaMemcpyDeviceToDevice, st));
+    SGIC_CUDA(cudaStreamSynchronize(st));
+  }
+  if (h->db) SGIC_CUDA(cudaFree(h->db));
+  h->db = nb;
+  h->capacity = cap;
+  return 0;
+}
+
+static int ensure_buf(void** p, size_t* cur, size_t need, bool pinned) {
+  if (need <= *cur) return 0;
+  if (*p) {
+    if (pinned) SGIC_CUDA(cudaFreeHost(*p));
+    else SGIC_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *cur = 0;
+  }
+  need = (need + 4095) & ~static_cast<size_t>(4095);
+  if (pinned) SGIC_CUDA(cudaMallocHost(p, need));
+  else SGIC_CUDA(cudaMalloc(p, need));
+  *cur = need;
+  return 0;
+}
+
+static int ensure_staging(sgic_index* h) {
+  for (int i = 0; i < 2; ++i) {
+    if (!h->pin[i]) SGIC_CUDA(cudaMallocHost(&h->pin[i], kStageChunkBytes));
+    if (!h->dstage[i]) SGIC_CUDA(cudaMalloc(&h->dstage[i], kStageChunkBytes));
+    if (!h->ev[i]) SGIC_CUDA(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+static unsigned grid_for(size_t n_items, int threads, int sm_count) {
+  size_t blocks = (n_items + threads - 1) / threads;
+  size_t cap = static_cast<size_t>(sm_count) * 8;
+  return static_cast<unsigned>(std::max<size_t>(1, std::min(blocks, cap)));
+}
+
+// ---- K2 / K1 launches -------------------------------------------------------------------
+static int launch_pack_f32(sgic_index* h, const float* dev_src, int64_t row0, int64_t n, cudaStream_t st) {
+  const size_t n8 = static_cast<size_t>(n) * h->d / 8;
+  void* dst = static_cast<uint8_t*>(h->db) + elt_rows_bytes(h, row0);
+  const unsigned g = grid_for(n8, 256, h->sm_count);
+  if (h->dtype == SGIC_F16) pack_f32_kernel<__half><<<g, 256, 0, st>>>(dev_src, dst, n8);
+  else pack_f32_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(dev_src, dst, n8);
+  h->stat_launches++;
+  SGIC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_dequant_u8(sgic_index* h, const uint8_t* dev_src, int64_t row0, int64_t n, cudaStream_t st) {
+  void* dst = static_cast<uint8_t*>(h->db) + elt_rows_bytes(h, row0);
+  const unsigned g = grid_for(static_cast<size_t>(n) * 32, 256, h->sm_count);
+  if (h->dtype == SGIC_F16)
+    dequant_u8_kernel<__half><<<g, 256, 0, st>>>(dev_src, dst, static_cast<uint32_t>(n), static_cast<uint32_t>(h->d));
+  else
+    dequant_u8_kernel<__nv_bfloat16>
+        <<<g, 256, 0, st>>>(dev_src, dst, static_cast<uint32_t>(n), static_cast<uint32_t>(h->d));
+  h->stat_launches++;
+  SGIC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Streams `n` host rows of `row_bytes` each through the pinned/device double buffer and
+// calls `consume(dev_ptr, first_row_of_chunk, rows)` for each chunk.
+template <typename F>
+static int stream_rows_h2d(sgic_index* h, const uint8_t* host, int64_t n, size_t row_bytes, F consume) {
+  int rc = ensure_staging(h);
+  if (rc) return rc;
+  const int64_t rows_per_chunk = std::max<int64_t>(1, static_cast<int64_t>(kStageChunkBytes / row_bytes));
+  SGIC_REQUIRE(row_bytes <= kStageChunkBytes, "row too large for the staging buffer");
+  int64_t done = 0;
+  int b = 0;
+  while (done < n) {
+    const int64_t rows = std::min(rows_per_chunk, n - done);
+    const size_t bytes = static_cast<size_t>(rows) * row_bytes;
+    SGIC_CUDA(cudaEventSynchronize(h->ev[b]));  // previous use of this buffer pair has drained
+    std::memcpy(h->pin[b], host + static_cast<size_t>(done) * row_bytes, bytes);
+    SGIC_CUDA(cudaMemcpyAsync(h->dstage[b], h->pin[b], bytes, cudaMemcpyHostToDevice, h->stream));
+    rc = consume(h->dstage[b], done, rows);
+    if (rc) return rc;
+    SGIC_CUDA(cudaEventRecord(h->ev[b], h->stream));
+    done += rows;
+    b ^= 1;
+  }
+  SGIC_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ---- K3 dispatch -------------------------------------------------------------------------
+struct ScanCfg {
+  int cpl, rb;
+};
+static ScanCfg scan_cfg_for_d(int d) {
+  if (d <= 256) return {1, 8};
+  if (d <= 512) return {2, 4};
+  if (d <= 768) return {3, 4};
+  if (d <= 1024) return {4, 2};
+  return {8, 1};
+}
+
+template <typename T, int NQ, int CPL, int RB>
+static cudaError_t launch_scan_inst(const ScanSmallParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+  auto kern = scan_small_kernel<T, NQ, CPL, RB>;
+  static size_t configured[64] = {0};  // per device: the attribute lives in the device's context
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured[dev & 63] < smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    configured[dev & 63] = smem;
+  }
+  kern<<<grid, kScanThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <typename T, int NQ>
+static cudaError_t launch_scan_nq(const ScanSmallParams& p, int cpl, unsigned grid, size_t smem, cudaStream_t st) {
+  switch (cpl) {
+    case 1: return launch_scan_inst<T, NQ, 1, 8>(p, grid, smem, st);
+    case 2: return launch_scan_inst<T, NQ, 2, 4>(p, grid, smem, st);
+    case 3: return launch_scan_inst<T, NQ, 3, 4>(p, grid, smem, st);
+    case 4: return launch_scan_inst<T, NQ, 4, 2>(p, grid, smem, st);
+    default: return launch_scan_inst<T, NQ, 8, 1>(p, grid, smem, st);
+  }
+}
+
+template <typename T>
+static cudaError_t launch_scan_t(const ScanSmallParams& p, int NQ, int cpl, unsigned grid, size_t smem,
+                                 cudaStream_t st) {
+  switch (NQ) {
+    case 1: return launch_scan_nq<T, 1>(p, cpl, grid, smem, st);
+    case 2: return launch_scan_nq<T, 2>(p, cpl, grid, smem, st);
+    default: return launch_scan_nq<T, 4>(p, cpl, grid, smem, st);
+  }
+}
+
+static int launch_merge_keys(sgic_index* h, const uint64_t* partial, uint32_t nq, uint32_t n_lists, uint32_t k,
+                             float* D, int64_t* I, int64_t id_base, cudaStream_t st) {
+  MergeKeysParams mp;
+  mp.partial = partial;
+  mp.n_lists = n_lists;
+  mp.k = k;
+  const uint32_t kp = next_pow2_u32(k);
+  uint32_t chunk = std::max<uint32_t>(2 * kp, std::min<uint32_t>(16384, next_pow2_u32(n_lists * k)));
+  chunk = std::max<uint32_t>(chunk, 64);
+  mp.chunk = chunk;
+  mp.D = D;
+  mp.I = reinterpret_cast<long long*>(I);
+  mp.id_base = id_base;
+  const size_t smem = static_cast<size_t>(chunk) * 8;
+  if (smem > 48 * 1024)
+    SGIC_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+  const int threads = static_cast<int>(std::min<uint32_t>(1024, std::max<uint32_t>(32, chunk / 2)));
+  merge_keys_kernel<<<nq, threads, smem, st>>>(mp);
+  h->stat_launches++;
+  SGIC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Searches `nq` device-resident fp32 queries; results to device buffers.
+static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
+                           int64_t id_base, cudaStream_t st) {
+  SGIC_REQUIRE(k >= 1, "k must be >= 1");
+  SGIC_REQUIRE(k <= kMaxK, "k > 1024 is not supported by this build");
+  SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
+  if (nq == 0) return 0;
+  SGIC_REQUIRE(h->ntotal < (1ll << 32) - 1, "more than 2^32-2 rows in one shard");
+  const ScanCfg cfg = scan_cfg_for_d(h->d);
+  const uint32_t kp = std::max<uint32_t>(2, next_pow2_u32(static_cast<uint32_t>(k)));
+  int NQ = (nq == 1) ? 1 : (nq == 2) ? 2 : 4;
+  while (NQ > 1 && static_cast<uint32_t>(NQ) * kp > 1024) NQ >>= 1;
+
+  const uint32_t R = kScanConsumerWarps * cfg.rb;
+  const uint32_t stage_bytes = ((R * h->d * 2u) + 127u) & ~127u;
+  const size_t list_bytes = static_cast<size_t>(NQ) * kScanConsumerWarps * kp * 8;
+  const size_t bar_bytes = 2 * kScanMaxStages * 8;
+  SGIC_REQUIRE(list_bytes + bar_bytes + 2 * stage_bytes <= kSmemBudget, "k too large for shared memory");
+  uint32_t stages = static_cast<uint32_t>((kSmemBudget - list_bytes - bar_bytes) / stage_bytes);
+  stages = std::min<uint32_t>(stages, kScanMaxStages);
+  if (h->opt_stages > 0) stages = std::min<uint32_t>(stages, static_cast<uint32_t>(h->opt_stages));
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + list_bytes + bar_bytes;
+
+  const uint32_t n_rows = static_cast<uint32_t>(h->ntotal);
+  const uint32_t n_tiles = (n_rows + R - 1) / R;
+  uint32_t grid = static_cast<uint32_t>(h->opt_grid > 0 ? h->opt_grid : h->sm_count);
+  grid = std::max<uint32_t>(1, std::min(grid, std::max<uint32_t>(n_tiles, 1)));
+  h->stat_last_grid = grid;
+  h->stat_last_stages = stages;
+
+  const size_t ws_need = static_cast<size_t>(NQ) * grid * static_cast<size_t>(k) * 8;
+  if (ws_need > h->ws_bytes) {
+    SGIC_CUDA(cudaStreamSynchronize(st));
+    int rc = ensure_buf(&h->ws, &h->ws_bytes, ws_need, false);
+    if (rc) return rc;
+  }
+
+  if (h->opt_timing) SGIC_CUDA(cudaEventRecord(h->t0, st));
+  for (int64_t q0 = 0; q0 < nq; q0 += NQ) {
+    const uint32_t nq_here = static_cast<uint32_t>(std::min<int64_t>(NQ, nq - q0));
+    ScanSmallParams p;
+    p.db = h->db;
+    p.q = dev_q + static_cast<size_t>(q0) * h->d;
+    p.partial = static_cast<uint64_t*>(h->ws);
+    p.n_rows = n_rows;
+    p.d = static_cast<uint32_t>(h->d);
+    p.nq = nq_here;
+    p.k = static_cast<uint32_t>(k);
+    p.kp = kp;
+    p.n_tiles = n_tiles;
+    p.n_stages = stages;
+    p.stage_bytes = stage_bytes;
+    p.evict_first = h->opt_evict_first ? 1u : 0u;
+    cudaError_t e;
+    if (n_rows > 0) {
+      if (h->dtype == SGIC_F16) e = launch_scan_t<__half>(p, NQ, cfg.cpl, grid, smem, st);
+      else e = launch_scan_t<__nv_bfloat16>(p, NQ, cfg.cpl, grid, smem, st);
+      h->stat_launches++;
+      if (e != cudaSuccess) {
+        set_error(std::string("scan_small launch failed: ") + cudaGetErrorString(e));
+        return 2;
+      }
+    } else {
+      SGIC_CUDA(cudaMemsetAsync(h->ws, 0, static_cast<size_t>(NQ) * grid * k * 8, st));
+    }
+    int rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nq_here, grid, static_cast<uint32_t>(k),
+                               dev_D + static_cast<size_t>(q0) * k, dev_I + static_cast<size_t>(q0) * k, id_base, st);
+    if (rc) return rc;
+  }
+  if (h->opt_timing) {
+    SGIC_CUDA(cudaEventRecord(h->t1, st));
+    SGIC_CUDA(cudaEventSynchronize(h->t1));
+    float ms = 0.f;
+    SGIC_CUDA(cudaEventElapsedTime(&ms, h->t0, h->t1));
+    h->stat_last_search_us = static_cast<int64_t>(ms * 1000.0f);
+  }
+  return 0;
+}
+
+// ---- IxFI ---------------------------------------------------------------------------------
+#pragma pack(push, 1)
+struct IxfiHeader {
+  char fourcc[4];
+  int32_t d;
+  int64_t ntotal;
+  int64_t dummy0;
+  int64_t dummy1;
+  uint8_t is_trained;
+  int32_t metric_type;
+  uint64_t count;
+};
+#pragma pack(pop)
+static_assert(sizeof(IxfiHeader) == 45, "IxFI header is 45 bytes (SURVEY.md §8a F3)");
+
+}  // namespace sgic
+
+using namespace sgic;
+
+extern "C" {
+
+const char* sgic_last_error(void) { return g_err.c_str(); }
+int sgic_version(void) { return 100; }
+
+int sgic_index_create(int d, int dtype, int device, int64_t capacity_rows, int flags, sgic_index** out) {
+  SGIC_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  SGIC_REQUIRE(d > 0 && d % 8 == 0 && d <= kMaxD, "d must be a positive multiple of 8 and <= 2048");
+  SGIC_REQUIRE(dtype == SGIC_F16 || dtype == SGIC_BF16, "dtype must be SGIC_F16 or SGIC_BF16");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    set_error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+              "); this library has no CPU fallback");
+    return 2;
+  }
+  SGIC_REQUIRE(device >= 0 && device < n_dev, "device ordinal out of range");
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  SGIC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+              "; this library is built for sm_100a (B200) only");
+    return 2;
+  }
+  sgic_index* h = new sgic_index();
+  h->d = d;
+  h->dtype = dtype;
+  h->device = device;
+  h->flags = flags;
+  h->sm_count = prop.multiProcessorCount;
+  h->retain_ok = (flags & SGIC_RETAIN_F32) != 0;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->t0) != cudaSuccess || cudaEventCreate(&h->t1) != cudaSuccess) {
+    set_error("stream/event creation failed");
+    delete h;
+    return 2;
+  }
+  if (capacity_rows > 0) {
+    int rc = ensure_capacity(h, capacity_rows, h->stream);
+    if (rc) {
+      sgic_index_destroy(h);
+      return rc;
+    }
+  }
+  *out = h;
+  return 0;
+}
+
+int sgic_index_destroy(sgic_index* h) {
+  if (!h) return 0;
+  DeviceGuard g(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int i = 0; i < 2; ++i) {
+    if (h->pin[i]) cudaFreeHost(h->pin[i]);
+    if (h->dstage[i]) cudaFree(h->dstage[i]);
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  }
+  if (h->ws) cudaFree(h->ws);
+  if (h->qdev) cudaFree(h->qdev);
+  if (h->odev) cudaFree(h->odev);
+  if (h->opin) cudaFreeHost(h->opin);
+  if (h->db) cudaFree(h->db);
+  if (h->t0) cudaEventDestroy(h->t0);
+  if (h->t1) cudaEventDestroy(h->t1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int64_t sgic_index_ntotal(const sgic_index* h) { return h ? h->ntotal : -1; }
+int sgic_index_d(const sgic_index* h) { return h ? h->d : -1; }
+int sgic_index_dtype(const sgic_index* h) { return h ? h->dtype : -1; }
+int sgic_index_device(const sgic_index* h) { return h ? h->device : -1; }
+const void* sgic_index_data_dev(const sgic_index* h) { return h ? h->db : nullptr; }
+
+int sgic_index_reserve(sgic_index* h, int64_t rows) {
+  SGIC_REQUIRE(h != nullptr, "index is NULL");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  if (rows <= h->capacity) return 0;
+  // exact reservation: no geometric slack on an explicit request
+  void* nb = nullptr;
+  cudaError_t e = cudaMalloc(&nb, elt_rows_bytes(h, rows));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaMalloc of " + std::to_string(elt_rows_bytes(h, rows)) + " bytes failed: " + cudaGetErrorString(e));
+    return 2;
+  }
+  if (h->ntotal > 0) {
+    SGIC_CUDA(cudaMemcpyAsync(nb, h->db, elt_rows_bytes(h, h->ntotal), cudaMemcpyDeviceToDevice, h->stream));
+    SGIC_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  if (h->db) SGIC_CUDA(cudaFree(h->db));
+  h->db = nb;
+  h->capacity = rows;
+  return 0;
+}
+
+int sgic_index_reset(sgic_index* h) {
+  SGIC_REQUIRE(h != nullptr, "index is NULL");
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->ntotal = 0;
+  h->retained.clear();
+  h->retain_ok = (h->flags & SGIC_RETAIN_F32) != 0;
+  return 0;
+}
+
+int sgic_index_add_f32(sgic_index* h, int64_t n, const float* host_x) {
+  SGIC_REQUIRE(h != nullptr, "index is NULL");
+  SGIC_REQUIRE(n >= 0, "n must be >= 0");
+  if (n == 0) return 0;
+  SGIC_REQUIRE(host_x != nullptr, "x is NULL");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  int rc = ensure_capacity(h, h->ntotal + n, h->stream);
+  if (rc) return rc;
+  const int64_t base = h->ntotal;
+  rc = stream_rows_h2d(h, reinterpret_cast<const uint8_t*>(host_x), n, static_cast<size_t>(h->d) * 4,
+                       [&](void* dev, int64_t first, int64_t rows) {
+                         return launch_pack_f32(h, static_cast<const float*>(dev), base + first, rows, h->stream);
+                       });
+  if (rc) return rc;
+  if (h->retain_ok) {
+    try {
+      h->retained.insert(h->retained.end(), host_x, host_x + static_cast<size_t>(n) * h->d);
+    } catch (const std::bad_alloc&) {
+      h->retained.clear();
+      h->retained.shrink_to_fit();
+      h->retain_ok = false;
+    }
+  }
+  h->ntotal += n;
+  return 0;
+}
+
+int sgic_index_add_f32_dev(sgic_index* h, int64_t n, const float* dev_x, void* stream) {
+  SGIC_REQUIRE(h != nullptr, "index is NULL");
+  SGIC_REQUIRE(n >= 0, "n must be >= 0");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  int rc = ensure_capacity(h, h->ntotal + n, st);
+  if (rc) return rc;
+  rc = launch_pack_f32(h, dev_x, h->ntotal, n, st);
+  if (rc) return rc;
+  h->retain_ok = false;
+  h->retained.clear();
+  h->ntotal += n;
+  return 0;
+}
+
+int sgic_index_add_packed_dev(sgic_index* h, int64_t n, const void* dev_rows, void* stream) {
+  SGIC_REQUIRE(h != nullptr, "index is NULL");
+  SGIC_REQUIRE(n >= 0, "n must be >= 0");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  int rc = ensure_capacity(h, h->ntotal + n, st);
+  if (rc) return rc;
+  SGIC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(h->db) + elt_rows_bytes(h, h->ntotal), dev_rows,
+                            elt_rows_bytes(h, n), cudaMemcpyDeviceToDevice, st));
+  h->retain_ok = false;
+  h->retained.clear();
+  h->ntotal += n;
+  return 0;
+}
+
+int sgic_index_add_u8(sgic_index* h, int64_t n, const uint8_t* host_q) {
+  SGIC_REQUIRE(h != nullptr, "index is NULL");
+  SGIC_REQUIRE(n >= 0, "n must be >= 0");
+  if (n == 0) return 0;
+  SGIC_REQUIRE(host_q != nullptr, "q is NULL");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  int rc = ensure_capacity(h, h->ntotal + n, h->stream);
+  if (rc) return rc;
+  const int64_t base = h->ntotal;
+  rc = stream_rows_h2d(h, host_q, n, static_cast<size_t>(h->d), [&](void* dev, int64_t first, int64_t rows) {
+    return launch_dequant_u8(h, static_cast<const uint8_t*>(dev), base + first, rows, h->stream);
+  });
+  if (rc) return rc;
+  h->retain_ok = false;
+  h->retained.clear();
+  h->ntotal += n;
+  return 0;
+}
+
+int sgic_index_add_u8_dev(sgic_index* h, int64_t n, const uint8_t* dev_q, void* stream) {
+  SGIC_REQUIRE(h != nullptr, "index is NULL");
+  SGIC_REQUIRE(n >= 0, "n must be >= 0");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  int rc = ensure_capacity(h, h->ntotal + n, st);
+  if (rc) return rc;
+  rc = launch_dequant_u8(h, dev_q, h->ntotal, n, st);
+  if (rc) return rc;
+  h->retain_ok = false;
+  h->retained.clear();
+  h->ntotal += n;
+  return 0;
+}
+
+int sgic_c2df_parse(const uint8_t* blob, const int64_t* offsets, int64_t n, int dim, uint8_t* out_u8,
+                    int32_t* status_out, int32_t* dim_out, int n_threads) {
+  SGIC_REQUIRE(blob != nullptr || n == 0, "blob is NULL");
+  SGIC_REQUIRE(offsets != nullptr && status_out != nullptr && (out_u8 != nullptr || n == 0), "NULL argument");
+  return c2df_parse_batch(blob, offsets, n, dim, out_u8, status_out, dim_out, n_threads);
+}
+
+int sgic_index_add_c2df(sgic_index* h, const uint8_t* blob, const int64_t* offsets, int64_t n, int32_t* status_out,
+                        int64_t* n_added, int n_threads) {
+  SGIC_REQUIRE(h != nullptr, "index is NULL");
+  SGIC_REQUIRE(n >= 0 && offsets != nullptr && status_out != nullptr, "bad arguments");
+  if (n_added) *n_added = 0;
+  if (n == 0) return 0;
+  const size_t d = static_cast<size_t>(h->d);
+  // Decode in slabs so that host memory stays bounded and zstd overlaps the H2D + K1 of the
+  // previous slab (stream_rows_h2d is asynchronous until its final synchronise).
+  const int64_t slab = std::max<int64_t>(1, static_cast<int64_t>((256u << 20) / d));
+  std::vector<uint8_t> rows;
+  int64_t added = 0;
+  for (int64_t s0 = 0; s0 < n; s0 += slab) {
+    const int64_t cnt = std::min(slab, n - s0);
+    rows.resize(static_cast<size_t>(cnt) * d);
+    int rc = c2df_parse_batch(blob, offsets + s0, cnt, h->d, rows.data(), status_out + s0, nullptr, n_threads);
+    if (rc) return rc;
+    // compact the good rows in place (order preserved, as build.py's `keep` list does)
+    int64_t w = 0;
+    for (int64_t i = 0; i < cnt; ++i) {
+      if (status_out[s0 + i] != SGIC_C2DF_OK) continue;
+      if (w != i) std::memmove(rows.data() + static_cast<size_t>(w) * d, rows.data() + static_cast<size_t>(i) * d, d);
+      ++w;
+    }
+    if (w > 0) {
+      rc = sgic_index_add_u8(h, w, rows.data());
+      if (rc) return rc;
+      added += w;
+    }
+  }
+  if (n_added) *n_added = added;
+  return 0;
+}
+
+int sgic_index_search_dev(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
+                          int64_t id_base, void* stream) {
+  SGIC_REQUIRE(h != nullptr, "index is NULL");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  return search_dev_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st);
+}
+
+int sgic_index_search(sgic_index* h, int64_t nq, const float* host_q, int64_t k, float* host_D, int64_t* host_I) {
+  SGIC_REQUIRE(h != nullptr, "index is NULL");
+  SGIC_REQUIRE(k >= 1, "k must be >= 1");
+  SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
+  if (nq == 0) return 0;
+  SGIC_REQUIRE(host_q && host_D && host_I, "NULL buffer");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  const size_t qbytes = static_cast<size_t>(nq) * h->d * 4;
+  const size_t dbytes = static_cast<size_t>(nq) * k * 4, ibytes = static_cast<size_t>(nq) * k * 8;
+  int rc = ensure_buf(&h->qdev, &h->qdev_bytes, qbytes, false);
+  if (rc) return rc;
+  rc = ensure_buf(&h->odev, &h->odev_bytes, dbytes + ibytes, false);
+  if (rc) return rc;
+  rc = ensure_buf(&h->opin, &h->opin_bytes, std::max(qbytes, dbytes + ibytes), true);
+  if (rc) return rc;
+  // queries: host -> pinned -> device; results: device -> pinned -> host
+  std::memcpy(h->opin, host_q, qbytes);
+  SGIC_CUDA(cudaMemcpyAsync(h->qdev, h->opin, qbytes, cudaMemcpyHostToDevice, h->stream));
+  int64_t* dI = reinterpret_cast<int64_t*>(h->odev);
+  float* dD = reinterpret_cast<float*>(static_cast<uint8_t*>(h->odev) + ibytes);
+  rc = search_dev_impl(h, nq, static_cast<const float*>(h->qdev), k, dD, dI, 0, h->stream);
+  if (rc) return rc;
+  SGIC_CUDA(cudaMemcpyAsync(h->opin, h->odev, dbytes + ibytes, cudaMemcpyDeviceToHost, h->stream));
+  SGIC_CUDA(cudaStreamSynchronize(h->stream));
+  std::memcpy(host_I, h->opin, ibytes);
+  std::memcpy(host_D, static_cast<uint8_t*>(h->opin) + ibytes, dbytes);
+  return 0;
+}
+
+int sgic_merge_topk_dev(int device, int64_t nq, int n_lists, int64_t k, const float* dev_D_lists,
+                        const int64_t* dev_I_lists, float* dev_D, int64_t* dev_I, void* stream) {
+  SGIC_REQUIRE(nq >= 0 && n_lists >= 1 && k >= 1, "bad arguments");
+  SGIC_REQUIRE(static_cast<int64_t>(n_lists) * k < (1ll << 31), "too many candidates");
+  if (nq == 0) return 0;
+  DeviceGuard g(device);
+  MergeListsParams mp;
+  mp.D_lists = dev_D_lists;
+  mp.I_lists = reinterpret_cast<const long long*>(dev_I_lists);
+  mp.n_lists = static_cast<uint32_t>(n_lists);
+  mp.nq = static_cast<uint32_t>(nq);
+  mp.k = static_cast<uint32_t>(k);
+  const uint32_t kp = next_pow2_u32(mp.k);
+  uint32_t chunk = std::max<uint32_t>(2 * kp, std::min<uint32_t>(16384, next_pow2_u32(mp.n_lists * mp.k)));
+  chunk = std::max<uint32_t>(chunk, 64);
+  SGIC_REQUIRE(static_cast<size_t>(chunk) * 8 <= kSmemBudget, "k too large for the merge kernel");
+  mp.chunk = chunk;
+  mp.D = dev_D;
+  mp.I = reinterpret_cast<long long*>(dev_I);
+  const size_t smem = static_cast<size_t>(chunk) * 8;
+  if (smem > 48 * 1024)
+    SGIC_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+  const int threads = static_cast<int>(std::min<uint32_t>(1024, std::max<uint32_t>(32, chunk / 2)));
+  merge_lists_kernel<<<static_cast<unsigned>(nq), threads, smem, static_cast<cudaStream_t>(stream)>>>(mp);
+  SGIC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sgic_index_reconstruct(sgic_index* h, int64_t i0, int64_t n, float* host_out) {
+  SGIC_REQUIRE(h != nullptr, "index is NULL");
+  SGIC_REQUIRE(i0 >= 0 && n >= 0 && i0 + n <= h->ntotal, "row range out of bounds");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  int rc = ensure_staging(h);
+  if (rc) return rc;
+  const size_t row_bytes = static_cast<size_t>(h->d) * 4;
+  const int64_t rows_per_chunk = std::max<int64_t>(1, static_cast<int64_t>(kStageChunkBytes / row_bytes));
+  for (int64_t done = 0; done < n; done += rows_per_chunk) {
+    const int64_t rows = std::min(rows_per_chunk, n - done);
+    const size_t n8 = static_cast<size_t>(rows) * h->d / 8;
+    const void* src = static_cast<const uint8_t*>(h->db) + elt_rows_bytes(h, i0 + done);
+    const unsigned gsz = grid_for(n8, 256, h->sm_count);
+    if (h->dtype == SGIC_F16)
+      unpack_rows_kernel<__half><<<gsz, 256, 0, h->stream>>>(src, static_cast<float*>(h->dstage[0]), n8);
+    else
+      unpack_rows_kernel<__nv_bfloat16><<<gsz, 256, 0, h->stream>>>(src, static_cast<float*>(h->dstage[0]), n8);
+    h->stat_launches++;
+    SGIC_CUDA(cudaGetLastError());
+    SGIC_CUDA(cudaMemcpyAsync(h->pin[0], h->dstage[0], static_cast<size_t>(rows) * row_bytes, cudaMemcpyDeviceToHost,
+                              h->stream));
+    SGIC_CUDA(cudaStreamSynchronize(h->stream));
+    std::memcpy(reinterpret_cast<uint8_t*>(host_out) + static_cast<size_t>(done) * row_bytes, h->pin[0],
+                static_cast<size_t>(rows) * row_bytes);
+  }
+  return 0;
+}
+
+int sgic_index_write(sgic_index* h, const char* path) {
+  SGIC_REQUIRE(h != nullptr && path != nullptr, "NULL argument");
+  FILE* f = std::fopen(path, "wb");
+  if (!f) {
+    set_error(std::string("could not open ") + path + " for writing");  // faiss: "could not open %s for writing"
+    return 3;
+  }
+  IxfiHeader hd;
+  std::memcpy(hd.fourcc, "IxFI", 4);
+  hd.d = h->d;
+  hd.ntotal = h->ntotal;
+  hd.dummy0 = 1 << 20;
+  hd.dummy1 = 1 << 20;
+  hd.is_trained = 1;
+  hd.metric_type = 0;  // METRIC_INNER_PRODUCT
+  hd.count = static_cast<uint64_t>(h->ntotal) * h->d;
+  bool ok = std::fwrite(&hd, sizeof(hd), 1, f) == 1;
+  const bool from_host =
+      h->retain_ok && h->retained.size() == static_cast<size_t>(h->ntotal) * static_cast<size_t>(h->d);
+  if (ok && h->ntotal > 0) {
+    if (from_host) {
+      ok = std::fwrite(h->retained.data(), sizeof(float), h->retained.size(), f) == h->retained.size();
+    } else {
+      const int64_t chunk = std::max<int64_t>(1, static_cast<int64_t>((64u << 20) / (h->d * 4)));
+      std::vector<float> buf(static_cast<size_t>(std::min(chunk, h->ntotal)) * h->d);
+      for (int64_t i0 = 0; ok && i0 < h->ntotal; i0 += chunk) {
+        const int64_t rows = std::min(chunk, h->ntotal - i0);
+        int rc = sgic_index_reconstruct(h, i0, rows, buf.data());
+        if (rc) {
+          std::fclose(f);
+          return rc;
+        }
+        ok = std::fwrite(buf.data(), sizeof(float), static_cast<size_t>(rows) * h->d, f) ==
+             static_cast<size_t>(rows) * h->d;
+      }
+    }
+  }
+  ok = (std::fclose(f) == 0) && ok;
+  if (!ok) {
+    set_error(std::string("write error on ") + path);
+    return 3;
+  }
+  return 0;
+}
+
+int sgic_index_read(const char* path, int dtype, int device, int flags, sgic_index** out) {
+  SGIC_REQUIRE(path != nullptr && out != nullptr, "NULL argument");
+  *out = nullptr;
+  FILE* f = std::fopen(path, "rb");
+  if (!f) {
+    set_error(std::string("could not open ") + path + " for reading");
+    return 3;
+  }
+  IxfiHeader hd;
+  if (std::fread(&hd, sizeof(hd), 1, f) != 1) {
+    std::fclose(f);
+    set_error(std::string("read error in ") + path + ": truncated header");
+    return 3;
+  }
+  if (std::memcmp(hd.fourcc, "IxFI", 4) != 0) {
+    std::fclose(f);
+    set_error(std::string("Index type 0x") + std::to_string(*reinterpret_cast<uint32_t*>(hd.fourcc)) +
+              " not recognized: only IxFI (IndexFlatIP) is supported");
+    return 3;
+  }
+  if (hd.d <= 0 || hd.ntotal < 0 || hd.count != static_cast<uint64_t>(hd.ntotal) * hd.d) {
+    std::fclose(f);
+    set_error(std::string("corrupt IxFI header in ") + path);
+    return 3;
+  }
+  sgic_index* h = nullptr;
+  int rc = sgic_index_create(hd.d, dtype, device, hd.ntotal, flags, &h);
+  if (rc) {
+    std::fclose(f);
+    return rc;
+  }
+  const int64_t chunk = std::max<int64_t>(1, static_cast<int64_t>((64u << 20) / (hd.d * 4)));
+  std::vector<float> buf(static_cast<size_t>(std::min<int64_t>(chunk, std::max<int64_t>(hd.ntotal, 1))) * hd.d);
+  for (int64_t i0 = 0; i0 < hd.ntotal; i0 += chunk) {
+    const int64_t rows = std::min(chunk, hd.ntotal - i0);
+    const size_t cnt = static_cast<size_t>(rows) * hd.d;
+    if (std::fread(buf.data(), sizeof(float), cnt, f) != cnt) {
+      std::fclose(f);
+      sgic_index_destroy(h);
+      set_error(std::string("read error in ") + path + ": file shorter than its header says");
+      return 3;
+    }
+    rc = sgic_index_add_f32(h, rows, buf.data());
+    if (rc) {
+      std::fclose(f);
+      sgic_index_destroy(h);
+      return rc;
+    }
+  }
+  std::fclose(f);
+  *out = h;
+  return 0;
+}
+
+int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
+  SGIC_REQUIRE(h != nullptr && name != nullptr, "NULL argument");
+  const std::string n(name);
+  if (n == "timing") h->opt_timing = value;
+  else if (n == "evict_first") h->opt_evict_first = value;
+  else if (n == "grid") h->opt_grid = value;
+  else if (n == "stages") h->opt_stages = value;
+  else if (n == "drop_retained") {
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->retain_ok = false;
+    h->retained.clear();
+    h->retained.shrink_to_fit();
+  }
+  else {
+    set_error("unknown option " + n);
+    return 1;
+  }
+  return 0;
+}
+
+int64_t sgic_index_get_stat(const sgic_index* h, const char* name) {
+  if (!h || !name) return -1;
+  const std::string n(name);
+  if (n == "launches") return h->stat_launches;
+  if (n == "last_search_us") return h->stat_last_search_us;
+  if (n == "last_grid") return h->stat_last_grid;
+  if (n == "last_stages") return h->stat_last_stages;
+  if (n == "capacity") return h->capacity;
+  if (n == "sm_count") return h->sm_count;
+  if (n == "retained_rows") return h->retain_ok ? static_cast<int64_t>(h->retained.size() / h->d) : -1;
+  return -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// Shared top-k building blocks: warp-cooperative sorted insertion, block-wide bitonic
+// sort of 64-bit candidate keys, and the final merge kernels (per-CTA partial lists
+// -> answer; per-shard answers -> global answer = K5 in SURVEY.md §2.1).
+#pragma once
+#include "ptx.cuh"
+
+namespace sgic {
+
+constexpr float kNegFltMax = -3.4028234663852886e38f;  // faiss pads missing slots with -FLT_MAX / -1
+
+__host__ __device__ __forceinline__ uint32_t next_pow2_u32(uint32_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Sort `n` (power of two) keys in shared memory, largest first.  All threads of the
+// block call it; ends with a __syncthreads().
+__device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* keys, uint32_t n) {
+  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  for (uint32_t size = 2; size <= n; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = tid; i < (n >> 1); i += nt) {
+        const uint32_t lo = 2 * i - (i & (stride - 1));
+        const uint32_t hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const uint64_t a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Insert `key` into the warp-private list L[0..k) (sorted, largest first, empty slots
+// are 0).  All 32 lanes call it with the same arguments.  Returns the list's new k-th
+// key (0 while the list is not full).
+__device__ __forceinline__ uint64_t warp_list_insert(uint64_t* L, int k, uint64_t key, int lane) {
+  int p = 0;
+  for (int base = 0; base < k; base += 32) {
+    const int i = base + lane;
+    const bool g = (i < k) && (L[i] > key);
+    const uint32_t m = __ballot_sync(0xffffffffu, g);
+    p += __popc(m);
+    if (m != 0xffffffffu) break;  // sorted: first chunk that is not entirely greater ends the scan
+  }
+  if (p < k) {
+    for (int base = ((k - 1) >> 5) << 5; base >= 0 && base + 31 > p; base -= 32) {
+      const int i = base + lane;
+      const bool mv = (i > p) && (i < k);
+      uint64_t t = 0;
+      if (mv) t = L[i - 1];
+      __syncwarp();
+      if (mv) L[i] = t;
+      __syncwarp();
+    }
+    if (lane == 0) L[p] = key;
+    __syncwarp();
+  }
+  return L[k - 1];
+}
+
+// ------------------------------------------------------------------ final merge (per-CTA partials)
+// partial: [nq][n_lists][k] keys (score, local id).  One CTA per query.  Keys are pulled
+// through shared memory in chunks of at most `chunk` (power of two) keys; each chunk is
+// sorted together with the best k carried from the previous one.
+struct MergeKeysParams {
+  const uint64_t* partial;
+  uint32_t n_lists;
+  uint32_t k;
+  uint32_t chunk;   // smem capacity in keys (power of two, >= 2*k_pow2)
+  float* D;         // [nq][k]
+  long long* I;     // [nq][k]
+  long long id_base;
+};
+
+__global__ void __launch_bounds__(1024, 1) merge_keys_kernel(MergeKeysParams p) {
+  extern __shared__ __align__(16) uint64_t mk_smem[];
+  const uint32_t q = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const uint64_t* src = p.partial + static_cast<size_t>(q) * p.n_lists * p.k;
+  const uint32_t n_total = p.n_lists * p.k;
+  uint32_t carry = 0, pos = 0;
+  while (pos < n_total) {
+    const uint32_t take = min(p.chunk - carry, n_total - pos);
+    const uint32_t m = max(next_pow2_u32(carry + take), 2u);
+    for (uint32_t i = tid; i < m - carry; i += nt) mk_smem[carry + i] = (i < take) ? src[pos + i] : 0ull;
+    __syncthreads();
+    block_bitonic_sort_desc(mk_smem, m);
+    carry = min(p.k, m);
+    pos += take;
+  }
+  for (uint32_t i = tid; i < p.k; i += nt) {
+    const uint64_t key = (i < carry) ? mk_smem[i] : 0ull;
+    const size_t o = static_cast<size_t>(q) * p.k + i;
+    if (key == 0ull) {
+      p.D[o] = kNegFltMax;
+      p.I[o] = -1;
+    } else {
+      p.D[o] = key_score(key);
+      p.I[o] = p.id_base + static_cast<long long>(key_id(key));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K5: merge of per-shard answers
+// D_lists / I_lists: [n_lists][nq][k] as an all-gather of each rank's (nq,k) answer lays
+// them out.  Shards hold ascending, disjoint row ranges and each list is ordered (score
+// desc, id asc), so the position g*k+j is a valid tie-break: ordering by (score desc,
+// position asc) equals (score desc, global id asc) and the G-GPU answer is identical to
+// the 1-GPU answer.
+struct MergeListsParams {
+  const float* D_lists;
+  const long long* I_lists;
+  uint32_t n_lists;
+  uint32_t nq;
+  uint32_t k;
+  uint32_t chunk;
+  float* D;
+  long long* I;
+};
+
+__global__ void __launch_bounds__(1024, 1) merge_lists_kernel(MergeListsParams p) {
+  extern __shared__ __align__(16) uint64_t ml_smem[];
+  const uint32_t q = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t n_total = p.n_lists * p.k;
+  uint32_t carry = 0, pos = 0;
+  while (pos < n_total) {
+    const uint32_t take = min(p.chunk - carry, n_total - pos);
+    const uint32_t m = max(next_pow2_u32(carry + take), 2u);
+    for (uint32_t i = tid; i < m - carry; i += nt) {
+      uint64_t key = 0ull;
+      if (i < take) {
+        const uint32_t e = pos + i, g = e / p.k, j = e - g * p.k;
+        const size_t o = (static_cast<size_t>(g) * p.nq + q) * p.k + j;
+        if (p.I_lists[o] >= 0) key = make_key(p.D_lists[o], e);
+      }
+      ml_smem[carry + i] = key;
+    }
+    __syncthreads();
+    block_bitonic_sort_desc(ml_smem, m);
+    carry = min(p.k, m);
+    pos += take;
+  }
+  for (uint32_t i = tid; i < p.k; i += nt) {
+    const uint64_t key = (i < carry) ? ml_smem[i] : 0ull;
+    const size_t out = static_cast<size_t>(q) * p.k + i;
+    if (key == 0ull) {
+      p.D[out] = kNegFltMax;
+      p.I[out] = -1;
+    } else {
+      const uint32_t e = key_id(key), g = e / p.k, j = e - g * p.k;
+      const size_t o = (static_cast<size_t>(g) * p.nq + q) * p.k + j;
+      p.D[out] = p.D_lists[o];
+      p.I[out] = p.I_lists[o];
+    }
+  }
+}
+
+}  // namespace sgic

@@ -1,0 +1,178 @@
+"""Index construction — host-side mirror of the reference's ``src/build.py``
+(``build_index_from_c2df_dir`` :71-103) and of the retrieval pieces of ``src/compress.py``
+(``ClipCodec.quantize_u8_and_compress`` :76-86, ``FaissDB`` :89-114).
+
+``build_index_from_c2df_dir`` keeps the reference's observable behaviour — sorted recursive
+glob, per-file ``[SKIP]`` on any decode error, both naming schemes written
+(``faiss.index`` + ``paths.json`` + ``meta.json`` and ``index.faiss`` + ``ids.txt``) — but the
+per-file Python loop is replaced by the batched C++ parser + device-side loader
+(``IndexFlatIP.add_c2df``).  ``build-images`` / ``download`` need CLIP weights / network
+and are out of scope.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import traceback
+from pathlib import Path
+from typing import List
+
+import numpy as np
+
+from . import _native
+from . import faiss_compat as faiss
+from . import zstd
+from .c2df import unpack_c2df
+from .retrieval import decode_clip_from_c2df, load_index  # build.py carries its own copies (:26-43, :106-126)
+
+__all__ = ["build_index_from_c2df_dir", "quantize_u8_and_compress", "FaissDB", "load_index", "from_npy_dir"]
+
+
+def quantize_u8_and_compress(z_unit: np.ndarray, model_id: str = "ViT-B-32:laion2b_s34b_b79k"):
+    """fp32 unit vector → (zstd-19 bytes of the u8 codes, clip_meta dict) — src/compress.py:76-86.
+    ``np.round`` is round-half-to-even, as in the reference."""
+    q = np.clip(np.round((z_unit * 0.5 + 0.5) * 255.0), 0, 255).astype(np.uint8)
+    meta = {"model_id": model_id, "dim": int(z_unit.shape[0]), "quant": "u8_symmetric_-1_1",
+            "codec": "zstd", "zstd_level": 19}
+    return zstd.compress(q.tobytes(), 19), meta
+
+
+def _skip_reason(path: Path, code: int) -> str:
+    """Message of the exception the reference would have printed for this file."""
+    if code in (3, 4, 6):
+        return f"{path} {_native.C2DF_STATUS[code]}"
+    return _native.C2DF_STATUS.get(code, f"status {code}")
+
+
+def build_index_from_c2df_dir(c2df_dir, index_dir, *, dtype="fp16", device=None, n_threads: int = 0) -> None:
+    c2df_dir, index_dir = Path(c2df_dir), Path(index_dir)
+    index_dir.mkdir(parents=True, exist_ok=True)
+    paths = sorted(c2df_dir.glob("**/*.c2df"))
+    if not paths:
+        raise RuntimeError(f"Empty folder: {c2df_dir}")
+
+    # the index dimension is that of the first decodable file (X.shape[1] upstream, build.py:92)
+    d = None
+    for p in paths:
+        try:
+            z, _ = decode_clip_from_c2df(p)
+            d = int(z.shape[0])
+            break
+        except Exception:
+            continue
+    if d is None:
+        for p in paths:
+            print(f"[SKIP] {p.name}: not a usable .c2df")
+        raise RuntimeError("No available .c2df")
+    model_id = None
+    index = faiss.IndexFlatIP(d, dtype=dtype, device=device, retain_fp32=False)
+    statuses = index.add_c2df_paths(paths, n_threads=n_threads)
+    keep: List[str] = []
+    for p, st in zip(paths, statuses):
+        if st == 0:
+            keep.append(str(p))
+            if model_id is None:
+                try:
+                    _, header = unpack_c2df(p)
+                    if isinstance(header, dict):
+                        model_id = header.get("model_id")
+                except Exception:
+                    pass
+        else:
+            print(f"[SKIP] {p.name}: {_skip_reason(p, int(st))}")
+    if not keep:
+        raise RuntimeError("No available .c2df")
+
+    faiss.write_index(index, str(index_dir / "faiss.index"))
+    (index_dir / "paths.json").write_text(json.dumps(keep, ensure_ascii=False, indent=2), encoding="utf-8")
+    (index_dir / "meta.json").write_text(json.dumps({"dim": d, "model_id": model_id}, ensure_ascii=False, indent=2),
+                                         encoding="utf-8")
+    faiss.write_index(index, str(index_dir / "index.faiss"))
+    (index_dir / "ids.txt").write_text("\n".join(keep), encoding="utf-8")
+    print(f"[OK] Index process completed!: N={index.ntotal}, dim={d}")
+    if model_id:
+        print(f"[INFO] Suggested CLIP model: {model_id}")
+
+
+class FaissDB:
+    """Open-or-create ``index.faiss`` + ``ids.txt`` and append — src/compress.py:89-114.
+
+    ``add`` renormalises with ``v / (||v|| + 1e-12)`` exactly as the reference does, and
+    ``persist`` writes one id per line with a trailing newline.
+    """
+
+    def __init__(self, index_dir: str, dim: int, **index_kwargs):
+        os.makedirs(index_dir, exist_ok=True)
+        self.index_path = os.path.join(index_dir, "index.faiss")
+        self.ids_path = os.path.join(index_dir, "ids.txt")
+        if os.path.exists(self.index_path):
+            self.index = faiss.read_index(self.index_path, **index_kwargs)
+        else:
+            self.index = faiss.IndexFlatIP(dim, **index_kwargs)
+        self.ids: List[str] = []
+        if os.path.exists(self.ids_path):
+            with open(self.ids_path, "r", encoding="utf-8") as f:
+                self.ids = [ln.strip() for ln in f if ln.strip()]
+
+    def add(self, vec_unit: np.ndarray, doc_id: str) -> None:
+        assert vec_unit.ndim == 1
+        v = vec_unit.copy()[None, :]
+        v /= np.linalg.norm(v, axis=1, keepdims=True) + 1e-12
+        self.index.add(v.astype("float32"))
+        self.ids.append(doc_id)
+
+    def add_many(self, vecs: np.ndarray, doc_ids: List[str]) -> None:
+        """Additive: the same renormalisation for a whole (n, d) block in one add."""
+        v = np.array(vecs, dtype=np.float32, copy=True)
+        v /= np.linalg.norm(v, axis=1, keepdims=True) + 1e-12
+        self.index.add(v.astype("float32"))
+        self.ids.extend(doc_ids)
+
+    def persist(self) -> None:
+        faiss.write_index(self.index, self.index_path)
+        with open(self.ids_path, "w", encoding="utf-8") as f:
+            for _id in self.ids:
+                f.write(_id + "\n")
+
+
+def from_npy_dir(clip_vecs_dir, bitstream_dir, index_dir, **index_kwargs) -> FaissDB:
+    """The rank-0 tail of ``compress.test`` (src/compress.py:295-306): every
+    ``clip_vecs/<stem>.npy`` in sorted order → ``FaissDB.add`` with id
+    ``<bitstream_dir>/<stem>.c2df`` → ``persist``.  Vectors are appended block-wise."""
+    files = sorted(Path(clip_vecs_dir).glob("*.npy"))
+    if not files:
+        raise RuntimeError(f"Empty folder: {clip_vecs_dir}")
+    first = np.load(files[0])
+    db = FaissDB(str(index_dir), int(first.shape[-1]), **index_kwargs)
+    block, ids = [], []
+    for f in files:
+        block.append(np.load(f).astype(np.float32).reshape(-1))
+        ids.append(os.path.join(str(bitstream_dir), f.stem + ".c2df"))
+        if len(block) >= 65536:
+            db.add_many(np.stack(block), ids)
+            block, ids = [], []
+    if block:
+        db.add_many(np.stack(block), ids)
+    db.persist()
+    return db
+
+
+def main(argv=None) -> None:
+    ap = argparse.ArgumentParser(description="build (from .c2df bitstreams)")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    sp = sub.add_parser("build", help="build the index from a directory of .c2df")
+    sp.add_argument("--c2df_dir", type=Path, required=True)
+    sp.add_argument("--index_dir", type=Path, required=True)
+    args = ap.parse_args(argv)
+    try:
+        build_index_from_c2df_dir(args.c2df_dir, args.index_dir)
+    except Exception as e:
+        print(f"[ERROR] {e}")
+        traceback.print_exc()
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

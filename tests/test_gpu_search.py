@@ -1,0 +1,110 @@
+"""GPU parity tests of the search path (K3 streaming kernel + merge) against the CPU oracle.
+Everything goes through the faiss-compatible surface, i.e. through the C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.flat_ip import check_topk, flat_ip_search, NEG_FLT_MAX
+
+
+def unit(rng, n, d):
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return x
+
+
+def rounded(x, dtype):
+    if dtype == "fp16":
+        return x.astype(np.float16).astype(np.float64)
+    import torch
+    return torch.from_numpy(x).to(torch.bfloat16).to(torch.float64).numpy()
+
+
+def make_index(xb, dtype="fp16"):
+    from sgic_b200 import faiss_compat as faiss
+    idx = faiss.IndexFlatIP(xb.shape[1], dtype=dtype, device=0)
+    idx.add(xb)
+    return idx
+
+
+@pytest.mark.parametrize("n,d,nq,k", [
+    (1, 512, 1, 1),
+    (7, 512, 1, 10),        # k > ntotal: -1 / -FLT_MAX padding
+    (33, 512, 2, 10),
+    (1000, 512, 1, 10),
+    (4097, 512, 3, 10),     # N not a multiple of the tile
+    (20000, 512, 1, 100),
+    (20000, 768, 4, 10),
+    (5000, 256, 1, 10),
+    (5000, 1024, 2, 10),
+    (3000, 2048, 1, 10),
+    (9999, 64, 1, 5),
+    (50000, 512, 7, 10),    # > 4 queries: several passes
+    (20000, 512, 1, 1024),
+])
+def test_search_matches_oracle(n, d, nq, k):
+    rng = np.random.default_rng(n * 31 + d + nq + k)
+    xb, xq = unit(rng, n, d), unit(rng, nq, d)
+    idx = make_index(xb)
+    assert idx.ntotal == n and idx.d == d
+    D, I = idx.search(xq, k)
+    # O-exact: oracle on the values the GPU holds (fp16-rounded db and queries)
+    check_topk(D, I, rounded(xb, "fp16"), rounded(xq, "fp16"), k, score_tol=2e-5, tie_tol=1e-6)
+    # O-ref: the fp32 vectors FAISS would hold; north_star tolerance 1e-3
+    check_topk(D, I, xb, xq, k, score_tol=1e-3)
+
+
+def test_bf16_storage():
+    rng = np.random.default_rng(5)
+    xb, xq = unit(rng, 30000, 512), unit(rng, 2, 512)
+    idx = make_index(xb, "bf16")
+    D, I = idx.search(xq, 10)
+    check_topk(D, I, rounded(xb, "bf16"), rounded(xq, "bf16"), 10, score_tol=2e-5, tie_tol=1e-6)
+    check_topk(D, I, xb, xq, 10, score_tol=4e-3)  # bf16 worst case 2^-8
+
+
+def test_exact_duplicates_resolve_to_lowest_ids():
+    """FaissDB re-adds every .npy on each run (src/compress.py:296-306), so exact ties are real."""
+    rng = np.random.default_rng(11)
+    base = unit(rng, 500, 512)
+    xb = np.concatenate([base, base, base])           # every row three times
+    xq = base[:3].copy()
+    idx = make_index(xb)
+    D, I = idx.search(xq, 6)
+    for r in range(3):
+        assert list(I[r, :3]) == [r, r + 500, r + 1000]   # (score desc, id asc)
+        assert D[r, 0] == D[r, 1] == D[r, 2]
+    Dref, Iref = flat_ip_search(rounded(xb, "fp16"), rounded(xq, "fp16"), 6, dtype=np.float64)
+    assert np.array_equal(I, Iref)
+
+
+def test_incremental_add_and_empty_index():
+    from sgic_b200 import faiss_compat as faiss
+    rng = np.random.default_rng(3)
+    idx = faiss.IndexFlatIP(512, device=0)
+    q = unit(rng, 1, 512)
+    D, I = idx.search(q, 4)                           # ntotal == 0
+    assert np.all(I == -1) and np.all(D == NEG_FLT_MAX)
+    xb = unit(rng, 3000, 512)
+    for s in range(0, 3000, 700):                     # grows the HBM allocation several times
+        idx.add(xb[s:s + 700])
+    for i in range(5):                                # one-row adds, as FaissDB.add does
+        idx.add(xb[i][None, :])
+    assert idx.ntotal == 3005
+    full = np.concatenate([xb, xb[:5]])
+    D, I = idx.search(q, 10)
+    check_topk(D, I, rounded(full, "fp16"), rounded(q, "fp16"), 10, score_tol=2e-5, tie_tol=1e-6)
+
+
+def test_argument_errors():
+    from sgic_b200 import faiss_compat as faiss
+    idx = faiss.IndexFlatIP(512, device=0)
+    with pytest.raises(AssertionError):
+        idx.add(np.zeros((2, 511), dtype=np.float32))
+    with pytest.raises(AssertionError):
+        idx.search(np.zeros((1, 512), dtype=np.float32), 0)
+    with pytest.raises(RuntimeError):
+        faiss.IndexFlatIP(513, device=0)
+    with pytest.raises(RuntimeError):
+        faiss.read_index("/nonexistent/index.faiss")
