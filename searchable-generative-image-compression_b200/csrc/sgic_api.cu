@@ -84,7 +84,7 @@ struct sgic_index {
   std::vector<float> retained;
   bool retain_ok = false;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0;
   int64_t stat_launches = 0, stat_last_search_us = 0, stat_last_grid = 0, stat_last_stages = 0;
 };
 
@@ -227,7 +227,12 @@ static cudaError_t launch_scan_inst(const ScanSmallParams& p, unsigned grid, siz
 }
 
 template <typename T, int NQ>
-static cudaError_t launch_scan_nq(const ScanSmallParams& p, int cpl, unsigned grid, size_t smem, cudaStream_t st) {
+static cudaError_t launch_scan_nq(const ScanSmallParams& p, int cpl, int rb, unsigned grid, size_t smem,
+                                  cudaStream_t st) {
+  if constexpr (NQ == 1) {  // tile-height variants of the d<=512 batch-1 kernel (tuning knob "rb")
+    if (cpl == 2 && rb == 2) return launch_scan_inst<T, NQ, 2, 2>(p, grid, smem, st);
+    if (cpl == 2 && rb == 8) return launch_scan_inst<T, NQ, 2, 8>(p, grid, smem, st);
+  }
   switch (cpl) {
     case 1: return launch_scan_inst<T, NQ, 1, 8>(p, grid, smem, st);
     case 2: return launch_scan_inst<T, NQ, 2, 4>(p, grid, smem, st);
@@ -238,12 +243,12 @@ static cudaError_t launch_scan_nq(const ScanSmallParams& p, int cpl, unsigned gr
 }
 
 template <typename T>
-static cudaError_t launch_scan_t(const ScanSmallParams& p, int NQ, int cpl, unsigned grid, size_t smem,
+static cudaError_t launch_scan_t(const ScanSmallParams& p, int NQ, int cpl, int rb, unsigned grid, size_t smem,
                                  cudaStream_t st) {
   switch (NQ) {
-    case 1: return launch_scan_nq<T, 1>(p, cpl, grid, smem, st);
-    case 2: return launch_scan_nq<T, 2>(p, cpl, grid, smem, st);
-    default: return launch_scan_nq<T, 4>(p, cpl, grid, smem, st);
+    case 1: return launch_scan_nq<T, 1>(p, cpl, rb, grid, smem, st);
+    case 2: return launch_scan_nq<T, 2>(p, cpl, rb, grid, smem, st);
+    default: return launch_scan_nq<T, 4>(p, cpl, rb, grid, smem, st);
   }
 }
 
@@ -279,7 +284,8 @@ static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_
   SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
   if (nq == 0) return 0;
   SGIC_REQUIRE(h->ntotal < (1ll << 32) - 1, "more than 2^32-2 rows in one shard");
-  const ScanCfg cfg = scan_cfg_for_d(h->d);
+  ScanCfg cfg = scan_cfg_for_d(h->d);
+  if (nq == 1 && cfg.cpl == 2 && (h->opt_rb == 2 || h->opt_rb == 8)) cfg.rb = static_cast<int>(h->opt_rb);
   const uint32_t kp = std::max<uint32_t>(2, next_pow2_u32(static_cast<uint32_t>(k)));
   int NQ = (nq == 1) ? 1 : (nq == 2) ? 2 : 4;
   while (NQ > 1 && static_cast<uint32_t>(NQ) * kp > 1024) NQ >>= 1;
@@ -289,9 +295,13 @@ static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_
   const size_t list_bytes = static_cast<size_t>(NQ) * kScanConsumerWarps * kp * 8;
   const size_t bar_bytes = 2 * kScanMaxStages * 8;
   SGIC_REQUIRE(list_bytes + bar_bytes + 2 * stage_bytes <= kSmemBudget, "k too large for shared memory");
-  uint32_t stages = static_cast<uint32_t>((kSmemBudget - list_bytes - bar_bytes) / stage_bytes);
-  stages = std::min<uint32_t>(stages, kScanMaxStages);
-  if (h->opt_stages > 0) stages = std::min<uint32_t>(stages, static_cast<uint32_t>(h->opt_stages));
+  // Measured on B200 (profiles/r01_k3_stage_sweep.md): ~128 KB of bulk copies in flight per SM is
+  // the sweet spot (7.4-7.5 TB/s); 160 KB and more drops to ~6.8 TB/s, 64 KB to ~6.4 TB/s.
+  const uint32_t max_stages =
+      std::min<uint32_t>(kScanMaxStages, static_cast<uint32_t>((kSmemBudget - list_bytes - bar_bytes) / stage_bytes));
+  uint32_t stages = std::max<uint32_t>(2, ((128u << 10) + stage_bytes / 2) / stage_bytes);
+  if (h->opt_stages > 0) stages = static_cast<uint32_t>(h->opt_stages);
+  stages = std::max<uint32_t>(2, std::min(stages, max_stages));
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + list_bytes + bar_bytes;
 
   const uint32_t n_rows = static_cast<uint32_t>(h->ntotal);
@@ -326,8 +336,8 @@ static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_
     p.evict_first = h->opt_evict_first ? 1u : 0u;
     cudaError_t e;
     if (n_rows > 0) {
-      if (h->dtype == SGIC_F16) e = launch_scan_t<__half>(p, NQ, cfg.cpl, grid, smem, st);
-      else e = launch_scan_t<__nv_bfloat16>(p, NQ, cfg.cpl, grid, smem, st);
+      if (h->dtype == SGIC_F16) e = launch_scan_t<__half>(p, NQ, cfg.cpl, cfg.rb, grid, smem, st);
+      else e = launch_scan_t<__nv_bfloat16>(p, NQ, cfg.cpl, cfg.rb, grid, smem, st);
       h->stat_launches++;
       if (e != cudaSuccess) {
         set_error(std::string("scan_small launch failed: ") + cudaGetErrorString(e));
@@ -823,6 +833,7 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "evict_first") h->opt_evict_first = value;
   else if (n == "grid") h->opt_grid = value;
   else if (n == "stages") h->opt_stages = value;
+  else if (n == "rb") h->opt_rb = value;
   else if (n == "drop_retained") {
     std::lock_guard<std::mutex> lk(h->mu);
     h->retain_ok = false;

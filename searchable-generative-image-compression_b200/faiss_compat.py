@@ -52,6 +52,13 @@ def _dtype_code(dtype) -> int:
     return _DTYPES[key]
 
 
+def _torch_stream(device) -> C.c_void_p:
+    """cudaStream_t of torch's current stream.  torch's default stream is the legacy stream
+    (handle 0); the C ABI reads NULL as "the index's own stream", so pass cudaStreamLegacy."""
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream or 1)
+
+
 def _ptr(a: np.ndarray) -> C.c_void_p:
     return C.c_void_p(a.ctypes.data)
 
@@ -209,7 +216,7 @@ class IndexFlatIP(Index):
         import torch
         assert x.is_cuda and x.dim() == 2 and x.shape[1] == self.d and x.is_contiguous()
         assert x.device.index == self.device
-        st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        st = _torch_stream(x.device)
         want = torch.bfloat16 if self.dtype == "bf16" else torch.float16
         if x.dtype == torch.float32:
             check(self._lib.sgic_index_add_f32_dev(self._h, x.shape[0], C.c_void_p(x.data_ptr()), st))
@@ -231,7 +238,7 @@ class IndexFlatIP(Index):
             I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
         else:
             D, I = out
-        st = C.c_void_p(torch.cuda.current_stream(q.device).cuda_stream)
+        st = _torch_stream(q.device)
         check(self._lib.sgic_index_search_dev(self._h, nq, C.c_void_p(q.data_ptr()), int(k),
                                               C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()),
                                               int(id_base), st))

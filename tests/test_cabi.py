@@ -1,0 +1,102 @@
+"""The C-ABI boundary without a GPU: the library loads, exports every symbol include/sgic.h
+declares, refuses loudly to work without a B200, and its host-only .c2df batch parser matches
+the reference-generated golden vectors."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from sgic_b200 import _native
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "sgic.h").read_text()
+    declared = set(re.findall(r"\b(sgic_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    lib = C.CDLL(str(_native.LIB_PATH))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/sgic.h but not exported"
+    assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
+    assert _native.lib().sgic_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from sgic_b200 import faiss_compat as faiss
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        faiss.IndexFlatIP(512)
+    with pytest.raises(RuntimeError):
+        faiss.read_index(str(ROOT / "tests" / "golden" / "index.faiss"))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = ROOT / "searchable-generative-image-compression_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.cpp")):
+        text = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+        assert "liboracle" not in text, f
+
+
+def _parse(blob, offsets, dim, threads=2):
+    lib = _native.lib()
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = offsets.size - 1
+    out = np.full((n, dim), 0xAB, dtype=np.uint8)
+    status = np.full(n, -1, dtype=np.int32)
+    dims = np.full(n, -1, dtype=np.int32)
+    rc = lib.sgic_c2df_parse(blob.ctypes.data, offsets.ctypes.data, n, dim, out.ctypes.data, status.ctypes.data,
+                             dims.ctypes.data, threads)
+    assert rc == 0, _native.last_error()
+    return out, status, dims
+
+
+def test_batch_parser_matches_reference_codes(golden):
+    g = np.load(golden / "c2df_golden.npz")
+    offs, dims = g["good_offsets"], g["good_dims"]
+    for want_dim in (512, 768, 64, 8):
+        out, status, got_dims = _parse(g["good_blob"], offs, want_dim)
+        pos = 0
+        for i, d in enumerate(dims):
+            assert got_dims[i] == d
+            if d == want_dim:
+                assert status[i] == 0
+                assert np.array_equal(out[i], g["good_codes"][pos:pos + d])   # bit-exact u8 rows
+            else:
+                assert status[i] == 7                                          # SGIC_C2DF_WRONG_D
+                assert np.all(out[i] == 0xAB)                                  # row untouched
+            pos += d
+    raw = np.frombuffer((golden / "apple.c2df").read_bytes(), dtype=np.uint8)
+    out, status, d = _parse(raw, [0, raw.size], 512, threads=1)
+    assert status[0] == 0 and d[0] == 512 and int(out[0].astype(np.int64).sum()) == 65377
+
+
+def test_batch_parser_status_codes_mirror_reference_exceptions(golden):
+    g = np.load(golden / "c2df_golden.npz")
+    out, status, _ = _parse(g["bad_blob"], g["bad_offsets"], 512)
+    # reference exception class -> acceptable status codes (sgic.h)
+    allowed = {
+        "AssertionError": {1}, "JSONDecodeError": {2}, "error": {2}, "TypeError": {5}, "ZstdError": {5}, "OK": {0},
+    }
+    by_name = {
+        "no_clip_stream": {3}, "no_clip_meta": {3}, "dim_zero": {4}, "dim_negative": {4}, "dim_missing": {4},
+        "meta_none": {4}, "dim_mismatch": {6},
+    }
+    for name, cls, st in zip(g["bad_names"], g["bad_classes"], status):
+        want = by_name.get(str(name), allowed.get(str(cls)))
+        assert want is not None, (name, cls)
+        assert int(st) in want, f"{name}: reference {cls} -> status {st}, expected {want}"
+        assert (st == 0) == (cls == "OK")           # skipped by us iff skipped by the reference
+
+
+def test_batch_parser_ragged_and_empty_inputs():
+    out, status, dims = _parse(np.zeros(0, np.uint8), [0], 512)
+    assert out.shape == (0, 512)
+    out, status, dims = _parse(np.zeros(4, np.uint8), [0, 0, 4], 512)       # empty file + junk
+    assert list(status) == [1, 1]
