@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Headline benchmark: exact inner-product k-NN queries/sec at k=10 on a 100M x 512 fp16 index
+(BASELINE.json `metric`; config C4 of SURVEY.md §8a, which at N=1 is also the largest
+single-GPU configuration: 102.4 GB in one B200's HBM).
+
+    python bench.py --gpus N --steps K --warmup W [--batch B] [--rows R] [--impl reference]
+
+A "step" is one search call over one batch of B synthetic unit queries (default B=1, the
+HBM-bound regime).  The index is fixed at R rows and row-sharded over the N ranks
+(`scaling: strong`); each rank searches its shard, the per-query candidates are all-gathered
+(NCCL) and merged on device.  One JSON line is printed by rank 0.
+
+  value     queries/s with the queries already resident in HBM (CUDA events, max over ranks)
+  e2e       queries/s through the public faiss-style call with HOST numpy buffers: pinned
+            H2D copy of the queries and D2H read of (D, I) inside the timed region
+  roofline  the dominant kernel (the database scan): algorithmic bytes N_local*d*2 per launch
+            / its CUDA-event duration, against MEASURED_PEAKS.json `hbm_gbs`
+  cpu_baseline  the C restatement of FAISS's CPU flat-IP path (oracle/flat_ip.c) timed on this
+            box's host cores on a bounded row sample, scaled linearly to R rows
+
+`--impl reference` times only that CPU path (the reference's own implementation of the search
+is faiss-cpu, which is not installable here: SURVEY.md §8c) and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "queries/sec at k=10 on 100M×512 fp16 index (batch 1 / 4096); % HBM/TC roofline"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=100_000_000)
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
+    ap.add_argument("--no-extras", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return {"hbm_gbs": float(j["hbm_gbs"]), "bf16_tflops": float(j.get("bf16_tflops", 1655.1)),
+                "bf16_tflops_sustained": float(j.get("bf16_tflops_sustained", 1404.9)), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [ln.strip().split(",") for ln in open(self.tmp.name) if ln.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_baseline(rows_full: int, d: int, k: int, batch: int, sample_rows: int, steps: int, warmup: int):
+    """FAISS CPU flat-IP restatement on a bounded sample; qps scaled linearly to `rows_full`."""
+    import numpy as np
+    import torch
+    from oracle import flat_ip_c
+    L = flat_ip_c.load(native=True)
+    blas = flat_ip_c.try_attach_blas(L) if batch >= 20 else None
+    n = min(rows_full, sample_rows)
+    g = torch.Generator().manual_seed(1234)
+    xb = torch.randn((n, d), generator=g)
+    xb /= xb.norm(dim=1, keepdim=True)
+    xb = xb.numpy()
+    q = torch.randn((batch, d), generator=g)
+    q /= q.norm(dim=1, keepdim=True)
+    q = q.numpy()
+    threads_avail = L.oracle_num_threads()
+    cores_used = min(batch, threads_avail) if batch < 20 else threads_avail   # FAISS: one thread per query when nq<20
+    for _ in range(max(1, min(warmup, 2))):
+        flat_ip_c.flat_ip_search_c(xb, q, k, native=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        flat_ip_c.flat_ip_search_c(xb, q, k, native=True)
+    dt = (time.perf_counter() - t0) / steps
+    qps_sample = batch / dt
+    out = {
+        "value": qps_sample * n / rows_full, "unit": "queries/s", "cores": cores_used, "kind": "port",
+        "sample": f"{n}x{d} fp32 rows, batch {batch}, k={k}, {steps} timed calls of oracle/flat_ip.c "
+                  f"({dt * 1e3:.1f} ms each); scaled x{n / rows_full:.4g} to {rows_full} rows (flat scan is linear in N)",
+        "ms_per_step_sample": dt * 1e3, "host_threads_available": threads_avail,
+        "blas": blas,
+    }
+    if batch < 20:   # "optimistic CPU": rows split over every thread (not what FAISS does for nq<20)
+        flat_ip_c.flat_ip_search_c(xb, q, k, rowpar=True, native=True)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            flat_ip_c.flat_ip_search_c(xb, q, k, rowpar=True, native=True)
+        dt2 = (time.perf_counter() - t0) / steps
+        out["optimistic_all_threads"] = {"value": batch / dt2 * n / rows_full, "cores": threads_avail}
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args.rows, args.dim, args.k, args.batch, args.cpu_sample_rows, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * args.batch / cb["value"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.rows}x{args.dim} flat inner-product index, batch {args.batch}, k={args.k}",
+                   "rows": args.rows, "dim": args.dim, "k": args.k, "batch": args.batch,
+                   "note": "FAISS CPU flat-IP path restated in C (faiss-cpu not installable offline); "
+                           "bounded row sample scaled linearly"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as graft
+    graft.build_native()
+    from sgic_b200 import faiss_compat as faiss
+    from sgic_b200.sharded import ShardedIndexFlatIP, shard_range
+    from sgic_b200.synth import fill_index_random, random_unit_queries
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    d, k, nq, R = args.dim, args.k, args.batch, args.rows
+
+    # ---- the index: R rows, contiguous shard per rank ------------------------------------
+    lo, hi = shard_range(R, world, rank)
+    chunk = 500_000   # generator granularity: shard starts of 100M/{1,2,4,8} fall on chunk boundaries
+    if world > 1:
+        index = ShardedIndexFlatIP(d, dtype=args.dtype)
+        # seeds are per chunk of the GLOBAL row number: any sharding holds the same database
+        lo_al = (lo // chunk) * chunk
+        def adder(local):
+            tmp_rows = hi - lo_al
+            fill_index_random(local, tmp_rows, row0=lo_al, chunk_rows=chunk)
+        if lo_al != lo:
+            raise SystemExit(f"rows/gpus must keep shard starts on {chunk}-row boundaries")
+        index.add_local(adder, lo, hi - lo, R)
+        local = index.local
+        search_dev = lambda q: index.search_torch(q, k)
+        search_host = lambda qh: index.search(qh, k)
+    else:
+        index = faiss.IndexFlatIP(d, dtype=args.dtype, device=local_rank, retain_fp32=False)
+        fill_index_random(index, R, chunk_rows=chunk)
+        local = index
+        Dbuf = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        Ibuf = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        search_dev = lambda q: index.search_torch(q, k, out=(Dbuf, Ibuf))
+        search_host = lambda qh: index.search(qh, k)
+    n_local = local.ntotal
+
+    qh = random_unit_queries(nq, d)
+    q = torch.from_numpy(qh).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ---------------------------------------------------------
+    for _ in range(args.warmup):
+        search_dev(q)
+    barrier()
+    launches0 = local.stat("launches")
+    clk = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = search_dev(q)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = clk.stop() if clk else None
+    launches = local.stat("launches") - launches0 + (args.steps if world > 1 else 0)   # + K5 merge per step
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = nq * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the host-buffer API ---------------------------------------------
+    for _ in range(min(args.warmup, 3)):
+        search_host(qh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        Dh, Ih = search_host(qh)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_qps = nq * args.steps / float(t.item())
+
+    # ---- roofline of the dominant kernel (the scan), measured live with CUDA events ----------
+    local.set_option("timing", 1)
+    scan_ns = []
+    for _ in range(max(5, min(args.steps, 20))):
+        search_dev(q)
+        scan_ns.append(local.stat("last_scan_ns"))
+    local.set_option("timing", 0)
+    scan_ms = statistics.mean(scan_ns) / 1e6
+    alg_bytes = n_local * d * 2
+    achieved = alg_bytes / (scan_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "kernel": "scan_small_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms": scan_ms, "frac_of_nominal_8TBs": achieved / 8000.0}
+    traffic_file = ROOT / "profiles" / "traffic.json"
+    if traffic_file.exists():   # dram bytes per row from the committed ncu capture (profiles/)
+        tj = json.loads(traffic_file.read_text())
+        if "dram_bytes_per_row_d512" in tj and d == 512:
+            roofline["traffic"] = tj["dram_bytes_per_row_d512"] * n_local
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
+        "config": {"workload": f"{R}x{d} {args.dtype} index row-sharded over {world} GPU(s), batch {nq}, k={k}",
+                   "rows": R, "dim": d, "k": k, "batch": nq, "rows_per_gpu": n_local,
+                   "l2": f"inputs larger than L2: every step streams the {n_local * d * 2 / 1e9:.1f} GB shard from HBM"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(nq * d * 4),
+                "d2h_bytes_per_step": int(nq * k * 12)},
+        "roofline": roofline,
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_baseline(R, d, k, nq, args.cpu_sample_rows, max(3, min(args.steps, 10)), 1)
+        if not args.no_extras:
+            line["extras"] = extras(faiss, fill_index_random, random_unit_queries, torch, dev, pk)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extras(faiss, fill_index_random, random_unit_queries, torch, dev, pk):
+    """Other BASELINE.json configs that fit one GPU, measured the same way (not the headline)."""
+    res = []
+    for rows, d, nq, k, name in ((1_000_000, 512, 1, 10, "C2: 1Mx512 fp16, batch 1, k=10"),):
+        idx = faiss.IndexFlatIP(d, device=dev.index, retain_fp32=False)
+        fill_index_random(idx, rows)
+        q = torch.from_numpy(random_unit_queries(nq, d)).to(dev)
+        D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
+        for _ in range(5):
+            idx.search_torch(q, k, out=(D, I))
+        ms = []
+        for _ in range(50):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            idx.search_torch(q, k, out=(D, I))
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms.append(e0.elapsed_time(e1))
+        m = statistics.median(ms)
+        gbs = rows * d * 2 / m / 1e6
+        res.append({"workload": name, "ms_per_step": m, "queries_per_s": nq / m * 1e3, "GBs": gbs,
+                    "frac_of_measured_hbm": gbs / pk["hbm_gbs"], "l2": "flushed between iterations (256 MB memset)"})
+        idx.close()
+    return res
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

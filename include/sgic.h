@@ -103,9 +103,13 @@ int sgic_index_search_dev(sgic_index* h, int64_t nq, const float* dev_q, int64_t
                           int64_t* dev_I, int64_t id_base, void* stream);
 
 /* Merge of per-shard answers after the all-gather: lists laid out
- * [n_lists][nq][k]; shard g holds rows below shard g+1.  Output (nq,k). */
+ * [n_lists][nq][k], each sorted (score desc, id asc), ids global, -1 = empty slot.
+ * Output (nq,k) ordered (score desc, id asc) — identical to a single-GPU search.
+ * tie_by_position = 0: ids < 2^32 (exact for any assignment of rows to shards);
+ * tie_by_position = 1: any int64 ids, but shard g must hold rows below shard g+1. */
 int sgic_merge_topk_dev(int device, int64_t nq, int n_lists, int64_t k, const float* dev_D_lists,
-                        const int64_t* dev_I_lists, float* dev_D, int64_t* dev_I, void* stream);
+                        const int64_t* dev_I_lists, float* dev_D, int64_t* dev_I, int tie_by_position,
+                        void* stream);
 
 /* faiss.write_index / faiss.read_index — src/build.py:95,99,235,238; src/compress.py:95,111;
  * src/search.py:69,76.  File layout "IxFI" (SURVEY.md §8a F3): fp32 little-endian rows. */

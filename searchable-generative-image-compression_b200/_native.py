@@ -44,7 +44,7 @@ _SIGNATURES = {
     "sgic_index_search_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.c_void_p]),
     "sgic_merge_topk_dev": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "sgic_index_write": (C.c_int, [C.c_void_p, C.c_char_p]),
     "sgic_index_read": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "sgic_index_reconstruct": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),

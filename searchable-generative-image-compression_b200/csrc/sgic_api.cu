@@ -79,13 +79,13 @@ struct sgic_index {
   size_t odev_bytes = 0;
   void* opin = nullptr;
   size_t opin_bytes = 0;
-  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr, tm = nullptr;
   // retained fp32 rows (SGIC_RETAIN_F32)
   std::vector<float> retained;
   bool retain_ok = false;
   // options / stats
   int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0;
-  int64_t stat_launches = 0, stat_last_search_us = 0, stat_last_grid = 0, stat_last_stages = 0;
+  int64_t stat_launches = 0, stat_last_search_ns = 0, stat_last_scan_ns = 0, stat_last_grid = 0, stat_last_stages = 0;
 };
 
 namespace sgic {
@@ -346,6 +346,7 @@ static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_
     } else {
       SGIC_CUDA(cudaMemsetAsync(h->ws, 0, static_cast<size_t>(NQ) * grid * k * 8, st));
     }
+    if (h->opt_timing && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));  // first scan launch alone
     int rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nq_here, grid, static_cast<uint32_t>(k),
                                dev_D + static_cast<size_t>(q0) * k, dev_I + static_cast<size_t>(q0) * k, id_base, st);
     if (rc) return rc;
@@ -355,7 +356,9 @@ static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_
     SGIC_CUDA(cudaEventSynchronize(h->t1));
     float ms = 0.f;
     SGIC_CUDA(cudaEventElapsedTime(&ms, h->t0, h->t1));
-    h->stat_last_search_us = static_cast<int64_t>(ms * 1000.0f);
+    h->stat_last_search_ns = static_cast<int64_t>(static_cast<double>(ms) * 1e6);
+    SGIC_CUDA(cudaEventElapsedTime(&ms, h->t0, h->tm));
+    h->stat_last_scan_ns = static_cast<int64_t>(static_cast<double>(ms) * 1e6);
   }
   return 0;
 }
@@ -414,7 +417,8 @@ int sgic_index_create(int d, int dtype, int device, int64_t capacity_rows, int f
   h->sm_count = prop.multiProcessorCount;
   h->retain_ok = (flags & SGIC_RETAIN_F32) != 0;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&h->t0) != cudaSuccess || cudaEventCreate(&h->t1) != cudaSuccess) {
+      cudaEventCreate(&h->t0) != cudaSuccess || cudaEventCreate(&h->t1) != cudaSuccess ||
+      cudaEventCreate(&h->tm) != cudaSuccess) {
     set_error("stream/event creation failed");
     delete h;
     return 2;
@@ -446,6 +450,7 @@ int sgic_index_destroy(sgic_index* h) {
   if (h->db) cudaFree(h->db);
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);
+  if (h->tm) cudaEventDestroy(h->tm);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -669,7 +674,8 @@ int sgic_index_search(sgic_index* h, int64_t nq, const float* host_q, int64_t k,
 }
 
 int sgic_merge_topk_dev(int device, int64_t nq, int n_lists, int64_t k, const float* dev_D_lists,
-                        const int64_t* dev_I_lists, float* dev_D, int64_t* dev_I, void* stream) {
+                        const int64_t* dev_I_lists, float* dev_D, int64_t* dev_I, int tie_by_position,
+                        void* stream) {
   SGIC_REQUIRE(nq >= 0 && n_lists >= 1 && k >= 1, "bad arguments");
   SGIC_REQUIRE(static_cast<int64_t>(n_lists) * k < (1ll << 31), "too many candidates");
   if (nq == 0) return 0;
@@ -685,6 +691,7 @@ int sgic_merge_topk_dev(int device, int64_t nq, int n_lists, int64_t k, const fl
   chunk = std::max<uint32_t>(chunk, 64);
   SGIC_REQUIRE(static_cast<size_t>(chunk) * 8 <= kSmemBudget, "k too large for the merge kernel");
   mp.chunk = chunk;
+  mp.tie_by_position = tie_by_position ? 1u : 0u;
   mp.D = dev_D;
   mp.I = reinterpret_cast<long long*>(dev_I);
   const size_t smem = static_cast<size_t>(chunk) * 8;
@@ -851,7 +858,8 @@ int64_t sgic_index_get_stat(const sgic_index* h, const char* name) {
   if (!h || !name) return -1;
   const std::string n(name);
   if (n == "launches") return h->stat_launches;
-  if (n == "last_search_us") return h->stat_last_search_us;
+  if (n == "last_search_ns") return h->stat_last_search_ns;
+  if (n == "last_scan_ns") return h->stat_last_scan_ns;
   if (n == "last_grid") return h->stat_last_grid;
   if (n == "last_stages") return h->stat_last_stages;
   if (n == "capacity") return h->capacity;

@@ -107,10 +107,11 @@ __global__ void __launch_bounds__(1024, 1) merge_keys_kernel(MergeKeysParams p) 
 
 // ------------------------------------------------------------------ K5: merge of per-shard answers
 // D_lists / I_lists: [n_lists][nq][k] as an all-gather of each rank's (nq,k) answer lays
-// them out.  Shards hold ascending, disjoint row ranges and each list is ordered (score
-// desc, id asc), so the position g*k+j is a valid tie-break: ordering by (score desc,
-// position asc) equals (score desc, global id asc) and the G-GPU answer is identical to
-// the 1-GPU answer.
+// them out.  Ordering is (score desc, global id asc) so that the G-GPU answer is identical to
+// the 1-GPU answer.  tie_by_position == 0: ids < 2^32, the id itself is the low key word.
+// tie_by_position == 1 (ids may exceed 32 bits): shards must hold ascending, disjoint row
+// ranges; each list is already ordered (score desc, id asc), so the position g*k+j orders ties
+// exactly like the global id does.
 struct MergeListsParams {
   const float* D_lists;
   const long long* I_lists;
@@ -118,6 +119,7 @@ struct MergeListsParams {
   uint32_t nq;
   uint32_t k;
   uint32_t chunk;
+  uint32_t tie_by_position;
   float* D;
   long long* I;
 };
@@ -135,7 +137,8 @@ __global__ void __launch_bounds__(1024, 1) merge_lists_kernel(MergeListsParams p
       if (i < take) {
         const uint32_t e = pos + i, g = e / p.k, j = e - g * p.k;
         const size_t o = (static_cast<size_t>(g) * p.nq + q) * p.k + j;
-        if (p.I_lists[o] >= 0) key = make_key(p.D_lists[o], e);
+        const long long id = p.I_lists[o];
+        if (id >= 0) key = make_key(p.D_lists[o], p.tie_by_position ? e : static_cast<uint32_t>(id));
       }
       ml_smem[carry + i] = key;
     }
@@ -150,11 +153,14 @@ __global__ void __launch_bounds__(1024, 1) merge_lists_kernel(MergeListsParams p
     if (key == 0ull) {
       p.D[out] = kNegFltMax;
       p.I[out] = -1;
-    } else {
+    } else if (p.tie_by_position) {
       const uint32_t e = key_id(key), g = e / p.k, j = e - g * p.k;
       const size_t o = (static_cast<size_t>(g) * p.nq + q) * p.k + j;
       p.D[out] = p.D_lists[o];
       p.I[out] = p.I_lists[o];
+    } else {
+      p.D[out] = key_score(key);
+      p.I[out] = static_cast<long long>(key_id(key));
     }
   }
 }

@@ -1,0 +1,170 @@
+"""Row-sharded index over the GPUs of one box (north-star item (c)).
+
+One process per GPU (``torchrun``); every rank holds a slice of the rows in its own HBM as a
+:class:`faiss_compat.IndexFlatIP`.  A search is: queries replicated on every rank → local
+top-k on each GPU (K3/K4) with global row numbers → ONE ``all_gather`` of the packed
+``(nq, k)`` candidates (NCCL over NVLink; 12·nq·k bytes per rank) → on-device merge
+``G·k → k`` (K5, ``sgic_merge_topk_dev``) ordered by (score desc, global id asc), so the
+G-GPU answer is identical to the 1-GPU answer.  There is no other collective on the path.
+
+The reference has no multi-GPU retrieval (its only ``torch.distributed`` use shards the image
+encoder over files, src/compress.py:34-55,293-306, with rank 0 building the index serially);
+this class is the additive surface the north star asks for and keeps the faiss names.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+from . import _native
+from .faiss_compat import Index, IndexFlatIP, _torch_stream
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range of ``rank`` when ``n`` rows are split over ``world`` ranks:
+    ``[rank*ceil(n/world), min(n, (rank+1)*ceil(n/world)))``."""
+    per = -(-n // world) if n > 0 else 0
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def _merge_cuda(D_lists, I_lists, k: int, by_position: bool):
+    """K5 through the C ABI.  ``D_lists``/``I_lists``: (G, nq, k) CUDA tensors."""
+    import torch
+    G, nq, _ = D_lists.shape
+    D = torch.empty((nq, k), dtype=torch.float32, device=D_lists.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=D_lists.device)
+    lib = _native.lib()
+    _native.check(lib.sgic_merge_topk_dev(D_lists.device.index, nq, G, k,
+                                          C.c_void_p(D_lists.data_ptr()), C.c_void_p(I_lists.data_ptr()),
+                                          C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()),
+                                          1 if by_position else 0, _torch_stream(D_lists.device)))
+    return D, I
+
+
+class ShardedIndexFlatIP(Index):
+    """``IndexFlatIP`` whose rows are spread over the ranks of a ``torch.distributed`` group.
+
+    Every method is collective: all ranks call it with the same arguments (``add`` /
+    ``search`` take the same arrays on every rank, as replicated queries do).
+    ``local_factory`` / ``merge_fn`` exist so that the host logic can be exercised on CPU
+    (gloo) with stand-ins; the product path uses the CUDA defaults.
+    """
+
+    def __init__(self, d: int, *, dtype="fp16", group=None, device: Optional[int] = None,
+                 local_factory: Optional[Callable] = None, merge_fn: Optional[Callable] = None):
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedIndexFlatIP needs torch.distributed to be initialised (torchrun)")
+        self._dist = dist
+        self._group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._d = int(d)
+        self._cuda = dist.get_backend(group) == "nccl"
+        if self._cuda:
+            dev = torch.cuda.current_device() if device is None else int(device)
+            self._dev = torch.device("cuda", dev)
+        else:
+            dev = None
+            self._dev = torch.device("cpu")
+        self.local = local_factory(d) if local_factory else IndexFlatIP(d, dtype=dtype, device=dev, retain_fp32=False)
+        self._merge = merge_fn or _merge_cuda
+        # segments of this rank: (global_start, local_start, count), ascending in both
+        self._segments: List[Tuple[int, int, int]] = []
+        self._ntotal = 0
+
+    # ---------------------------------------------------------------- faiss attributes
+    @property
+    def d(self) -> int:
+        return self._d
+
+    @property
+    def ntotal(self) -> int:
+        return self._ntotal
+
+    @property
+    def local_ntotal(self) -> int:
+        return self.local.ntotal
+
+    # ---------------------------------------------------------------- add
+    def _note_segment(self, global_start: int, count: int) -> None:
+        if count <= 0:
+            return
+        local_start = self.local.ntotal - count
+        if self._segments and self._segments[-1][0] + self._segments[-1][2] == global_start:
+            g0, l0, c0 = self._segments[-1]
+            self._segments[-1] = (g0, l0, c0 + count)
+        else:
+            self._segments.append((global_start, local_start, count))
+
+    def add(self, x) -> None:
+        """Same ``x`` (n, d) on every rank; rank g keeps the g-th contiguous slice."""
+        x = np.ascontiguousarray(x, dtype="float32")
+        assert x.ndim == 2 and x.shape[1] == self._d
+        lo, hi = shard_range(x.shape[0], self.world, self.rank)
+        if hi > lo:
+            self.local.add(x[lo:hi])
+        self._note_segment(self._ntotal + lo, hi - lo)
+        self._ntotal += x.shape[0]
+
+    def add_local(self, adder: Callable[[IndexFlatIP], None], global_start: int, count: int, total: int) -> None:
+        """Loader path: ``adder(local_index)`` appends this rank's ``count`` rows (by any of the
+        local index's add_* methods); they are global rows ``[global_start, global_start+count)``
+        of a block of ``total`` rows appended collectively."""
+        before = self.local.ntotal
+        adder(self.local)
+        assert self.local.ntotal - before == count, "adder appended a different number of rows"
+        self._note_segment(self._ntotal + global_start, count)
+        self._ntotal += total
+
+    # ---------------------------------------------------------------- search
+    def _to_global(self, I_local):
+        """local row numbers → global row numbers (identity + base for a single segment)."""
+        import torch
+        if len(self._segments) <= 1:
+            base = self._segments[0][0] - self._segments[0][1] if self._segments else 0
+            return torch.where(I_local >= 0, I_local + base, I_local) if base else I_local
+        l_starts = torch.tensor([s[1] for s in self._segments], dtype=torch.int64, device=I_local.device)
+        offs = torch.tensor([s[0] - s[1] for s in self._segments], dtype=torch.int64, device=I_local.device)
+        seg = torch.bucketize(I_local.clamp(min=0), l_starts, right=True) - 1
+        return torch.where(I_local >= 0, I_local + offs[seg], I_local)
+
+    def search_torch(self, q, k: int):
+        """``q``: fp32 (nq, d) tensor on this rank's device, identical on every rank.
+        Returns device tensors (D, I), identical on every rank."""
+        import torch
+        assert k > 0
+        nq = q.shape[0]
+        if len(self._segments) == 1 and self._cuda:
+            base = self._segments[0][0] - self._segments[0][1]
+            D, I = self.local.search_torch(q, k, id_base=base)        # id_base folded into the merge kernel
+        else:
+            D, I = self.local.search_torch(q, k)
+            I = self._to_global(I)
+        if self.world == 1:
+            return D, I
+        # pack (ids, scores) into one buffer so that the exchange is a single all_gather
+        packed = torch.empty((nq, k, 3), dtype=torch.int32, device=q.device)
+        packed[..., :2] = I.view(torch.int32).view(nq, k, 2)
+        packed[..., 2] = D.view(torch.int32)
+        gathered = torch.empty((self.world * nq, k, 3), dtype=torch.int32, device=q.device)
+        self._dist.all_gather_into_tensor(gathered, packed, group=self._group)
+        gathered = gathered.view(self.world, nq, k, 3)
+        I_lists = gathered[..., :2].contiguous().view(torch.int64).view(self.world, nq, k)
+        D_lists = gathered[..., 2].contiguous().view(torch.float32)
+        contiguous_shards = self._ntotal >= (1 << 32)   # ids beyond 32 bits: tie-break by shard position
+        return self._merge(D_lists, I_lists, k, contiguous_shards)
+
+    def search(self, x, k: int):
+        """faiss signature: host fp32 (nq, d) in, host (D, I) out — on every rank."""
+        import torch
+        x = np.ascontiguousarray(x, dtype="float32")
+        assert x.ndim == 2 and x.shape[1] == self._d, "search expects (n, d)"
+        assert k > 0, "k must be positive"
+        q = torch.from_numpy(x).to(self._dev, non_blocking=False)
+        D, I = self.search_torch(q, k)
+        return D.cpu().numpy(), I.cpu().numpy()

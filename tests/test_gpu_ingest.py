@@ -1,0 +1,186 @@
+"""GPU tests of the ingest side (K1 dequant+normalise, K2 fp32 pack, batched .c2df ingest) and
+of the file formats / glue either side of the search call, all through the C ABI."""
+import io
+import json
+import contextlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import c2df_ref
+from oracle.flat_ip import check_topk
+
+
+def fp16_ulp_diff(a, b):
+    """Distance in fp16 ulps between two fp32 arrays holding fp16-representable values."""
+    ia = a.astype(np.float16).view(np.int16).astype(np.int32)
+    ib = b.astype(np.float16).view(np.int16).astype(np.int32)
+    ia = np.where(ia < 0, -32768 - ia, ia)
+    ib = np.where(ib < 0, -32768 - ib, ib)
+    return np.abs(ia - ib)
+
+
+def test_add_f32_rounds_to_nearest_even_fp16_and_bf16():
+    import torch
+    from sgic_b200 import faiss_compat as faiss
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((1000, 512)).astype(np.float32)
+    idx = faiss.IndexFlatIP(512, device=0)
+    idx.add(x)
+    assert np.array_equal(idx.reconstruct_n(0, 1000), x.astype(np.float16).astype(np.float32))   # bit-exact
+    assert np.array_equal(idx.reconstruct(17), x[17].astype(np.float16).astype(np.float32))
+    idb = faiss.IndexFlatIP(512, device=0, dtype="bf16")
+    idb.add(x)
+    assert np.array_equal(idb.reconstruct_n(0, 1000), torch.from_numpy(x).bfloat16().float().numpy())
+
+
+def test_add_u8_matches_dequantize_clip_u8():
+    from sgic_b200 import faiss_compat as faiss
+    rng = np.random.default_rng(1)
+    for d in (512, 768, 64):
+        q = rng.integers(0, 256, size=(4000, d), dtype=np.uint8)
+        q[0] = 0; q[1] = 255; q[2] = 128                       # extreme rows
+        idx = faiss.IndexFlatIP(d, device=0)
+        idx.add_u8(q)
+        got = idx.reconstruct_n(0, q.shape[0])
+        want = c2df_ref.dequantize_clip_u8(q)                  # fp32, reference operation order
+        ulp = fp16_ulp_diff(got, want)
+        # fp32 sum-of-squares order differs from numpy's pairwise sum: allow 1 fp16 ulp on a few elements
+        assert ulp.max() <= 1 and (ulp > 0).mean() < 2e-3, (ulp.max(), (ulp > 0).mean())
+        assert np.abs(got - want).max() < 6e-4
+
+
+def test_add_c2df_batch_and_skip_semantics(golden):
+    from sgic_b200 import faiss_compat as faiss
+    g = np.load(golden / "c2df_golden.npz")
+    # good files of mixed dimension followed by every malformed file
+    blob = np.concatenate([g["good_blob"], g["bad_blob"]])
+    offs = np.concatenate([g["good_offsets"], g["bad_offsets"][1:] + g["good_offsets"][-1]])
+    idx = faiss.IndexFlatIP(512, device=0)
+    added, status = idx.add_c2df(blob, offs, n_threads=3)
+    dims = g["good_dims"]
+    n_good512 = int((dims == 512).sum())
+    n_ok_bad = int((g["bad_classes"] == "OK").sum())          # dim given as "512" / 512.0 decode fine upstream
+    assert added == n_good512 + n_ok_bad == idx.ntotal
+    assert list(status[:len(dims)]) == [0 if d == 512 else 7 for d in dims]
+    rows = idx.reconstruct_n(0, n_good512)
+    pos = 0
+    k = 0
+    for d in dims:
+        if d == 512:
+            want = g["good_vecs"][pos:pos + d]
+            assert fp16_ulp_diff(rows[k], want).max() <= 1
+            k += 1
+        pos += d
+
+
+def test_write_index_is_bit_identical_to_the_shipped_faiss_file(golden, tmp_path):
+    """KAT-2 through the product: FaissDB.add(npy) + persist == IO/faiss/{index.faiss, ids.txt}."""
+    from sgic_b200.index_build import FaissDB
+    db = FaissDB(str(tmp_path), 512, device=0)
+    db.add(np.load(golden / "apple.npy"), "../IO/bitstreams/apple.c2df")
+    db.persist()
+    assert (tmp_path / "index.faiss").read_bytes() == (golden / "index.faiss").read_bytes()
+    assert (tmp_path / "ids.txt").read_bytes() == (golden / "ids.txt").read_bytes()
+    # resume: reopen, append, persist (compress.py:94-101) — no de-duplication, as upstream
+    db2 = FaissDB(str(tmp_path), 512, device=0)
+    assert db2.index.ntotal == 1 and db2.ids == ["../IO/bitstreams/apple.c2df"]
+    db2.add(np.load(golden / "apple.npy"), "dup")
+    db2.persist()
+    x = c2df_ref.read_ixfi(tmp_path / "index.faiss")
+    assert x.shape == (2, 512) and np.array_equal(x[0], x[1])
+
+
+def test_kat3_kat4_kat6_through_load_index_and_do_search(golden, tmp_path):
+    from sgic_b200 import retrieval
+    for name in ("index.faiss", "ids.txt"):
+        (tmp_path / name).write_bytes((golden / name).read_bytes())
+    index, paths, meta = retrieval.load_index(tmp_path)
+    assert index.ntotal == 1 and index.d == 512 and paths == ["../IO/bitstreams/apple.c2df"] and meta == {"dim": 512}
+    res = retrieval.do_search(np.load(golden / "apple.npy")[None, :], index, paths, topk=10)   # KAT-6: k clamps to 1
+    assert len(res) == 1 and res[0][0] == "../IO/bitstreams/apple.c2df" and abs(res[0][1] - 1.0) < 1e-3
+    res = retrieval.do_search(retrieval.encode_c2df_query(golden / "apple.c2df"), index, paths, topk=10)
+    assert res[0][0] == "../IO/bitstreams/apple.c2df" and abs(res[0][1] - 0.9987136) < 1e-3
+    with pytest.raises(FileNotFoundError):
+        retrieval.load_index(tmp_path / "nope")
+
+
+def _write_corpus(dirpath, vecs, rng):
+    from sgic_b200 import c2df as c2
+    from sgic_b200.index_build import quantize_u8_and_compress
+    (dirpath / "sub").mkdir(parents=True)
+    names = []
+    for i, v in enumerate(vecs):
+        stream, meta = quantize_u8_and_compress(v)
+        enc = {"z_bit_stream": rng.integers(0, 256, 100, dtype=np.uint8).tobytes(), "token_length": 512,
+               "clip_stream": stream, "clip_meta": meta}
+        header = {"version": 2, "model_id": "ViT-B-32:laion2b_s34b_b79k", "embed_dim": int(v.shape[0])}
+        p = dirpath / ("sub" if i % 3 == 0 else "") / f"img_{i:04d}.c2df"
+        p.write_bytes(c2.pack_c2df(enc, header))
+        names.append(p)
+    return names
+
+
+def test_build_index_from_c2df_dir_and_cli(tmp_path, capsys):
+    from sgic_b200 import index_build, retrieval
+    rng = np.random.default_rng(7)
+    vecs = rng.standard_normal((40, 512)).astype(np.float32)
+    vecs /= np.linalg.norm(vecs, axis=1, keepdims=True)
+    src = tmp_path / "bitstreams"
+    src.mkdir()
+    files = _write_corpus(src, vecs, rng)
+    (src / "broken.c2df").write_bytes(b"XXXXnot a container")
+    (src / "noclip.c2df").write_bytes(__import__("sgic_b200").c2df.pack_c2df({"token_length": 1}, {"version": 2}))
+    out = tmp_path / "faiss"
+    index_build.build_index_from_c2df_dir(src, out)
+    log = capsys.readouterr().out
+    assert "[SKIP] broken.c2df" in log and "[SKIP] noclip.c2df" in log and "[OK] Index process completed!: N=40, dim=512" in log
+    want_paths = [str(p) for p in sorted(src.glob("**/*.c2df")) if p.name not in ("broken.c2df", "noclip.c2df")]
+    assert json.loads((out / "paths.json").read_text()) == want_paths
+    assert (out / "ids.txt").read_text() == "\n".join(want_paths)                  # no trailing newline (build.py:100)
+    assert json.loads((out / "meta.json").read_text()) == {"dim": 512, "model_id": "ViT-B-32:laion2b_s34b_b79k"}
+    assert (out / "faiss.index").read_bytes() == (out / "index.faiss").read_bytes()
+    # both naming schemes load; the preferred one carries meta.json
+    index, paths, meta = retrieval.load_index(out)
+    assert index.ntotal == 40 and meta["model_id"].startswith("ViT-B-32")
+    # query with one of the bitstreams: it must come back first with score ~1
+    target = want_paths[5]
+    res = retrieval.do_search(retrieval.encode_c2df_query(target), index, paths, topk=5)
+    assert res[0][0] == target and abs(res[0][1] - 1.0) < 1e-3 and len(res) == 5
+    # row order == sorted path order: compare every stored row with the oracle decode
+    rows = index.reconstruct_n(0, 40)
+    for i, p in enumerate(want_paths):
+        _, z = c2df_ref.decode_clip(open(p, "rb").read())
+        assert np.abs(rows[i] - z).max() < 6e-4
+    # CLI: stdout is exactly the JSON document webapp.py:249 parses
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        retrieval.main(["query-c2df", "--index_dir", str(out), "--c2df", target, "--topk", "3"])
+    doc = json.loads(buf.getvalue())
+    assert [set(e) for e in doc] == [{"path", "score"}] * 3 and doc[0]["path"] == target
+    assert buf.getvalue() == json.dumps(doc, ensure_ascii=False, indent=2) + "\n"
+    # legacy naming only
+    legacy = tmp_path / "legacy"
+    legacy.mkdir()
+    for n in ("index.faiss", "ids.txt"):
+        (legacy / n).write_bytes((out / n).read_bytes())
+    index2, paths2, meta2 = retrieval.load_index(legacy)
+    assert paths2 == want_paths and meta2 == {"dim": 512, "model_id": "ViT-B-32:laion2b_s34b_b79k"}
+
+
+def test_from_npy_dir_matches_sorted_glob_order(tmp_path):
+    from sgic_b200 import index_build
+    rng = np.random.default_rng(9)
+    vecs = rng.standard_normal((25, 512)).astype(np.float32)
+    (tmp_path / "clip_vecs").mkdir()
+    for i, v in enumerate(vecs):
+        np.save(tmp_path / "clip_vecs" / f"im{(i * 7) % 25:03d}.npy", v)
+    db = index_build.from_npy_dir(tmp_path / "clip_vecs", "../IO/bitstreams", tmp_path / "faiss", device=0)
+    assert db.index.ntotal == 25
+    assert db.ids[0] == "../IO/bitstreams/im000.c2df" and db.ids == sorted(db.ids)
+    x = c2df_ref.read_ixfi(tmp_path / "faiss" / "index.faiss")
+    order = sorted(range(25), key=lambda i: f"im{(i * 7) % 25:03d}")
+    want = vecs[order] / (np.linalg.norm(vecs[order], axis=1, keepdims=True) + 1e-12)
+    assert np.array_equal(x, want.astype(np.float32))         # fp32 rows kept bit-exact on disk
