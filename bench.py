@@ -66,46 +66,63 @@ def peaks():
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """`nvidia-smi` polled every 50 ms in the background; samples are kept with their timestamps and
+    only those taken inside the timed regions are summarised (the recipe's clocks line)."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
+        self.windows = []
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
-            pass
+            return
+        t_end = time.time() + 5.0
+        while time.time() < t_end and os.path.getsize(self.tmp.name) == 0:   # first sample is in
+            time.sleep(0.05)
+
+    def begin(self):
+        self._t0 = time.time()
+
+    def end(self):
+        self.windows.append((self._t0, time.time()))
 
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        self.tmp.flush()
         rows = [ln.strip().split(",") for ln in open(self.tmp.name) if ln.strip()]
         os.unlink(self.tmp.name)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if self.windows and not any(a - 0.05 <= ts <= b + 0.05 for a, b in self.windows):
+                    continue
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                pw.append(float(r[3]))
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(names, r[3:7]):
+            for name, v in zip(names, r[4:8]):
                 if v.strip().lower().startswith("active"):
                     reasons.add(name)
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw))
         return out
 
 
@@ -228,11 +245,13 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput ---------------------------------------------------------
+    clk = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         search_dev(q)
     barrier()
     launches0 = local.stat("launches")
-    clk = ClockSampler(local_rank) if rank == 0 else None
+    if clk:
+        clk.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -240,7 +259,8 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    clocks = clk.stop() if clk else None
+    if clk:
+        clk.end()
     launches = local.stat("launches") - launches0 + (args.steps if world > 1 else 0)   # + K5 merge per step
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -253,11 +273,15 @@ def run_ours(args):
     for _ in range(min(args.warmup, 3)):
         search_host(qh)
     barrier()
+    if clk:
+        clk.begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         Dh, Ih = search_host(qh)
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
+    if clk:
+        clk.end()
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -270,6 +294,7 @@ def run_ours(args):
         search_dev(q)
         scan_ns.append(local.stat("last_scan_ns"))
     local.set_option("timing", 0)
+    clocks = clk.stop() if clk else None
     scan_ms = statistics.mean(scan_ns) / 1e6
     alg_bytes = n_local * d * 2
     achieved = alg_bytes / (scan_ms / 1e3) / 1e9

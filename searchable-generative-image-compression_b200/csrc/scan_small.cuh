@@ -33,6 +33,12 @@ struct ScanSmallParams {
   uint32_t n_stages;
   uint32_t stage_bytes;  // R * d * 2 rounded up to 128
   uint32_t evict_first;  // L2 policy for the database stream
+  // fused final merge: the last CTA to finish merges every CTA's list and writes the answer
+  uint32_t fused;        // 0: partial lists only (merge_keys_kernel follows)
+  uint32_t* counter;     // zero on entry, reset to zero by the last CTA
+  float* D;              // [nq][k]
+  long long* I;          // [nq][k]
+  long long id_base;
 };
 
 template <typename T>
@@ -216,6 +222,32 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanS
     uint64_t* dst = p.partial + (static_cast<size_t>(qi) * gridDim.x + blockIdx.x) * p.k;
     for (uint32_t i = tid; i < p.k; i += kScanThreads) dst[i] = Lq[i];
   }
+  if (!p.fused) return;
+
+  // ---------------------------------------------------------------- fused grid-level merge
+  // "last block done": every CTA publishes its lists, bumps a counter; the CTA that sees the final
+  // count stages all lists in shared memory (the stage ring is free now) and one warp per query
+  // runs the multiway merge.  Saves the second kernel launch on the latency-critical small scans.
+  __shared__ uint32_t s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  uint64_t* all = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t per_q = gridDim.x * p.k;
+  for (uint32_t i = tid; i < p.nq * per_q; i += kScanThreads) all[i] = __ldcg(p.partial + i);
+  __syncthreads();
+  if (warp < static_cast<int>(p.nq)) {
+    float* D = p.D;
+    long long* I = p.I;
+    const size_t o0 = static_cast<size_t>(warp) * p.k;
+    const long long base = p.id_base;
+    warp_multiway_merge<kMergeMaxLpl>(all + static_cast<size_t>(warp) * per_q, gridDim.x, p.k, p.k, lane,
+                                      [=](uint32_t r, uint64_t key) { store_answer(D, I, o0 + r, key, base); });
+  }
+  if (tid == 0) *p.counter = 0u;
 }
 
 }  // namespace sgic

@@ -71,7 +71,8 @@ struct sgic_index {
   void* dstage[2] = {nullptr, nullptr};
   cudaEvent_t ev[2] = {nullptr, nullptr};
   // search workspaces
-  void* ws = nullptr;  // partial keys
+  void* ws = nullptr;  // partial keys (+ the fused merge's CTA counter)
+  uint32_t* ws_counter = nullptr;
   size_t ws_bytes = 0;
   void* qdev = nullptr;  // queries / outputs for the host-buffer search
   size_t qdev_bytes = 0;
@@ -84,7 +85,7 @@ struct sgic_index {
   std::vector<float> retained;
   bool retain_ok = false;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1;
   int64_t stat_launches = 0, stat_last_search_ns = 0, stat_last_scan_ns = 0, stat_last_grid = 0, stat_last_stages = 0;
 };
 
@@ -265,6 +266,17 @@ static int launch_merge_keys(sgic_index* h, const uint64_t* partial, uint32_t nq
   mp.D = D;
   mp.I = reinterpret_cast<long long*>(I);
   mp.id_base = id_base;
+  const size_t all_bytes = static_cast<size_t>(n_lists) * k * 8;
+  if (n_lists <= 32u * kMergeMaxLpl && all_bytes <= 200u * 1024) {
+    // every list fits in shared memory: multiway merge by one warp (k short rounds)
+    if (all_bytes > 48 * 1024)
+      SGIC_CUDA(cudaFuncSetAttribute(merge_keys_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(all_bytes)));
+    merge_keys_small_kernel<<<nq, 128, all_bytes, st>>>(mp);
+    h->stat_launches++;
+    SGIC_CUDA(cudaGetLastError());
+    return 0;
+  }
   const size_t smem = static_cast<size_t>(chunk) * 8;
   if (smem > 48 * 1024)
     SGIC_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -311,11 +323,21 @@ static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_
   h->stat_last_grid = grid;
   h->stat_last_stages = stages;
 
-  const size_t ws_need = static_cast<size_t>(NQ) * grid * static_cast<size_t>(k) * 8;
+  // fused grid-level merge (last CTA) when all partial lists fit in the freed stage ring
+  const size_t partial_bytes = static_cast<size_t>(NQ) * grid * static_cast<size_t>(k) * 8;
+  const bool fused = h->opt_fused && n_rows > 0 && grid <= 32u * kMergeMaxLpl &&
+                     partial_bytes <= static_cast<size_t>(stages) * stage_bytes && NQ <= kScanConsumerWarps;
+  const size_t ws_need = partial_bytes + 16;  // + the "CTAs done" counter behind the lists
   if (ws_need > h->ws_bytes) {
     SGIC_CUDA(cudaStreamSynchronize(st));
     int rc = ensure_buf(&h->ws, &h->ws_bytes, ws_need, false);
     if (rc) return rc;
+    h->ws_counter = nullptr;
+  }
+  uint32_t* counter = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(h->ws) + ((partial_bytes + 7) & ~size_t(7)));
+  if (h->ws_counter != counter) {  // (re)allocated or a different layout: zero the counter once
+    SGIC_CUDA(cudaMemsetAsync(counter, 0, 8, st));
+    h->ws_counter = counter;
   }
 
   if (h->opt_timing) SGIC_CUDA(cudaEventRecord(h->t0, st));
@@ -334,6 +356,11 @@ static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_
     p.n_stages = stages;
     p.stage_bytes = stage_bytes;
     p.evict_first = h->opt_evict_first ? 1u : 0u;
+    p.fused = fused ? 1u : 0u;
+    p.counter = counter;
+    p.D = dev_D + static_cast<size_t>(q0) * k;
+    p.I = reinterpret_cast<long long*>(dev_I + static_cast<size_t>(q0) * k);
+    p.id_base = id_base;
     cudaError_t e;
     if (n_rows > 0) {
       if (h->dtype == SGIC_F16) e = launch_scan_t<__half>(p, NQ, cfg.cpl, cfg.rb, grid, smem, st);
@@ -347,6 +374,7 @@ static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_
       SGIC_CUDA(cudaMemsetAsync(h->ws, 0, static_cast<size_t>(NQ) * grid * k * 8, st));
     }
     if (h->opt_timing && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));  // first scan launch alone
+    if (fused) continue;
     int rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nq_here, grid, static_cast<uint32_t>(k),
                                dev_D + static_cast<size_t>(q0) * k, dev_I + static_cast<size_t>(q0) * k, id_base, st);
     if (rc) return rc;
@@ -841,6 +869,7 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "grid") h->opt_grid = value;
   else if (n == "stages") h->opt_stages = value;
   else if (n == "rb") h->opt_rb = value;
+  else if (n == "fused") h->opt_fused = value;
   else if (n == "drop_retained") {
     std::lock_guard<std::mutex> lk(h->mu);
     h->retain_ok = false;

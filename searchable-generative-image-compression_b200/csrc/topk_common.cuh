@@ -63,6 +63,66 @@ __device__ __forceinline__ uint64_t warp_list_insert(uint64_t* L, int k, uint64_
   return L[k - 1];
 }
 
+// Writes one answer slot from a key (0 = empty slot -> faiss padding).
+__device__ __forceinline__ void store_answer(float* D, long long* I, size_t o, uint64_t key, long long id_base) {
+  if (key == 0ull) {
+    D[o] = kNegFltMax;
+    I[o] = -1;
+  } else {
+    D[o] = key_score(key);
+    I[o] = id_base + static_cast<long long>(key_id(key));
+  }
+}
+
+// One warp merges `n_lists` (<= 32*MAXLPL) lists, each sorted largest-first and `len` keys long
+// (list l at lists[l*len]), into the `k_out` largest keys overall, handed to emit(rank, key) by
+// lane 0 in rank order.  A multiway merge over the list heads: per output one register max per
+// lane, a 5-step warp max, and one list advance by the owning lane — k_out short rounds instead
+// of sorting n_lists*len candidates.  Keys are unique (the id is part of the key).
+template <int MAXLPL, typename Emit>
+__device__ __forceinline__ void warp_multiway_merge(const uint64_t* lists, uint32_t n_lists, uint32_t len,
+                                                    uint32_t k_out, int lane, Emit emit) {
+  uint64_t head[MAXLPL];
+  uint32_t pos[MAXLPL];
+#pragma unroll
+  for (int j = 0; j < MAXLPL; ++j) {
+    const uint32_t l = lane + 32 * j;
+    head[j] = (l < n_lists && len > 0) ? lists[static_cast<size_t>(l) * len] : 0ull;
+    pos[j] = 0;
+  }
+  for (uint32_t r = 0; r < k_out; ++r) {
+    uint64_t best = head[0];
+    int bj = 0;
+#pragma unroll
+    for (int j = 1; j < MAXLPL; ++j)
+      if (head[j] > best) {
+        best = head[j];
+        bj = j;
+      }
+    uint64_t w = best;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const uint64_t o = __shfl_xor_sync(0xffffffffu, w, off);
+      w = (o > w) ? o : w;
+    }
+    if (lane == 0) emit(r, w);
+    if (w == 0ull) {  // every list exhausted: the rest is padding
+      for (uint32_t r2 = r + 1 + lane; r2 < k_out; r2 += 32) emit(r2, 0ull);
+      break;
+    }
+    if (best == w) {
+#pragma unroll
+      for (int j = 0; j < MAXLPL; ++j)
+        if (bj == j) {
+          const uint32_t l = lane + 32 * j;
+          ++pos[j];
+          head[j] = (pos[j] < len) ? lists[static_cast<size_t>(l) * len + pos[j]] : 0ull;
+        }
+    }
+  }
+}
+constexpr int kMergeMaxLpl = 5;  // lists per lane: up to 160 lists (one per SM of a 148-SM grid)
+
 // ------------------------------------------------------------------ final merge (per-CTA partials)
 // partial: [nq][n_lists][k] keys (score, local id).  One CTA per query.  Keys are pulled
 // through shared memory in chunks of at most `chunk` (power of two) keys; each chunk is
@@ -105,6 +165,25 @@ __global__ void __launch_bounds__(1024, 1) merge_keys_kernel(MergeKeysParams p) 
   }
 }
 
+// Fast path of the above when n_lists <= 160 and all lists fit in shared memory: stage the lists
+// with one coalesced pass, then one warp runs the multiway merge (k short rounds).
+__global__ void __launch_bounds__(128, 1) merge_keys_small_kernel(MergeKeysParams p) {
+  extern __shared__ __align__(16) uint64_t ms_smem[];
+  const uint32_t q = blockIdx.x, tid = threadIdx.x;
+  const uint64_t* src = p.partial + static_cast<size_t>(q) * p.n_lists * p.k;
+  const uint32_t n_total = p.n_lists * p.k;
+  for (uint32_t i = tid; i < n_total; i += blockDim.x) ms_smem[i] = __ldcg(src + i);
+  __syncthreads();
+  if (tid < 32) {
+    float* D = p.D;
+    long long* I = p.I;
+    const size_t o0 = static_cast<size_t>(q) * p.k;
+    const long long base = p.id_base;
+    warp_multiway_merge<kMergeMaxLpl>(ms_smem, p.n_lists, p.k, p.k, static_cast<int>(tid),
+                                      [=](uint32_t r, uint64_t key) { store_answer(D, I, o0 + r, key, base); });
+  }
+}
+
 // ------------------------------------------------------------------ K5: merge of per-shard answers
 // D_lists / I_lists: [n_lists][nq][k] as an all-gather of each rank's (nq,k) answer lays
 // them out.  Ordering is (score desc, global id asc) so that the G-GPU answer is identical to
@@ -128,6 +207,36 @@ __global__ void __launch_bounds__(1024, 1) merge_lists_kernel(MergeListsParams p
   extern __shared__ __align__(16) uint64_t ml_smem[];
   const uint32_t q = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const uint32_t n_total = p.n_lists * p.k;
+  if (n_total <= p.chunk && p.n_lists <= 32u * kMergeMaxLpl) {
+    // fast path: all candidates fit in shared memory -> stage the keys, one warp merges the heads
+    for (uint32_t e = tid; e < n_total; e += nt) {
+      const uint32_t g = e / p.k, j = e - g * p.k;
+      const size_t o = (static_cast<size_t>(g) * p.nq + q) * p.k + j;
+      const long long id = p.I_lists[o];
+      ml_smem[e] = (id >= 0) ? make_key(p.D_lists[o], p.tie_by_position ? e : static_cast<uint32_t>(id)) : 0ull;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const MergeListsParams pp = p;
+      warp_multiway_merge<kMergeMaxLpl>(ml_smem, p.n_lists, p.k, p.k, static_cast<int>(tid),
+                                        [=](uint32_t r, uint64_t key) {
+                                          const size_t out = static_cast<size_t>(q) * pp.k + r;
+                                          if (key == 0ull) {
+                                            pp.D[out] = kNegFltMax;
+                                            pp.I[out] = -1;
+                                          } else if (pp.tie_by_position) {
+                                            const uint32_t e = key_id(key), g = e / pp.k, j = e - g * pp.k;
+                                            const size_t o = (static_cast<size_t>(g) * pp.nq + q) * pp.k + j;
+                                            pp.D[out] = pp.D_lists[o];
+                                            pp.I[out] = pp.I_lists[o];
+                                          } else {
+                                            pp.D[out] = key_score(key);
+                                            pp.I[out] = static_cast<long long>(key_id(key));
+                                          }
+                                        });
+    }
+    return;
+  }
   uint32_t carry = 0, pos = 0;
   while (pos < n_total) {
     const uint32_t take = min(p.chunk - carry, n_total - pos);
