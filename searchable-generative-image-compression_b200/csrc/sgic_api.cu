@@ -1,5 +1,6 @@
 // C-ABI implementation (include/sgic.h): index object, HBM database, ingest, search dispatch,
 // IxFI (de)serialisation.  Host logic only; the kernels live in the .cuh files next to this.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -11,6 +12,7 @@
 
 #include "../../include/sgic.h"
 #include "ingest.cuh"
+#include "scan_dense.cuh"
 #include "scan_small.cuh"
 #include "topk_common.cuh"
 
@@ -74,6 +76,10 @@ struct sgic_index {
   void* ws = nullptr;  // partial keys (+ the fused merge's CTA counter)
   uint32_t* ws_counter = nullptr;
   size_t ws_bytes = 0;
+  void* qh = nullptr;  // queries rounded to the storage dtype (dense path operand A)
+  size_t qh_bytes = 0;
+  void* lists_ws = nullptr;  // dense path: per-CTA top-k lists when they do not fit in shared memory
+  size_t lists_ws_bytes = 0;
   void* qdev = nullptr;  // queries / outputs for the host-buffer search
   size_t qdev_bytes = 0;
   void* odev = nullptr;
@@ -85,7 +91,7 @@ struct sgic_index {
   std::vector<float> retained;
   bool retain_ok = false;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 5;
   int64_t stat_launches = 0, stat_last_search_ns = 0, stat_last_scan_ns = 0, stat_last_grid = 0, stat_last_stages = 0;
 };
 
@@ -288,9 +294,184 @@ static int launch_merge_keys(sgic_index* h, const uint64_t* partial, uint32_t nq
   return 0;
 }
 
-// Searches `nq` device-resident fp32 queries; results to device buffers.
+// ---- K4 dispatch (tcgen05 dense path) ------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// Row-major [rows][d] 16-bit matrix, box = 64 elements (128 B) x box_rows, 128-byte swizzle,
+// out-of-bounds elements read as zero (ragged last tile / d not a multiple of 64).
+static int make_tmap_rows(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t d, uint32_t box_rows, int dtype) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  SGIC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t gdim[2] = {d, rows};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(d) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kDenseBK), box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, dtype == SGIC_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                         const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 2;
+  }
+  return 0;
+}
+
+static uint32_t gcd_u32(uint32_t a, uint32_t b) {
+  while (b) {
+    const uint32_t t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+static int launch_merge_keys(sgic_index* h, const uint64_t* partial, uint32_t nq, uint32_t n_lists, uint32_t k,
+                             float* D, int64_t* I, int64_t id_base, cudaStream_t st);
+
+constexpr int kDenseBN = 256;
+constexpr int kDenseStages = 4;
+constexpr int64_t kDenseQueryBlock = 4096;  // queries per launch (FAISS blocks queries by 4096 too)
+
+static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
+                             int64_t id_base, cudaStream_t st) {
+  using Cfg = DenseCfg<kDenseBN>;
+  const uint32_t n_rows = static_cast<uint32_t>(h->ntotal);
+  const uint32_t kp = std::max<uint32_t>(2, next_pow2_u32(static_cast<uint32_t>(k)));
+  const bool lists_in_smem = static_cast<size_t>(kDenseBM) * kp * 8 <= 16 * 1024;
+  const size_t smem = 1024 + static_cast<size_t>(kDenseStages) * Cfg::kStageBytes +
+                      static_cast<size_t>(kDenseBuf) * kDenseBM * 8 +
+                      (lists_in_smem ? static_cast<size_t>(kDenseBM) * kp * 8 : 0) + (2 * kDenseStages + 4) * 8 + 16;
+  SGIC_REQUIRE(smem <= kSmemBudget, "dense path: shared memory budget exceeded");
+  auto kern = scan_dense_kernel<kDenseBN, kDenseStages>;
+  static bool configured[64] = {false};
+  if (!configured[h->device & 63]) {
+    SGIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+    configured[h->device & 63] = true;
+  }
+  const uint32_t n_tiles = (n_rows + kDenseBN - 1) / kDenseBN;
+
+  // queries -> storage dtype, once for the whole call
+  const size_t qh_need = static_cast<size_t>(nq) * h->d * 2;
+  if (qh_need > h->qh_bytes) {
+    SGIC_CUDA(cudaStreamSynchronize(st));
+    int rc = ensure_buf(&h->qh, &h->qh_bytes, qh_need, false);
+    if (rc) return rc;
+  }
+  {
+    const size_t n8 = static_cast<size_t>(nq) * h->d / 8;
+    const unsigned g = grid_for(n8, 256, h->sm_count);
+    if (h->dtype == SGIC_F16) pack_f32_kernel<__half><<<g, 256, 0, st>>>(dev_q, h->qh, n8);
+    else pack_f32_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(dev_q, h->qh, n8);
+    h->stat_launches++;
+    SGIC_CUDA(cudaGetLastError());
+  }
+  CUtensorMap tm_db;
+  int rc = make_tmap_rows(&tm_db, h->db, n_rows, static_cast<uint32_t>(h->d), kDenseBN, h->dtype);
+  if (rc) return rc;
+
+  if (h->opt_timing) SGIC_CUDA(cudaEventRecord(h->t0, st));
+  for (int64_t q0 = 0; q0 < nq; q0 += kDenseQueryBlock) {
+    const uint32_t nqb = static_cast<uint32_t>(std::min<int64_t>(kDenseQueryBlock, nq - q0));
+    const uint32_t m_tiles = (nqb + kDenseBM - 1) / kDenseBM;
+    // slices: items = m_tiles * n_slices is a multiple of the SM count whenever the database is big
+    // enough, so every CTA gets the same number of (equal-sized) items
+    uint32_t n_slices = static_cast<uint32_t>(h->sm_count) / gcd_u32(m_tiles, static_cast<uint32_t>(h->sm_count));
+    n_slices = std::max<uint32_t>(1, std::min(n_slices, n_tiles));
+    const uint32_t tiles_per_slice = (n_tiles + n_slices - 1) / n_slices;
+    n_slices = (n_tiles + tiles_per_slice - 1) / tiles_per_slice;
+    const uint32_t n_items = m_tiles * n_slices;
+    const uint32_t grid = std::min<uint32_t>(static_cast<uint32_t>(h->sm_count), n_items);
+
+    const size_t partial_bytes = static_cast<size_t>(nqb) * n_slices * static_cast<size_t>(k) * 8;
+    if (partial_bytes + 16 > h->ws_bytes) {
+      SGIC_CUDA(cudaStreamSynchronize(st));
+      rc = ensure_buf(&h->ws, &h->ws_bytes, partial_bytes + 16, false);
+      if (rc) return rc;
+      h->ws_counter = nullptr;
+    }
+    if (!lists_in_smem) {
+      const size_t need = static_cast<size_t>(grid) * kDenseBM * kp * 8;
+      if (need > h->lists_ws_bytes) {
+        SGIC_CUDA(cudaStreamSynchronize(st));
+        rc = ensure_buf(&h->lists_ws, &h->lists_ws_bytes, need, false);
+        if (rc) return rc;
+      }
+    }
+    CUtensorMap tm_q;
+    rc = make_tmap_rows(&tm_q, static_cast<const uint8_t*>(h->qh) + static_cast<size_t>(q0) * h->d * 2, nqb,
+                        static_cast<uint32_t>(h->d), kDenseBM, h->dtype);
+    if (rc) return rc;
+    DenseParams p;
+    p.partial = static_cast<uint64_t*>(h->ws);
+    p.lists_ws = static_cast<uint64_t*>(h->lists_ws);
+    p.n_rows = n_rows;
+    p.nq = nqb;
+    p.k = static_cast<uint32_t>(k);
+    p.kp = kp;
+    p.m_tiles = m_tiles;
+    p.n_slices = n_slices;
+    p.tiles_per_slice = tiles_per_slice;
+    p.n_tiles = n_tiles;
+    p.kc = (static_cast<uint32_t>(h->d) + kDenseBK - 1) / kDenseBK;
+    p.lists_in_smem = lists_in_smem ? 1u : 0u;
+    p.idesc = ptx::umma_idesc_f16(kDenseBM, kDenseBN, h->dtype == SGIC_BF16 ? 1u : 0u);
+    p.db_evict_first = (m_tiles == 1 && h->opt_evict_first) ? 1u : 0u;
+    kern<<<grid, kDenseThreads, kSmemBudget, st>>>(tm_q, tm_db, p);
+    h->stat_launches++;
+    SGIC_CUDA(cudaGetLastError());
+    h->stat_last_grid = grid;
+    h->stat_last_stages = kDenseStages;
+    if (h->opt_timing && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));
+    rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nqb, n_slices, static_cast<uint32_t>(k),
+                           dev_D + static_cast<size_t>(q0) * k, dev_I + static_cast<size_t>(q0) * k, id_base, st);
+    if (rc) return rc;
+  }
+  if (h->opt_timing) {
+    SGIC_CUDA(cudaEventRecord(h->t1, st));
+    SGIC_CUDA(cudaEventSynchronize(h->t1));
+    float ms = 0.f;
+    SGIC_CUDA(cudaEventElapsedTime(&ms, h->t0, h->t1));
+    h->stat_last_search_ns = static_cast<int64_t>(static_cast<double>(ms) * 1e6);
+    SGIC_CUDA(cudaEventElapsedTime(&ms, h->t0, h->tm));
+    h->stat_last_scan_ns = static_cast<int64_t>(static_cast<double>(ms) * 1e6);
+  }
+  return 0;
+}
+
+static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
+                             int64_t id_base, cudaStream_t st);
+
+// Searches `nq` device-resident fp32 queries; results to device buffers.  Regime choice: a few
+// queries -> K3 (CUDA-core streaming scan, HBM-bound); batches -> K4 (tcgen05 dense contraction).
 static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
                            int64_t id_base, cudaStream_t st) {
+  SGIC_REQUIRE(k >= 1, "k must be >= 1");
+  SGIC_REQUIRE(k <= kMaxK, "k > 1024 is not supported by this build");
+  SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
+  if (nq == 0) return 0;
+  SGIC_REQUIRE(h->ntotal < (1ll << 32) - 1, "more than 2^32-2 rows in one shard");
+  if (h->ntotal > 0 && nq >= h->opt_dense_min_nq) return search_dense_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st);
+  return search_small_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st);
+}
+
+static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
+                             int64_t id_base, cudaStream_t st) {
   SGIC_REQUIRE(k >= 1, "k must be >= 1");
   SGIC_REQUIRE(k <= kMaxK, "k > 1024 is not supported by this build");
   SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
@@ -473,6 +654,8 @@ int sgic_index_destroy(sgic_index* h) {
   }
   if (h->ws) cudaFree(h->ws);
   if (h->qdev) cudaFree(h->qdev);
+  if (h->qh) cudaFree(h->qh);
+  if (h->lists_ws) cudaFree(h->lists_ws);
   if (h->odev) cudaFree(h->odev);
   if (h->opin) cudaFreeHost(h->opin);
   if (h->db) cudaFree(h->db);
@@ -870,6 +1053,7 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "stages") h->opt_stages = value;
   else if (n == "rb") h->opt_rb = value;
   else if (n == "fused") h->opt_fused = value;
+  else if (n == "dense_min_nq") h->opt_dense_min_nq = value;
   else if (n == "drop_retained") {
     std::lock_guard<std::mutex> lk(h->mu);
     h->retain_ok = false;
