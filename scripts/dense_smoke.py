@@ -11,13 +11,17 @@ def unit(rng, n, d):
 
 cases = [(256, 64, 5, 4), (1000, 64, 5, 10), (1000, 512, 8, 10), (5000, 512, 128, 10), (5000, 512, 129, 10),
          (70000, 512, 300, 10), (20000, 768, 64, 100), (3001, 520, 17, 10), (200000, 512, 1024, 10)]
-if len(sys.argv) > 1:
-    cases = cases[:int(sys.argv[1])]
+mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+if len(sys.argv) > 2:
+    cases = cases[:int(sys.argv[2])]
+print("dense_mode", mode, flush=True)
 for n, d, nq, k in cases:
     rng = np.random.default_rng(n + d + nq + k)
     xb, xq = unit(rng, n, d), unit(rng, nq, d)
     idx = faiss.IndexFlatIP(d, device=0)
     idx.add(xb)
+    idx.set_option("dense_mode", mode)
+    idx.search(xq, k)
     t0 = time.time()
     D, I = idx.search(xq, k)
     dt = time.time() - t0

@@ -6,6 +6,8 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
+#include "tmem_ld.cuh"
+
 namespace sgic {
 namespace ptx {
 
@@ -109,25 +111,6 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// 32 consecutive fp32 columns of this thread's TMEM lane (SASS LDTM.x32).  Lane quadrant of the
-// issuing warp = warp_id % 4 (hardware rule), encoded in bits [31:16] of the address by the caller.
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-      "%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // K-major, 128-byte-swizzled operand tile in shared memory (rows of 64 16-bit elements = 128 B,
 // 8-row swizzle atoms of 1024 B; exactly what a TMA box {64, rows} with SWIZZLE_128B writes).
 // Field layout per cute/arch/mma_sm100_desc.hpp (UMMA::SmemDescriptor): start>>4 [0,14),

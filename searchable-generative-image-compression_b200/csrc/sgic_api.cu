@@ -91,7 +91,7 @@ struct sgic_index {
   std::vector<float> retained;
   bool retain_ok = false;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 5;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 5, opt_debug = 0, opt_dense_mode = 0;
   int64_t stat_launches = 0, stat_last_search_ns = 0, stat_last_scan_ns = 0, stat_last_grid = 0, stat_last_stages = 0;
 };
 
@@ -359,11 +359,20 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
                       (lists_in_smem ? static_cast<size_t>(kDenseBM) * kp * 8 : 0) + (2 * kDenseStages + 4) * 8 + 16;
   SGIC_REQUIRE(smem <= kSmemBudget, "dense path: shared memory budget exceeded");
   auto kern = scan_dense_kernel<kDenseBN, kDenseStages>;
+  auto kern2r = scan_dense2_kernel<true, 4>;   // CTA pairs, query tile resident (d <= 512)
+  auto kern2s = scan_dense2_kernel<false, 6>;  // CTA pairs, query tile streamed with the database
   static bool configured[64] = {false};
   if (!configured[h->device & 63]) {
     SGIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+    SGIC_CUDA(cudaFuncSetAttribute(kern2r, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+    SGIC_CUDA(cudaFuncSetAttribute(kern2s, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
     configured[h->device & 63] = true;
   }
+  // cta_group::2 is the default; "dense_mode" = 1 forces the single-CTA kernel (A/B comparisons)
+  const bool pairs = h->opt_dense_mode != 1 && h->sm_count >= 2;
+  const bool a_resident = h->d <= kD2MaxKc * kDenseBK && h->opt_dense_mode != 2;
+  const uint32_t q_tile = pairs ? 256u : static_cast<uint32_t>(kDenseBM);
+  const uint32_t n_units = pairs ? static_cast<uint32_t>(h->sm_count) / 2 : static_cast<uint32_t>(h->sm_count);
   const uint32_t n_tiles = (n_rows + kDenseBN - 1) / kDenseBN;
 
   // queries -> storage dtype, once for the whole call
@@ -382,21 +391,21 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     SGIC_CUDA(cudaGetLastError());
   }
   CUtensorMap tm_db;
-  int rc = make_tmap_rows(&tm_db, h->db, n_rows, static_cast<uint32_t>(h->d), kDenseBN, h->dtype);
+  int rc = make_tmap_rows(&tm_db, h->db, n_rows, static_cast<uint32_t>(h->d), pairs ? kDenseBM : kDenseBN, h->dtype);
   if (rc) return rc;
 
   if (h->opt_timing) SGIC_CUDA(cudaEventRecord(h->t0, st));
   for (int64_t q0 = 0; q0 < nq; q0 += kDenseQueryBlock) {
     const uint32_t nqb = static_cast<uint32_t>(std::min<int64_t>(kDenseQueryBlock, nq - q0));
-    const uint32_t m_tiles = (nqb + kDenseBM - 1) / kDenseBM;
-    // slices: items = m_tiles * n_slices is a multiple of the SM count whenever the database is big
-    // enough, so every CTA gets the same number of (equal-sized) items
-    uint32_t n_slices = static_cast<uint32_t>(h->sm_count) / gcd_u32(m_tiles, static_cast<uint32_t>(h->sm_count));
+    const uint32_t m_tiles = (nqb + q_tile - 1) / q_tile;
+    // slices: items = m_tiles * n_slices is a multiple of the number of CTAs (CTA pairs) whenever the
+    // database is big enough, so every CTA gets the same number of (equal-sized) items
+    uint32_t n_slices = n_units / gcd_u32(m_tiles, n_units);
     n_slices = std::max<uint32_t>(1, std::min(n_slices, n_tiles));
     const uint32_t tiles_per_slice = (n_tiles + n_slices - 1) / n_slices;
     n_slices = (n_tiles + tiles_per_slice - 1) / tiles_per_slice;
     const uint32_t n_items = m_tiles * n_slices;
-    const uint32_t grid = std::min<uint32_t>(static_cast<uint32_t>(h->sm_count), n_items);
+    const uint32_t grid = std::min<uint32_t>(n_units, n_items) * (pairs ? 2u : 1u);
 
     const size_t partial_bytes = static_cast<size_t>(nqb) * n_slices * static_cast<size_t>(k) * 8;
     if (partial_bytes + 16 > h->ws_bytes) {
@@ -430,9 +439,12 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.n_tiles = n_tiles;
     p.kc = (static_cast<uint32_t>(h->d) + kDenseBK - 1) / kDenseBK;
     p.lists_in_smem = lists_in_smem ? 1u : 0u;
-    p.idesc = ptx::umma_idesc_f16(kDenseBM, kDenseBN, h->dtype == SGIC_BF16 ? 1u : 0u);
+    p.idesc = ptx::umma_idesc_f16(q_tile, kDenseBN, h->dtype == SGIC_BF16 ? 1u : 0u);
     p.db_evict_first = (m_tiles == 1 && h->opt_evict_first) ? 1u : 0u;
-    kern<<<grid, kDenseThreads, kSmemBudget, st>>>(tm_q, tm_db, p);
+    p.debug = static_cast<uint32_t>(h->opt_debug);
+    if (!pairs) kern<<<grid, kDenseThreads, kSmemBudget, st>>>(tm_q, tm_db, p);
+    else if (a_resident) kern2r<<<grid, kDenseThreads, kSmemBudget, st>>>(tm_q, tm_db, p);
+    else kern2s<<<grid, kDenseThreads, kSmemBudget, st>>>(tm_q, tm_db, p);
     h->stat_launches++;
     SGIC_CUDA(cudaGetLastError());
     h->stat_last_grid = grid;
@@ -1054,6 +1066,8 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "rb") h->opt_rb = value;
   else if (n == "fused") h->opt_fused = value;
   else if (n == "dense_min_nq") h->opt_dense_min_nq = value;
+  else if (n == "debug") h->opt_debug = value;
+  else if (n == "dense_mode") h->opt_dense_mode = value;
   else if (n == "drop_retained") {
     std::lock_guard<std::mutex> lk(h->mu);
     h->retain_ok = false;
