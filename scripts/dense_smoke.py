@@ -10,7 +10,9 @@ def unit(rng, n, d):
     x = rng.standard_normal((n, d)).astype(np.float32); x /= np.linalg.norm(x, axis=1, keepdims=True); return x
 
 cases = [(256, 64, 5, 4), (1000, 64, 5, 10), (1000, 512, 8, 10), (5000, 512, 128, 10), (5000, 512, 129, 10),
-         (70000, 512, 300, 10), (20000, 768, 64, 100), (3001, 520, 17, 10), (200000, 512, 1024, 10)]
+         (70000, 512, 300, 10), (20000, 768, 64, 100), (3001, 520, 17, 10), (200000, 512, 1024, 10),
+         (40000, 512, 200, 32), (40000, 512, 200, 33), (9000, 256, 130, 1), (300, 512, 140, 32),
+         (50000, 768, 260, 10), (100000, 128, 4096, 5), (20000, 512, 64, 1024)]
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 if len(sys.argv) > 2:
     cases = cases[:int(sys.argv[2])]

@@ -8,10 +8,12 @@
 //   MMA       : one elected thread issues tcgen05.mma.kind::f16 (K=16 per instruction), fp32 accumulators in
 //               TMEM, two accumulator stages (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of
 //               tile i+1; tcgen05.commit releases smem stages / publishes accumulators
-//   epilogue  : 4 warps; thread t owns TMEM lane t = query t.  tcgen05.ld 64 columns at a time, a tree of
-//               3-input max + one compare against the query's running k-th score rejects a whole chunk;
-//               survivors are appended to a per-query buffer in shared memory and merged into the query's
-//               sorted list by the whole warp (warp_list_insert).  No score matrix ever leaves the SM.
+//   epilogue  : 4 warps; thread t owns TMEM lane t = query t.  tcgen05.ld a chunk of columns, a tree of
+//               3-input max + one compare against the query's running k-th score rejects the whole chunk.
+//               k <= 32: every thread keeps ITS query's sorted list in shared memory ([rank][query], conflict
+//               free) and inserts survivors itself, so 32 queries insert in parallel and the threshold is
+//               always fresh.  k > 32: survivors go to a per-query buffer and the warp merges them into the
+//               query's list together (warp_list_insert).  No score matrix ever leaves the SM.
 // Work split: items = (query tile m, database slice s), m fastest, so CTAs that run concurrently share a
 // slice and each database tile is fetched from HBM once and re-used from L2 by the other query tiles.
 // Every item writes k keys per query; merge_keys_small_kernel merges the slices.
@@ -42,11 +44,20 @@ struct DenseParams {
   uint32_t m_tiles;        // query tiles: of 128 (1-CTA kernel) or 256 (2-CTA kernel)
   uint32_t n_slices, tiles_per_slice, n_tiles;
   uint32_t kc;             // K chunks of 64 elements (ceil(d/64); TMA zero-fills the tail)
-  uint32_t lists_in_smem;  // 128*kp*8 bytes fit next to the stages
+  uint32_t lists_in_smem;  // k > 32 only: 128*kp*8 bytes fit next to the stages
+  uint32_t tp;             // k <= 32: thread-private lists [k][128] in shared memory, no candidate buffer
+  uint32_t a_rows;         // rows of the query box (1-CTA kernel; < 128 for small batches)
   uint32_t idesc;          // UMMA instruction descriptor
   uint32_t db_evict_first; // single query tile: the database is streamed once -> evict_first
   uint32_t debug;          // timing experiments only (wrong results): 1 skip A loads, 2 skip B loads, 4 skip epilogue
 };
+
+// shared memory of the epilogue: thread-private lists (k <= 32) or candidate buffer (+ lists when they fit)
+__host__ __device__ __forceinline__ uint32_t dense_epi_bytes(uint32_t k, uint32_t kp, uint32_t tp,
+                                                             uint32_t lists_in_smem) {
+  if (tp) return k * kDenseBM * 8u;
+  return kDenseBuf * kDenseBM * 8u + (lists_in_smem ? kDenseBM * kp * 8u : 0u);
+}
 
 template <int BN>
 struct DenseCfg {
@@ -142,6 +153,151 @@ struct DenseEpi {
   }
 };
 
+// k <= 32: thread t keeps the sorted list of ITS query at lst[rank * 128] (shared memory; the rank stride of
+// 1 KB keeps every lane on its own bank pair whatever rank it touches).  A survivor is inserted by its own
+// thread with a short shift loop — 32 queries insert in parallel and `thr` is always the current k-th score.
+struct DenseEpiTP {
+  uint64_t* lst;
+  uint32_t k;
+  float thr;
+
+  __device__ __forceinline__ void reset() {
+    for (uint32_t i = 0; i < k; ++i) lst[i * kDenseBM] = 0ull;
+    thr = -INFINITY;
+  }
+  // requires key > current k-th key (the caller compared the score with thr)
+  __device__ __forceinline__ void insert(uint64_t key) {
+    uint32_t i = k - 1;
+#pragma unroll 1
+    while (i > 0) {
+      const uint64_t a = lst[(i - 1) * kDenseBM];
+      if (a > key) break;
+      lst[i * kDenseBM] = a;
+      --i;
+    }
+    lst[i * kDenseBM] = key;
+    const uint64_t kth = lst[(k - 1) * kDenseBM];
+    thr = (kth == 0ull) ? -INFINITY : key_score(kth);
+  }
+
+  template <int BN>
+  __device__ __forceinline__ void scan_tile(uint32_t taddr0, uint32_t row0, uint32_t n_valid, bool q_valid) {
+#pragma unroll 1
+    for (uint32_t c = 0; c < BN / 32; ++c) {
+      if (c * 32 >= n_valid) break;
+      float v[32];
+      ptx::tmem_ld_32x32b_x32(taddr0 + c * 32, v);
+      float m4[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float a = fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), v[8 * g + 2]);
+        const float b = fmaxf(fmaxf(v[8 * g + 3], v[8 * g + 4]), v[8 * g + 5]);
+        m4[g] = fmaxf(fmaxf(a, b), fmaxf(v[8 * g + 6], v[8 * g + 7]));
+      }
+      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      const bool hit = q_valid && m > thr;
+      if (__any_sync(0xffffffffu, hit)) {
+        // Rare once the lists have warmed up.  Straight-line survivor mask (2 instructions per column, no
+        // branches), then the warp walks the UNION of the lanes' survivor columns and re-reads each one from
+        // TMEM (the accumulator is the only dynamically indexable copy of the scores): one single-column
+        // tcgen05.ld per distinct column, the owning lanes insert.
+        const uint32_t col0 = c * 32;
+        uint32_t mask = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mask |= (v[j] > thr) ? (1u << j) : 0u;
+        if (!q_valid) mask = 0;
+        if (n_valid - col0 < 32u) mask &= (1u << (n_valid - col0)) - 1u;
+        uint32_t um = __reduce_or_sync(0xffffffffu, mask);
+        while (um) {
+          const uint32_t j = __ffs(um) - 1;
+          um &= um - 1;
+          const float sc = ptx::tmem_ld_32x32b_x1(taddr0 + col0 + j);
+          if (((mask >> j) & 1u) && sc > thr) insert(make_key(sc, row0 + col0 + j));
+          __syncwarp();
+        }
+      }
+      __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next chunk
+    }
+  }
+
+  __device__ __forceinline__ void store(uint64_t* partial, uint32_t q, uint32_t nq, uint32_t n_slices, uint32_t slice) {
+    if (q >= nq) return;
+    uint64_t* dst = partial + (static_cast<size_t>(q) * n_slices + slice) * k;
+    for (uint32_t i = 0; i < k; ++i) dst[i] = lst[i * kDenseBM];
+  }
+};
+
+// The epilogue warps' loop over this CTA's items; `arrive(as)` hands accumulator stage `as` back to the
+// MMA issuer.  q_off: first query of this CTA inside the item's query tile (pairs: rank * 128).
+template <int BN, typename Arrive>
+__device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t unit, uint32_t n_units, uint32_t q_tile,
+                                               uint32_t q_off, uint32_t tmem_base, uint8_t* epi_smem,
+                                               uint64_t* acc_full, int warp, int lane, Arrive arrive) {
+  const uint32_t n_items = p.m_tiles * p.n_slices;
+  const int row0w = (warp & 3) * 32;  // TMEM lane quadrant this warp may read = warp_id % 4
+  const int t = row0w + lane;
+  const uint32_t tq = tmem_base + (static_cast<uint32_t>(row0w) << 16);
+  uint32_t tc = 0;
+  if (p.tp) {
+    DenseEpiTP epi;
+    epi.lst = reinterpret_cast<uint64_t*>(epi_smem) + t;
+    epi.k = p.k;
+    for (uint32_t item = unit; item < n_items; item += n_units) {
+      const uint32_t m_tile = item % p.m_tiles, slice = item / p.m_tiles;
+      const uint32_t t0 = slice * p.tiles_per_slice, t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+      const uint32_t q0 = m_tile * q_tile + q_off;
+      const bool q_valid = q0 + t < p.nq;
+      const bool warp_valid = q0 + row0w < p.nq;
+      epi.reset();
+      for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
+        const uint32_t as = tc & 1;
+        ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t row0 = tile * BN;
+        const uint32_t n_valid = min(static_cast<uint32_t>(BN), p.n_rows - row0);
+        if (warp_valid && !(p.debug & 4u)) epi.template scan_tile<BN>(tq + as * BN, row0, n_valid, q_valid);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive(as);
+      }
+      epi.store(p.partial, q0 + t, p.nq, p.n_slices, slice);
+    }
+  } else {
+    DenseEpi epi;
+    epi.cand = reinterpret_cast<uint64_t*>(epi_smem);
+    epi.lists = p.lists_in_smem ? epi.cand + kDenseBuf * kDenseBM
+                                : p.lists_ws + static_cast<size_t>(blockIdx.x) * kDenseBM * p.kp;
+    epi.kp = p.kp;
+    epi.k = p.k;
+    epi.row0w = row0w;
+    epi.lane = lane;
+    epi.t = t;
+    for (uint32_t item = unit; item < n_items; item += n_units) {
+      const uint32_t m_tile = item % p.m_tiles, slice = item / p.m_tiles;
+      const uint32_t t0 = slice * p.tiles_per_slice, t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+      const uint32_t q0 = m_tile * q_tile + q_off;
+      const bool q_valid = q0 + t < p.nq;
+      const bool warp_valid = q0 + row0w < p.nq;
+      epi.reset();
+      for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
+        const uint32_t as = tc & 1;
+        ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t row0 = tile * BN;
+        const uint32_t n_valid = min(static_cast<uint32_t>(BN), p.n_rows - row0);
+        if (warp_valid && !(p.debug & 4u)) epi.template scan_tile<BN>(tq + as * BN, row0, n_valid, q_valid);
+        // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive(as);
+        // keep thresholds fresh: merge buffered survivors as soon as a few have piled up
+        if (__any_sync(0xffffffffu, epi.cnt >= 4)) epi.flush();
+      }
+      epi.store_lists(p.partial, q0, p.nq, p.n_slices, slice);
+    }
+  }
+}
+
 // ================================================================================================ 1-CTA kernel
 template <int BN, int NS>
 __global__ void __launch_bounds__(kDenseThreads, 1)
@@ -152,9 +308,8 @@ scan_dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = dense_smem_raw + ((1024u - (ptx::smem_u32(dense_smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = smem;
-  uint64_t* cand = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(NS) * Cfg::kStageBytes);
-  uint64_t* lists_sm = cand + kDenseBuf * kDenseBM;
-  uint64_t* bars = lists_sm + (p.lists_in_smem ? static_cast<size_t>(kDenseBM) * p.kp : 0);
+  uint8_t* epi_smem = smem + static_cast<size_t>(NS) * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + dense_epi_bytes(p.k, p.kp, p.tp, p.lists_in_smem));
   uint64_t* full = bars;
   uint64_t* empty = bars + NS;
   uint64_t* acc_full = bars + 2 * NS;
@@ -199,7 +354,7 @@ scan_dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             if (u > 0) ptx::mbar_wait(&empty[s], (u - 1) & 1);
             uint8_t* a_dst = stages + static_cast<size_t>(s) * Cfg::kStageBytes;
             const bool ld_a = !(p.debug & 1u) || it < NS, ld_b = !(p.debug & 2u) || it < NS;
-            ptx::mbar_expect_tx(&full[s], (ld_a ? Cfg::kABytes : 0u) + (ld_b ? Cfg::kBBytes : 0u));
+            ptx::mbar_expect_tx(&full[s], (ld_a ? p.a_rows * (kDenseBK * 2u) : 0u) + (ld_b ? Cfg::kBBytes : 0u));
             if (ld_a)
               ptx::tma_load_2d(a_dst, &tm_q, static_cast<int32_t>(kc * kDenseBK),
                                static_cast<int32_t>(m_tile * kDenseBM), &full[s], pol_q);
@@ -240,38 +395,8 @@ scan_dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     }
   } else {
     // ================================================================ epilogue: fused top-k
-    DenseEpi epi;
-    epi.cand = cand;
-    epi.lists = p.lists_in_smem ? lists_sm : p.lists_ws + static_cast<size_t>(blockIdx.x) * kDenseBM * p.kp;
-    epi.kp = p.kp;
-    epi.k = p.k;
-    epi.row0w = (warp & 3) * 32;  // TMEM lane quadrant this warp may read = warp_id % 4
-    epi.lane = lane;
-    epi.t = epi.row0w + lane;
-    uint32_t tc = 0;
-    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const uint32_t m_tile = item % p.m_tiles, slice = item / p.m_tiles;
-      const uint32_t t0 = slice * p.tiles_per_slice, t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
-      const bool q_valid = m_tile * kDenseBM + epi.t < p.nq;
-      epi.reset();
-      for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
-        const uint32_t as = tc & 1;
-        ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
-        ptx::tc_fence_after();
-        const uint32_t row0 = tile * BN;
-        const uint32_t n_valid = min(static_cast<uint32_t>(BN), p.n_rows - row0);
-        if (!(p.debug & 4u))
-          epi.template scan_tile<BN>(tmem_base + (static_cast<uint32_t>(epi.row0w) << 16) + as * BN, row0, n_valid,
-                                     q_valid);
-        // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&acc_empty[as]);
-        // keep thresholds fresh: merge buffered survivors as soon as a few have piled up
-        if (__any_sync(0xffffffffu, epi.cnt >= 4)) epi.flush();
-      }
-      epi.store_lists(p.partial, m_tile * kDenseBM, p.nq, p.n_slices, slice);
-    }
+    dense_epilogue<BN>(p, blockIdx.x, gridDim.x, kDenseBM, 0u, tmem_base, epi_smem, acc_full, warp, lane,
+                       [&](uint32_t as) { ptx::mbar_arrive(&acc_empty[as]); });
   }
 
   ptx::tc_fence_before();
@@ -296,7 +421,10 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release at CTA scope), as cutlass::arch::ClusterBarrier::arrive(cta_id) does: the
+  // accumulator hand-over is ordered by tcgen05.fence::before/after_thread_sync, so no cluster-scope memory
+  // fence (MEMBAR.GPU + ERRBAR in SASS, 10 % of the epilogue's samples) is needed
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(smem_dst)),
@@ -350,9 +478,8 @@ scan_dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint8_t* smem = dense_smem_raw + ((1024u - (ptx::smem_u32(dense_smem_raw) & 1023u)) & 1023u);
   uint8_t* a_res = smem;  // ARES only: kc chunks of 16 KB
   uint8_t* stages = smem + (ARES ? static_cast<size_t>(kD2MaxKc) * kD2HalfBytes : 0);
-  uint64_t* cand = reinterpret_cast<uint64_t*>(stages + static_cast<size_t>(NS) * kStage);
-  uint64_t* lists_sm = cand + kDenseBuf * kDenseBM;
-  uint64_t* bars = lists_sm + (p.lists_in_smem ? static_cast<size_t>(kDenseBM) * p.kp : 0);
+  uint8_t* epi_smem = stages + static_cast<size_t>(NS) * kStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + dense_epi_bytes(p.k, p.kp, p.tp, p.lists_in_smem));
   uint64_t* full = bars;                     // leader's copy is the live one
   uint64_t* empty = bars + NS;               // each CTA its own (multicast commit)
   uint64_t* acc_full = bars + 2 * NS;        // each CTA its own (multicast commit)
@@ -459,38 +586,9 @@ scan_dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else {
     // ================================================================ epilogue (both CTAs): fused top-k
-    DenseEpi epi;
-    epi.cand = cand;
-    epi.lists = p.lists_in_smem ? lists_sm : p.lists_ws + static_cast<size_t>(blockIdx.x) * kDenseBM * p.kp;
-    epi.kp = p.kp;
-    epi.k = p.k;
-    epi.row0w = (warp & 3) * 32;
-    epi.lane = lane;
-    epi.t = epi.row0w + lane;
     const uint32_t acc_empty_leader0 = ptx2::mapa(ptx::smem_u32(&acc_empty[0]), 0);
-    uint32_t tc = 0;
-    for (uint32_t item = pair; item < n_items; item += n_pairs) {
-      const uint32_t m_tile = item % p.m_tiles, slice = item / p.m_tiles;
-      const uint32_t t0 = slice * p.tiles_per_slice, t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
-      const uint32_t q0 = m_tile * 256 + rank * kDenseBM;
-      const bool q_valid = q0 + epi.t < p.nq;
-      epi.reset();
-      for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
-        const uint32_t as = tc & 1;
-        ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
-        ptx::tc_fence_after();
-        const uint32_t row0 = tile * BN;
-        const uint32_t n_valid = min(static_cast<uint32_t>(BN), p.n_rows - row0);
-        if (!(p.debug & 4u))
-          epi.template scan_tile<BN>(tmem_base + (static_cast<uint32_t>(epi.row0w) << 16) + as * BN, row0, n_valid,
-                                     q_valid);
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx2::mbar_arrive_cluster(acc_empty_leader0 + as * 8);
-        if (__any_sync(0xffffffffu, epi.cnt >= 4)) epi.flush();
-      }
-      epi.store_lists(p.partial, q0, p.nq, p.n_slices, slice);
-    }
+    dense_epilogue<BN>(p, pair, n_pairs, 256u, rank * kDenseBM, tmem_base, epi_smem, acc_full, warp, lane,
+                       [&](uint32_t as) { ptx2::mbar_arrive_cluster(acc_empty_leader0 + as * 8); });
   }
 
   ptx::tc_fence_before();

@@ -353,11 +353,17 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
   using Cfg = DenseCfg<kDenseBN>;
   const uint32_t n_rows = static_cast<uint32_t>(h->ntotal);
   const uint32_t kp = std::max<uint32_t>(2, next_pow2_u32(static_cast<uint32_t>(k)));
-  const bool lists_in_smem = static_cast<size_t>(kDenseBM) * kp * 8 <= 16 * 1024;
-  const size_t smem = 1024 + static_cast<size_t>(kDenseStages) * Cfg::kStageBytes +
-                      static_cast<size_t>(kDenseBuf) * kDenseBM * 8 +
-                      (lists_in_smem ? static_cast<size_t>(kDenseBM) * kp * 8 : 0) + (2 * kDenseStages + 4) * 8 + 16;
-  SGIC_REQUIRE(smem <= kSmemBudget, "dense path: shared memory budget exceeded");
+  // k <= 32: thread-private lists in shared memory (k KB per CTA); larger k: warp-cooperative lists in an
+  // L2-resident workspace + a 16 KB candidate buffer
+  const bool tp = k <= 32;
+  const bool lists_in_smem = false;
+  const size_t epi_bytes = dense_epi_bytes(static_cast<uint32_t>(k), kp, tp, lists_in_smem);
+  // the three kernels' shared memory: alignment slack + operand ring (+ resident query tile) + epilogue + barriers
+  const size_t smem_1cta = 1024 + static_cast<size_t>(kDenseStages) * Cfg::kStageBytes + epi_bytes + 256;
+  const size_t smem_2r = 1024 + static_cast<size_t>(kD2MaxKc + 4) * kD2HalfBytes + epi_bytes + 256;
+  const size_t smem_2s = 1024 + static_cast<size_t>(6) * 2 * kD2HalfBytes + epi_bytes + 256;
+  SGIC_REQUIRE(std::max(smem_1cta, std::max(smem_2r, smem_2s)) <= kSmemBudget,
+               "dense path: shared memory budget exceeded");
   auto kern = scan_dense_kernel<kDenseBN, kDenseStages>;
   auto kern2r = scan_dense2_kernel<true, 4>;   // CTA pairs, query tile resident (d <= 512)
   auto kern2s = scan_dense2_kernel<false, 6>;  // CTA pairs, query tile streamed with the database
@@ -368,8 +374,10 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     SGIC_CUDA(cudaFuncSetAttribute(kern2s, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
     configured[h->device & 63] = true;
   }
-  // cta_group::2 is the default; "dense_mode" = 1 forces the single-CTA kernel (A/B comparisons)
-  const bool pairs = h->opt_dense_mode != 1 && h->sm_count >= 2;
+  // cta_group::2 (CTA pairs, 256 queries per tile) for batches of more than 128 queries; up to 128 queries
+  // fit one CTA's TMEM lanes and the scan is HBM-bound: single-CTA kernel with the query box cut to the
+  // batch.  "dense_mode" = 1 forces the single-CTA kernel, 3 forces pairs (A/B comparisons).
+  const bool pairs = h->sm_count >= 2 && h->opt_dense_mode != 1 && (nq > kDenseBM || h->opt_dense_mode == 3);
   const bool a_resident = h->d <= kD2MaxKc * kDenseBK && h->opt_dense_mode != 2;
   const uint32_t q_tile = pairs ? 256u : static_cast<uint32_t>(kDenseBM);
   const uint32_t n_units = pairs ? static_cast<uint32_t>(h->sm_count) / 2 : static_cast<uint32_t>(h->sm_count);
@@ -414,7 +422,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
       if (rc) return rc;
       h->ws_counter = nullptr;
     }
-    if (!lists_in_smem) {
+    if (!tp) {
       const size_t need = static_cast<size_t>(grid) * kDenseBM * kp * 8;
       if (need > h->lists_ws_bytes) {
         SGIC_CUDA(cudaStreamSynchronize(st));
@@ -424,7 +432,9 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     }
     CUtensorMap tm_q;
     rc = make_tmap_rows(&tm_q, static_cast<const uint8_t*>(h->qh) + static_cast<size_t>(q0) * h->d * 2, nqb,
-                        static_cast<uint32_t>(h->d), kDenseBM, h->dtype);
+                        static_cast<uint32_t>(h->d),
+                        pairs ? static_cast<uint32_t>(kDenseBM) : std::min<uint32_t>(kDenseBM, (nqb + 7u) & ~7u),
+                        h->dtype);
     if (rc) return rc;
     DenseParams p;
     p.partial = static_cast<uint64_t*>(h->ws);
@@ -439,6 +449,8 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.n_tiles = n_tiles;
     p.kc = (static_cast<uint32_t>(h->d) + kDenseBK - 1) / kDenseBK;
     p.lists_in_smem = lists_in_smem ? 1u : 0u;
+    p.tp = tp ? 1u : 0u;
+    p.a_rows = pairs ? static_cast<uint32_t>(kDenseBM) : std::min<uint32_t>(kDenseBM, (nqb + 7u) & ~7u);
     p.idesc = ptx::umma_idesc_f16(q_tile, kDenseBN, h->dtype == SGIC_BF16 ? 1u : 0u);
     p.db_evict_first = (m_tiles == 1 && h->opt_evict_first) ? 1u : 0u;
     p.debug = static_cast<uint32_t>(h->opt_debug);
