@@ -12,7 +12,8 @@ def unit(rng, n, d):
 cases = [(256, 64, 5, 4), (1000, 64, 5, 10), (1000, 512, 8, 10), (5000, 512, 128, 10), (5000, 512, 129, 10),
          (70000, 512, 300, 10), (20000, 768, 64, 100), (3001, 520, 17, 10), (200000, 512, 1024, 10),
          (40000, 512, 200, 32), (40000, 512, 200, 33), (9000, 256, 130, 1), (300, 512, 140, 32),
-         (50000, 768, 260, 10), (100000, 128, 4096, 5), (20000, 512, 64, 1024)]
+         (50000, 768, 260, 10), (100000, 128, 4096, 5), (20000, 512, 64, 1024),
+         (300, 512, 140, 100), (5000, 512, 1000, 128), (150000, 768, 300, 100), (60000, 256, 129, 500)]
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 if len(sys.argv) > 2:
     cases = cases[:int(sys.argv[2])]

@@ -10,7 +10,7 @@ from sgic_b200.synth import fill_index_random, random_unit_queries
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 10
-nqs = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [4096, 1024, 256, 128, 64, 16, 8]
+nqs = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [1, 4, 8, 16, 64, 128, 256, 1024, 4096]
 modes = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0]
 dbgs = [int(x) for x in sys.argv[6].split(",")] if len(sys.argv) > 6 else [0, 4]
 names = {0: "auto", 1: "1cta", 2: "pairs+stream", 3: "pairs"}
@@ -28,14 +28,18 @@ for nq in nqs:
             for _ in range(2):
                 idx.search_torch(q, k, out=(D, I))
             torch.cuda.synchronize()
-            reps = 5 if nq >= 1024 else 20
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(reps):
-                idx.search_torch(q, k, out=(D, I))
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / reps
+            reps = 3 if nq >= 1024 else 10
+            samples = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    idx.search_torch(q, k, out=(D, I))
+                e1.record()
+                torch.cuda.synchronize()
+                samples.append(e0.elapsed_time(e1) / reps)
+            samples.sort()
+            ms, best = samples[len(samples) // 2], samples[0]
             tf = 2 * nq * n * d / ms / 1e9
-            print(f"nq={nq:5d} mode={names[mode]:12s} skipEpi={dbg >> 2} ms={ms:8.3f} TF={tf:7.0f} "
+            print(f"nq={nq:5d} mode={names[mode]:12s} skipEpi={dbg >> 2} ms={ms:8.3f} (best {best:8.3f}) TF={tf:7.0f} "
                   f"({tf / 1404.9:.3f} of sustained)  GB/s={n * d * 2 / ms / 1e6:6.0f}  qps={nq / ms * 1e3:9.0f}", flush=True)

@@ -12,8 +12,9 @@
 //               3-input max + one compare against the query's running k-th score rejects the whole chunk.
 //               k <= 32: every thread keeps ITS query's sorted list in shared memory ([rank][query], conflict
 //               free) and inserts survivors itself, so 32 queries insert in parallel and the threshold is
-//               always fresh.  k > 32: survivors go to a per-query buffer and the warp merges them into the
-//               query's list together (warp_list_insert).  No score matrix ever leaves the SM.
+//               always fresh.  k > 32: reservoir selection — survivors are appended to the query's reservoir
+//               in an L2-resident workspace and the warp compacts a full reservoir to its k best by bisection
+//               over the key bits.  No score matrix ever leaves the SM.
 // Work split: items = (query tile m, database slice s), m fastest, so CTAs that run concurrently share a
 // slice and each database tile is fetched from HBM once and re-used from L2 by the other query tiles.
 // Every item writes k keys per query; merge_keys_small_kernel merges the slices.
@@ -35,28 +36,24 @@ namespace sgic {
 constexpr int kDenseThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int kDenseBM = 128;       // queries per CTA (TMEM lanes)
 constexpr int kDenseBK = 64;        // K chunk: 64 x 16-bit = one 128-byte swizzle row
-constexpr int kDenseBuf = 16;       // candidate buffer depth per query (entries)
 
 struct DenseParams {
   uint64_t* partial;   // [nq][n_slices][k] keys
-  uint64_t* lists_ws;  // [grid][128][kp] keys, used when the lists do not fit in shared memory
-  uint32_t n_rows, nq, k, kp;
+  uint64_t* lists_ws;  // k > 32: [grid][128][res_cap] reservoirs (L2-resident workspace)
+  uint32_t n_rows, nq, k, res_cap;
   uint32_t m_tiles;        // query tiles: of 128 (1-CTA kernel) or 256 (2-CTA kernel)
   uint32_t n_slices, tiles_per_slice, n_tiles;
   uint32_t kc;             // K chunks of 64 elements (ceil(d/64); TMA zero-fills the tail)
-  uint32_t lists_in_smem;  // k > 32 only: 128*kp*8 bytes fit next to the stages
-  uint32_t tp;             // k <= 32: thread-private lists [k][128] in shared memory, no candidate buffer
+  uint32_t tp;             // k <= 32: thread-private lists [k][128] in shared memory; else reservoirs
   uint32_t a_rows;         // rows of the query box (1-CTA kernel; < 128 for small batches)
   uint32_t idesc;          // UMMA instruction descriptor
   uint32_t db_evict_first; // single query tile: the database is streamed once -> evict_first
   uint32_t debug;          // timing experiments only (wrong results): 1 skip A loads, 2 skip B loads, 4 skip epilogue
 };
 
-// shared memory of the epilogue: thread-private lists (k <= 32) or candidate buffer (+ lists when they fit)
-__host__ __device__ __forceinline__ uint32_t dense_epi_bytes(uint32_t k, uint32_t kp, uint32_t tp,
-                                                             uint32_t lists_in_smem) {
-  if (tp) return k * kDenseBM * 8u;
-  return kDenseBuf * kDenseBM * 8u + (lists_in_smem ? kDenseBM * kp * 8u : 0u);
+// shared memory of the epilogue: thread-private lists (k <= 32); the reservoirs of larger k live in L2
+__host__ __device__ __forceinline__ uint32_t dense_epi_bytes(uint32_t k, uint32_t tp) {
+  return tp ? k * kDenseBM * 8u : 0u;
 }
 
 template <int BN>
@@ -67,91 +64,18 @@ struct DenseCfg {
   static constexpr uint32_t kTmemCols = 2 * BN;
 };
 
-// Merge every lane's buffered candidates into that lane's sorted list; all 32 lanes cooperate on one
-// list at a time (ballot-count position + parallel shift).  Updates each lane's threshold.
-__device__ __noinline__ void dense_warp_flush(const uint64_t* cand, uint64_t* lists, uint32_t kp, uint32_t k,
-                                              int row0, int lane, uint32_t& cnt, float& thr) {
-  __syncwarp();
-  for (int L = 0; L < 32; ++L) {
-    const uint32_t n = __shfl_sync(0xffffffffu, cnt, L);
-    if (n == 0) continue;
-    uint64_t* list = lists + static_cast<size_t>(row0 + L) * kp;
-    uint64_t kth = 0ull;
-    for (uint32_t e = 0; e < n; ++e) kth = warp_list_insert(list, static_cast<int>(k), cand[e * kDenseBM + row0 + L], lane);
-    if (lane == L) thr = (kth == 0ull) ? -INFINITY : key_score(kth);
-  }
-  cnt = 0;
-  __syncwarp();
+// v[j] for a run-time j in [0,32): binary select tree over the registers (16+8+4+2+1 SEL)
+__device__ __forceinline__ float select32(const float (&v)[32], uint32_t j) {
+  float a[16], b[8], c[4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1u) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2u) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4u) ? b[2 * i + 1] : b[2 * i];
+  const float d0 = (j & 8u) ? c[1] : c[0], d1 = (j & 8u) ? c[3] : c[2];
+  return (j & 16u) ? d1 : d0;
 }
-
-// Per-warp epilogue state and the scan of one accumulator tile (BN columns of this warp's 32 TMEM lanes).
-struct DenseEpi {
-  uint64_t* cand;   // [kDenseBuf][128] candidate buffer (shared memory)
-  uint64_t* lists;  // [128][kp] sorted lists of this CTA (shared or global)
-  uint32_t kp, k;
-  int row0w, lane, t;
-  uint32_t cnt;
-  float thr;
-
-  __device__ __forceinline__ void reset() {
-    for (int L = 0; L < 32; ++L)
-      for (uint32_t i = lane; i < kp; i += 32) lists[static_cast<size_t>(row0w + L) * kp + i] = 0ull;
-    cnt = 0;
-    thr = -INFINITY;
-    __syncwarp();
-  }
-  __device__ __forceinline__ void flush() { dense_warp_flush(cand, lists, kp, k, row0w, lane, cnt, thr); }
-
-  // taddr0: TMEM address of column 0 of the tile for this warp's lane quadrant
-  template <int BN>
-  __device__ __forceinline__ void scan_tile(uint32_t taddr0, uint32_t row0, uint32_t n_valid, bool q_valid) {
-#pragma unroll 1
-    for (uint32_t c = 0; c < BN / 64; ++c) {
-      float v[64];
-      ptx::tmem_ld_32x32b_x64(taddr0 + c * 64, v);
-      // per-group-of-8 maxima as balanced trees (3-input max): short dependency chains
-      float m8[8];
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float a = fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), v[8 * g + 2]);
-        const float b = fmaxf(fmaxf(v[8 * g + 3], v[8 * g + 4]), v[8 * g + 5]);
-        m8[g] = fmaxf(fmaxf(a, b), fmaxf(v[8 * g + 6], v[8 * g + 7]));
-      }
-      const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
-                            fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-      const bool hit = q_valid && (m > thr) && (c * 64 < n_valid);
-      if (__any_sync(0xffffffffu, hit)) {
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          if (!__any_sync(0xffffffffu, q_valid && m8[g] > thr)) continue;  // no lane has a survivor here
-          if (__any_sync(0xffffffffu, cnt > kDenseBuf - 8)) flush();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t col = c * 64 + g * 8 + j;
-            if (q_valid && v[g * 8 + j] > thr && col < n_valid) {
-              cand[cnt * kDenseBM + t] = make_key(v[g * 8 + j], row0 + col);
-              ++cnt;
-            }
-          }
-        }
-      }
-    }
-  }
-
-  // item finished: every query's list -> partial[(q * n_slices + slice) * k]
-  __device__ __forceinline__ void store_lists(uint64_t* partial, uint32_t q0, uint32_t nq, uint32_t n_slices,
-                                              uint32_t slice) {
-    flush();
-    for (int L = 0; L < 32; ++L) {
-      const uint32_t q = q0 + row0w + L;
-      if (q >= nq) break;
-      uint64_t* dst = partial + (static_cast<size_t>(q) * n_slices + slice) * k;
-      const uint64_t* src = lists + static_cast<size_t>(row0w + L) * kp;
-      for (uint32_t i = lane; i < k; i += 32) dst[i] = src[i];
-    }
-    __syncwarp();
-  }
-};
 
 // k <= 32: thread t keeps the sorted list of ITS query at lst[rank * 128] (shared memory; the rank stride of
 // 1 KB keeps every lane on its own bank pair whatever rank it touches).  A survivor is inserted by its own
@@ -165,18 +89,33 @@ struct DenseEpiTP {
     for (uint32_t i = 0; i < k; ++i) lst[i * kDenseBM] = 0ull;
     thr = -INFINITY;
   }
-  // requires key > current k-th key (the caller compared the score with thr)
+  // requires key > current k-th key (the caller compared the score with thr).  Shift loop from the tail,
+  // four predecessors loaded per round trip to shared memory (the loop is a latency chain: one warp per
+  // scheduler, nothing else to hide it); the new k-th key is tracked in registers.
   __device__ __forceinline__ void insert(uint64_t key) {
     uint32_t i = k - 1;
+    uint64_t kth = key;
 #pragma unroll 1
     while (i > 0) {
-      const uint64_t a = lst[(i - 1) * kDenseBM];
-      if (a > key) break;
-      lst[i * kDenseBM] = a;
+      const uint64_t a0 = lst[(i - 1) * kDenseBM];
+      const uint64_t a1 = (i >= 2) ? lst[(i - 2) * kDenseBM] : ~0ull;
+      const uint64_t a2 = (i >= 3) ? lst[(i - 3) * kDenseBM] : ~0ull;
+      const uint64_t a3 = (i >= 4) ? lst[(i - 4) * kDenseBM] : ~0ull;
+      if (a0 > key) break;
+      if (i == k - 1) kth = a0;  // the old (k-1)-th key becomes the k-th
+      lst[i * kDenseBM] = a0;
+      --i;
+      if (a1 > key) break;
+      lst[i * kDenseBM] = a1;
+      --i;
+      if (a2 > key) break;
+      lst[i * kDenseBM] = a2;
+      --i;
+      if (a3 > key) break;
+      lst[i * kDenseBM] = a3;
       --i;
     }
     lst[i * kDenseBM] = key;
-    const uint64_t kth = lst[(k - 1) * kDenseBM];
     thr = (kth == 0ull) ? -INFINITY : key_score(kth);
   }
 
@@ -198,22 +137,20 @@ struct DenseEpiTP {
       const bool hit = q_valid && m > thr;
       if (__any_sync(0xffffffffu, hit)) {
         // Rare once the lists have warmed up.  Straight-line survivor mask (2 instructions per column, no
-        // branches), then the warp walks the UNION of the lanes' survivor columns and re-reads each one from
-        // TMEM (the accumulator is the only dynamically indexable copy of the scores): one single-column
-        // tcgen05.ld per distinct column, the owning lanes insert.
+        // branches); then every lane walks ITS OWN survivors — the score comes out of the lane's registers
+        // through a 5-level select tree (31 SEL; registers cannot be indexed dynamically) — so the 32 queries
+        // of the warp insert in parallel even when their survivors sit in different columns.
         const uint32_t col0 = c * 32;
         uint32_t mask = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) mask |= (v[j] > thr) ? (1u << j) : 0u;
         if (!q_valid) mask = 0;
         if (n_valid - col0 < 32u) mask &= (1u << (n_valid - col0)) - 1u;
-        uint32_t um = __reduce_or_sync(0xffffffffu, mask);
-        while (um) {
-          const uint32_t j = __ffs(um) - 1;
-          um &= um - 1;
-          const float sc = ptx::tmem_ld_32x32b_x1(taddr0 + col0 + j);
-          if (((mask >> j) & 1u) && sc > thr) insert(make_key(sc, row0 + col0 + j));
-          __syncwarp();
+        while (mask) {
+          const uint32_t j = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float sc = select32(v, j);
+          if (sc > thr) insert(make_key(sc, row0 + col0 + j));
         }
       }
       __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next chunk
@@ -224,6 +161,192 @@ struct DenseEpiTP {
     if (q >= nq) return;
     uint64_t* dst = partial + (static_cast<size_t>(q) * n_slices + slice) * k;
     for (uint32_t i = 0; i < k; ++i) dst[i] = lst[i * kDenseBM];
+  }
+};
+
+// k > 32: reservoir selection (what FAISS does for k >= 100, ReservoirTopN behind exhaustive_inner_product_blas).
+// Thread t appends every score above its threshold to ITS query's reservoir of C = max(256, 2*kp) keys in an
+// L2-resident workspace — one fire-and-forget store, nothing to wait for.  When a reservoir is full the warp
+// compacts it together: the k-th largest key is found by bisection over the key bits (count(key >= cand) with a
+// REDUX per step; C = 256 keeps the keys in registers, 8 per lane), the k survivors move to the front, and the
+// query's threshold becomes the k-th score.  A stale threshold only lets extra candidates in, never drops one,
+// so the k keys left at the end of an item are exactly its top-k (unsorted; the merge kernel sorts).
+struct DenseEpiRes {
+  uint64_t* res_warp;  // reservoir of this warp's lane 0; lane L's starts at res_warp + L * C
+  uint32_t k, C;
+  int lane;
+  uint32_t cnt;
+  float thr;
+
+  __device__ __forceinline__ void reset() {
+    cnt = 0;
+    thr = -INFINITY;
+  }
+  __device__ __forceinline__ void append(uint64_t key) {
+    __stcg(res_warp + static_cast<size_t>(lane) * C + cnt, key);
+    ++cnt;
+  }
+
+  // Warp-cooperative: keep the k largest of R[0..n) (n > k) in R[0..k); returns the k-th largest key.
+  template <bool REG>
+  __device__ __forceinline__ uint64_t select_topk(uint64_t* R, uint32_t n) {
+    constexpr int KPL = 8;  // REG: n <= 256
+    uint64_t key[KPL];
+    if (REG) {
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        const uint32_t idx = i * 32 + lane;
+        key[i] = idx < n ? __ldcg(R + idx) : 0ull;  // 0 sorts below every real key
+      }
+    }
+    // bits above the highest bit in which two keys differ are common to all keys: start the bisection there
+    const uint64_t k0 = __ldcg(R);
+    uint32_t xh = 0, xl = 0;
+    if (REG) {
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        const uint64_t x = key[i] ? key[i] ^ k0 : 0ull;
+        xh |= static_cast<uint32_t>(x >> 32);
+        xl |= static_cast<uint32_t>(x);
+      }
+    } else {
+      for (uint32_t idx = lane; idx < n; idx += 32) {
+        const uint64_t x = __ldcg(R + idx) ^ k0;
+        xh |= static_cast<uint32_t>(x >> 32);
+        xl |= static_cast<uint32_t>(x);
+      }
+    }
+    xh = __reduce_or_sync(0xffffffffu, xh);
+    xl = __reduce_or_sync(0xffffffffu, xl);
+    int b = xh ? 63 - __clz(xh) : 31 - __clz(xl);  // keys are unique and n >= 2: some bit differs
+    uint64_t prefix = (b == 63) ? 0ull : (k0 >> (b + 1)) << (b + 1);
+    for (; b >= 0; --b) {
+      const uint64_t cand = prefix | (1ull << b);
+      uint32_t c = 0;
+      if (REG) {
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) c += key[i] >= cand ? 1u : 0u;
+      } else {
+        for (uint32_t idx = lane; idx < n; idx += 32) c += __ldcg(R + idx) >= cand ? 1u : 0u;
+      }
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= k) prefix = cand;
+      if (c == k) break;  // exactly k keys at or above cand: they are the top-k
+    }
+    // k-th key = the smallest key >= prefix
+    uint64_t kth = ~0ull;
+    if (REG) {
+#pragma unroll
+      for (int i = 0; i < KPL; ++i)
+        if (key[i] >= prefix && key[i] < kth) kth = key[i];
+    } else {
+      for (uint32_t idx = lane; idx < n; idx += 32) {
+        const uint64_t x = __ldcg(R + idx);
+        if (x >= prefix && x < kth) kth = x;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const uint64_t o = __shfl_xor_sync(0xffffffffu, kth, off);
+      kth = o < kth ? o : kth;
+    }
+    // survivors to the front (stable, in place: the write position never passes the read position)
+    uint32_t out = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+    if (REG) {
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        const bool keep = key[i] >= kth;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) __stcg(R + out + __popc(m & lt), key[i]);
+        out += __popc(m);
+      }
+    } else {
+      for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t idx = base + lane;
+        const uint64_t x = idx < n ? __ldcg(R + idx) : 0ull;
+        const bool keep = x >= kth;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) __stcg(R + out + __popc(m & lt), x);
+        out += __popc(m);
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+    return kth;
+  }
+
+  // compact the reservoirs of the lanes named in `need` (warp-uniform mask)
+  __device__ __forceinline__ void compact(uint32_t need) {
+    __syncwarp();
+    while (need) {
+      const int L = __ffs(need) - 1;
+      need &= need - 1;
+      const uint32_t n = __shfl_sync(0xffffffffu, cnt, L);
+      uint64_t* R = res_warp + static_cast<size_t>(L) * C;
+      const uint64_t kth = (C == 256u) ? select_topk<true>(R, n) : select_topk<false>(R, n);
+      if (lane == L) {
+        cnt = k;
+        thr = key_score(kth);
+      }
+    }
+  }
+
+  template <int BN>
+  __device__ __forceinline__ void scan_tile(uint32_t taddr0, uint32_t row0, uint32_t n_valid, bool q_valid) {
+#pragma unroll 1
+    for (uint32_t c = 0; c < BN / 32; ++c) {
+      if (c * 32 >= n_valid) break;
+      float v[32];
+      ptx::tmem_ld_32x32b_x32(taddr0 + c * 32, v);
+      float m4[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float a = fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), v[8 * g + 2]);
+        const float b = fmaxf(fmaxf(v[8 * g + 3], v[8 * g + 4]), v[8 * g + 5]);
+        m4[g] = fmaxf(fmaxf(a, b), fmaxf(v[8 * g + 6], v[8 * g + 7]));
+      }
+      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      const bool hit = q_valid && m > thr;
+      if (__any_sync(0xffffffffu, hit)) {
+        const uint32_t col0 = c * 32;
+        uint32_t mask = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mask |= (v[j] > thr) ? (1u << j) : 0u;
+        if (!q_valid) mask = 0;
+        if (n_valid - col0 < 32u) mask &= (1u << (n_valid - col0)) - 1u;
+        // warp-uniform loop: every lane appends its next survivor, full reservoirs are compacted at once
+        while (__any_sync(0xffffffffu, mask != 0u)) {
+          if (mask) {
+            const uint32_t j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float sc = select32(v, j);
+            if (sc > thr) append(make_key(sc, row0 + col0 + j));
+          }
+          const uint32_t full = __ballot_sync(0xffffffffu, cnt == C);
+          if (full) compact(full);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  // item finished: reservoirs down to k keys, then the warp copies each query's keys out (coalesced)
+  __device__ __forceinline__ void store(uint64_t* partial, uint32_t q0w, uint32_t nq, uint32_t n_slices,
+                                        uint32_t slice) {
+    const uint32_t over = __ballot_sync(0xffffffffu, cnt > k);
+    if (over) compact(over);
+    __syncwarp();
+    for (int L = 0; L < 32; ++L) {
+      const uint32_t q = q0w + L;
+      if (q >= nq) break;
+      const uint32_t n = __shfl_sync(0xffffffffu, cnt, L);
+      const uint64_t* R = res_warp + static_cast<size_t>(L) * C;
+      uint64_t* dst = partial + (static_cast<size_t>(q) * n_slices + slice) * k;
+      for (uint32_t i = lane; i < k; i += 32) dst[i] = i < n ? __ldcg(R + i) : 0ull;
+    }
+    __syncwarp();
   }
 };
 
@@ -263,15 +386,11 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
       epi.store(p.partial, q0 + t, p.nq, p.n_slices, slice);
     }
   } else {
-    DenseEpi epi;
-    epi.cand = reinterpret_cast<uint64_t*>(epi_smem);
-    epi.lists = p.lists_in_smem ? epi.cand + kDenseBuf * kDenseBM
-                                : p.lists_ws + static_cast<size_t>(blockIdx.x) * kDenseBM * p.kp;
-    epi.kp = p.kp;
+    DenseEpiRes epi;
     epi.k = p.k;
-    epi.row0w = row0w;
+    epi.C = p.res_cap;
     epi.lane = lane;
-    epi.t = t;
+    epi.res_warp = p.lists_ws + (static_cast<size_t>(blockIdx.x) * kDenseBM + row0w) * p.res_cap;
     for (uint32_t item = unit; item < n_items; item += n_units) {
       const uint32_t m_tile = item % p.m_tiles, slice = item / p.m_tiles;
       const uint32_t t0 = slice * p.tiles_per_slice, t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
@@ -286,14 +405,11 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
         const uint32_t row0 = tile * BN;
         const uint32_t n_valid = min(static_cast<uint32_t>(BN), p.n_rows - row0);
         if (warp_valid && !(p.debug & 4u)) epi.template scan_tile<BN>(tq + as * BN, row0, n_valid, q_valid);
-        // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive(as);
-        // keep thresholds fresh: merge buffered survivors as soon as a few have piled up
-        if (__any_sync(0xffffffffu, epi.cnt >= 4)) epi.flush();
       }
-      epi.store_lists(p.partial, q0, p.nq, p.n_slices, slice);
+      if (warp_valid) epi.store(p.partial, q0 + row0w, p.nq, p.n_slices, slice);
     }
   }
 }
@@ -309,7 +425,7 @@ scan_dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   uint8_t* smem = dense_smem_raw + ((1024u - (ptx::smem_u32(dense_smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = smem;
   uint8_t* epi_smem = smem + static_cast<size_t>(NS) * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + dense_epi_bytes(p.k, p.kp, p.tp, p.lists_in_smem));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + dense_epi_bytes(p.k, p.tp));
   uint64_t* full = bars;
   uint64_t* empty = bars + NS;
   uint64_t* acc_full = bars + 2 * NS;
@@ -479,7 +595,7 @@ scan_dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint8_t* a_res = smem;  // ARES only: kc chunks of 16 KB
   uint8_t* stages = smem + (ARES ? static_cast<size_t>(kD2MaxKc) * kD2HalfBytes : 0);
   uint8_t* epi_smem = stages + static_cast<size_t>(NS) * kStage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + dense_epi_bytes(p.k, p.kp, p.tp, p.lists_in_smem));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + dense_epi_bytes(p.k, p.tp));
   uint64_t* full = bars;                     // leader's copy is the live one
   uint64_t* empty = bars + NS;               // each CTA its own (multicast commit)
   uint64_t* acc_full = bars + 2 * NS;        // each CTA its own (multicast commit)

@@ -259,8 +259,9 @@ static cudaError_t launch_scan_t(const ScanSmallParams& p, int NQ, int cpl, int 
   }
 }
 
+// sorted_lists: every list is ordered best-first (the multiway merge needs that); the bitonic kernel does not care
 static int launch_merge_keys(sgic_index* h, const uint64_t* partial, uint32_t nq, uint32_t n_lists, uint32_t k,
-                             float* D, int64_t* I, int64_t id_base, cudaStream_t st) {
+                             float* D, int64_t* I, int64_t id_base, cudaStream_t st, bool sorted_lists = true) {
   MergeKeysParams mp;
   mp.partial = partial;
   mp.n_lists = n_lists;
@@ -273,7 +274,7 @@ static int launch_merge_keys(sgic_index* h, const uint64_t* partial, uint32_t nq
   mp.I = reinterpret_cast<long long*>(I);
   mp.id_base = id_base;
   const size_t all_bytes = static_cast<size_t>(n_lists) * k * 8;
-  if (n_lists <= 32u * kMergeMaxLpl && all_bytes <= 200u * 1024) {
+  if (sorted_lists && n_lists <= 32u * kMergeMaxLpl && all_bytes <= 200u * 1024) {
     // every list fits in shared memory: multiway merge by one warp (k short rounds)
     if (all_bytes > 48 * 1024)
       SGIC_CUDA(cudaFuncSetAttribute(merge_keys_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -341,9 +342,6 @@ static uint32_t gcd_u32(uint32_t a, uint32_t b) {
   return a;
 }
 
-static int launch_merge_keys(sgic_index* h, const uint64_t* partial, uint32_t nq, uint32_t n_lists, uint32_t k,
-                             float* D, int64_t* I, int64_t id_base, cudaStream_t st);
-
 constexpr int kDenseBN = 256;
 constexpr int kDenseStages = 4;
 constexpr int64_t kDenseQueryBlock = 4096;  // queries per launch (FAISS blocks queries by 4096 too)
@@ -353,11 +351,11 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
   using Cfg = DenseCfg<kDenseBN>;
   const uint32_t n_rows = static_cast<uint32_t>(h->ntotal);
   const uint32_t kp = std::max<uint32_t>(2, next_pow2_u32(static_cast<uint32_t>(k)));
-  // k <= 32: thread-private lists in shared memory (k KB per CTA); larger k: warp-cooperative lists in an
-  // L2-resident workspace + a 16 KB candidate buffer
+  // k <= 32: thread-private sorted lists in shared memory (k KB per CTA); larger k: per-query reservoirs of
+  // res_cap keys in an L2-resident workspace, compacted by the warp when full (lists come out unsorted)
   const bool tp = k <= 32;
-  const bool lists_in_smem = false;
-  const size_t epi_bytes = dense_epi_bytes(static_cast<uint32_t>(k), kp, tp, lists_in_smem);
+  const uint32_t res_cap = std::max<uint32_t>(256, 2 * kp);
+  const size_t epi_bytes = dense_epi_bytes(static_cast<uint32_t>(k), tp);
   // the three kernels' shared memory: alignment slack + operand ring (+ resident query tile) + epilogue + barriers
   const size_t smem_1cta = 1024 + static_cast<size_t>(kDenseStages) * Cfg::kStageBytes + epi_bytes + 256;
   const size_t smem_2r = 1024 + static_cast<size_t>(kD2MaxKc + 4) * kD2HalfBytes + epi_bytes + 256;
@@ -423,7 +421,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
       h->ws_counter = nullptr;
     }
     if (!tp) {
-      const size_t need = static_cast<size_t>(grid) * kDenseBM * kp * 8;
+      const size_t need = static_cast<size_t>(grid) * kDenseBM * res_cap * 8;
       if (need > h->lists_ws_bytes) {
         SGIC_CUDA(cudaStreamSynchronize(st));
         rc = ensure_buf(&h->lists_ws, &h->lists_ws_bytes, need, false);
@@ -442,13 +440,12 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.n_rows = n_rows;
     p.nq = nqb;
     p.k = static_cast<uint32_t>(k);
-    p.kp = kp;
+    p.res_cap = res_cap;
     p.m_tiles = m_tiles;
     p.n_slices = n_slices;
     p.tiles_per_slice = tiles_per_slice;
     p.n_tiles = n_tiles;
     p.kc = (static_cast<uint32_t>(h->d) + kDenseBK - 1) / kDenseBK;
-    p.lists_in_smem = lists_in_smem ? 1u : 0u;
     p.tp = tp ? 1u : 0u;
     p.a_rows = pairs ? static_cast<uint32_t>(kDenseBM) : std::min<uint32_t>(kDenseBM, (nqb + 7u) & ~7u);
     p.idesc = ptx::umma_idesc_f16(q_tile, kDenseBN, h->dtype == SGIC_BF16 ? 1u : 0u);
@@ -463,7 +460,8 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     h->stat_last_stages = kDenseStages;
     if (h->opt_timing && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));
     rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nqb, n_slices, static_cast<uint32_t>(k),
-                           dev_D + static_cast<size_t>(q0) * k, dev_I + static_cast<size_t>(q0) * k, id_base, st);
+                           dev_D + static_cast<size_t>(q0) * k, dev_I + static_cast<size_t>(q0) * k, id_base, st,
+                           /*sorted_lists=*/tp);
     if (rc) return rc;
   }
   if (h->opt_timing) {
