@@ -90,35 +90,44 @@ class ClockSampler:
         self._t0 = time.time()
 
     def end(self):
-        self.windows.append((self._t0, time.time()))
+        w = (self._t0, time.time())
+        self.windows.append(w)
+        return w
 
     def stop(self):
+        """Stops nvidia-smi and parses every sample once; `summary(windows)` then filters by time."""
         import datetime
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.rows = []
         if self.proc is None:
-            return out
+            return
         time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        rows = [ln.strip().split(",") for ln in open(self.tmp.name) if ln.strip()]
-        os.unlink(self.tmp.name)
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
+        for ln in open(self.tmp.name):
+            r = ln.strip().split(",")
             try:
                 ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                if self.windows and not any(a - 0.05 <= ts <= b + 0.05 for a, b in self.windows):
-                    continue
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                pw.append(float(r[3]))
+                self.rows.append((ts, float(r[1]), float(r[2]), float(r[3]), [v.strip().lower() for v in r[4:8]]))
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(names, r[4:8]):
-                if v.strip().lower().startswith("active"):
+        os.unlink(self.tmp.name)
+        self.proc = None
+
+    def summary(self, windows):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, c, m, w, flags in getattr(self, "rows", []):
+            if windows and not any(a - 0.05 <= ts <= b + 0.05 for a, b in windows):
+                continue
+            sm.append(c)
+            mx.append(m)
+            pw.append(w)
+            for name, v in zip(names, flags):
+                if v.startswith("active"):
                     reasons.add(name)
         if sm:
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
@@ -135,6 +144,8 @@ def cpu_baseline(rows_full: int, d: int, k: int, batch: int, sample_rows: int, s
     L = flat_ip_c.load(native=True)
     blas = flat_ip_c.try_attach_blas(L) if batch >= 20 else None
     n = min(rows_full, sample_rows)
+    if batch >= 20:   # sgemm path: keep one call near 1e12 flop so that the arm finishes in seconds
+        n = min(n, max(100_000, int(1e12 / (2.0 * batch * d))))
     g = torch.Generator().manual_seed(1234)
     xb = torch.randn((n, d), generator=g)
     xb /= xb.norm(dim=1, keepdim=True)
@@ -224,110 +235,147 @@ def run_ours(args):
             raise SystemExit(f"rows/gpus must keep shard starts on {chunk}-row boundaries")
         index.add_local(adder, lo, hi - lo, R)
         local = index.local
-        search_dev = lambda q: index.search_torch(q, k)
-        search_host = lambda qh: index.search(qh, k)
     else:
         index = faiss.IndexFlatIP(d, dtype=args.dtype, device=local_rank, retain_fp32=False)
         fill_index_random(index, R, chunk_rows=chunk)
         local = index
-        Dbuf = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        Ibuf = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        search_dev = lambda q: index.search_torch(q, k, out=(Dbuf, Ibuf))
-        search_host = lambda qh: index.search(qh, k)
     n_local = local.ntotal
-
-    qh = random_unit_queries(nq, d)
-    q = torch.from_numpy(qh).to(dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident throughput ---------------------------------------------------------
     clk = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(args.warmup):
-        search_dev(q)
-    barrier()
-    launches0 = local.stat("launches")
-    if clk:
-        clk.begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = search_dev(q)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    if clk:
-        clk.end()
-    launches = local.stat("launches") - launches0 + (args.steps if world > 1 else 0)   # + K5 merge per step
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = nq * args.steps / (ms_total / 1e3)
 
-    # ---- end to end through the host-buffer API ---------------------------------------------
-    for _ in range(min(args.warmup, 3)):
-        search_host(qh)
-    barrier()
-    if clk:
-        clk.begin()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        Dh, Ih = search_host(qh)
-    torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    if clk:
-        clk.end()
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_qps = nq * args.steps / float(t.item())
+    def measure(nq, steps, warmup):
+        """One batch size: device-resident throughput, end-to-end throughput, roofline of the scan kernel."""
+        qh = random_unit_queries(nq, d)
+        q = torch.from_numpy(qh).to(dev)
+        if world > 1:
+            search_dev = lambda qq: index.search_torch(qq, k)
+        else:
+            Dbuf = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            Ibuf = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            search_dev = lambda qq: index.search_torch(qq, k, out=(Dbuf, Ibuf))
+        search_host = lambda qq: index.search(qq, k)
+        windows = []
+        # ---- device-resident throughput ------------------------------------------------------
+        for _ in range(warmup):
+            search_dev(q)
+        barrier()
+        launches0 = local.stat("launches")
+        if clk:
+            clk.begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            search_dev(q)
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        if clk:
+            windows.append(clk.end())
+        launches = local.stat("launches") - launches0 + (steps if world > 1 else 0)   # + K5 merge per step
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        value = nq * steps / (ms_total / 1e3)
+        # ---- end to end through the host-buffer API ------------------------------------------
+        for _ in range(min(warmup, 3)):
+            search_host(qh)
+        barrier()
+        if clk:
+            clk.begin()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            search_host(qh)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if clk:
+            windows.append(clk.end())
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_qps = nq * steps / float(t.item())
+        # ---- roofline of the dominant kernel (the scan), CUDA events on its stream ---------------
+        local.set_option("timing", 1)
+        scan_ns = []
+        for _ in range(max(3, min(steps, 20))):
+            search_dev(q)
+            scan_ns.append(local.stat("last_scan_ns"))
+        local.set_option("timing", 0)
+        scan_ms = statistics.mean(scan_ns) / 1e6
+        dense = nq >= local.stat("dense_min_nq")
+        if dense and nq > 128:
+            # tensor-core regime: 2*nq*N_local*d flop per launch (SURVEY §8d; top-k work is not counted)
+            flops = 2.0 * nq * n_local * d
+            achieved = flops / (scan_ms / 1e3) / 1e12
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"],
+                        "peak_kind": "cuBLAS bf16 sustained (kernel timed inside a long step)",
+                        "kernel": "scan_dense2_kernel", "algorithmic_flops_per_launch": flops, "kernel_ms": scan_ms,
+                        "frac_of_burst": achieved / pk["bf16_tflops"], "frac_of_nominal_2250": achieved / 2250.0}
+        else:
+            alg_bytes = n_local * d * 2
+            achieved = alg_bytes / (scan_ms / 1e3) / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                        "kernel": "scan_dense_kernel" if dense else "scan_small_kernel",
+                        "algorithmic_bytes_per_launch": alg_bytes,
+                        "kernel_ms": scan_ms, "frac_of_nominal_8TBs": achieved / 8000.0}
+            traffic_file = ROOT / "profiles" / "traffic.json"
+            if traffic_file.exists() and not dense:   # dram bytes per row from the committed ncu capture
+                tj = json.loads(traffic_file.read_text())
+                if "dram_bytes_per_row_d512" in tj and d == 512:
+                    roofline["traffic"] = tj["dram_bytes_per_row_d512"] * n_local
+        return {"batch": nq, "value": value, "ms_per_step": ms_total / steps, "steps": steps, "warmup": warmup,
+                "gpu_launches": int(launches),
+                "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(nq * d * 4),
+                        "d2h_bytes_per_step": int(nq * k * 12)},
+                "roofline": roofline, "_windows": windows}
 
-    # ---- roofline of the dominant kernel (the scan), measured live with CUDA events ----------
-    local.set_option("timing", 1)
-    scan_ns = []
-    for _ in range(max(5, min(args.steps, 20))):
-        search_dev(q)
-        scan_ns.append(local.stat("last_scan_ns"))
-    local.set_option("timing", 0)
-    clocks = clk.stop() if clk else None
-    scan_ms = statistics.mean(scan_ns) / 1e6
-    alg_bytes = n_local * d * 2
-    achieved = alg_bytes / (scan_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                "kernel": "scan_small_kernel", "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel_ms": scan_ms, "frac_of_nominal_8TBs": achieved / 8000.0}
-    traffic_file = ROOT / "profiles" / "traffic.json"
-    if traffic_file.exists():   # dram bytes per row from the committed ncu capture (profiles/)
-        tj = json.loads(traffic_file.read_text())
-        if "dram_bytes_per_row_d512" in tj and d == 512:
-            roofline["traffic"] = tj["dram_bytes_per_row_d512"] * n_local
+    nq = args.batch
+    main = measure(nq, args.steps, args.warmup)
+    others = {}
+    if not args.no_extras:   # the metric's other batch sizes on the same resident index (BASELINE.json: 1 / 4096; C4: 1024)
+        for b in (1024, 4096):
+            if b != nq:
+                others[f"batch{b}"] = measure(b, max(3, min(args.steps, 5)), 3)
+    if clk:
+        clk.stop()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    def public(m):
+        m = dict(m)
+        m["clocks"] = clk.summary(m.pop("_windows")) if clk else None
+        return m
+
+    main = public(main)
     line = {
-        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "metric": METRIC, "value": main["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
         "config": {"workload": f"{R}x{d} {args.dtype} index row-sharded over {world} GPU(s), batch {nq}, k={k}",
                    "rows": R, "dim": d, "k": k, "batch": nq, "rows_per_gpu": n_local,
                    "l2": f"inputs larger than L2: every step streams the {n_local * d * 2 / 1e9:.1f} GB shard from HBM"},
-        "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(nq * d * 4),
-                "d2h_bytes_per_step": int(nq * k * 12)},
-        "roofline": roofline,
+        "clocks": main["clocks"], "gpu_launches": main["gpu_launches"],
+        "e2e": main["e2e"],
+        "roofline": main["roofline"],
     }
+    for name, m in others.items():
+        line[name] = public(m)
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(R, d, k, nq, args.cpu_sample_rows, max(3, min(args.steps, 10)), 1)
         if not args.no_extras:
+            if "batch4096" in line:
+                line["batch4096"]["cpu_baseline"] = cpu_baseline(R, d, k, 4096, args.cpu_sample_rows, 2, 1)
+            index.close()   # free the 100 GB index before the side configs allocate theirs
             line["extras"] = extras(faiss, fill_index_random, random_unit_queries, torch, dev, pk)
     print(json.dumps(line), flush=True)
     if world > 1:

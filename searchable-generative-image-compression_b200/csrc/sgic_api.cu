@@ -1101,6 +1101,7 @@ int64_t sgic_index_get_stat(const sgic_index* h, const char* name) {
   if (n == "last_stages") return h->stat_last_stages;
   if (n == "capacity") return h->capacity;
   if (n == "sm_count") return h->sm_count;
+  if (n == "dense_min_nq") return h->opt_dense_min_nq;
   if (n == "retained_rows") return h->retain_ok ? static_cast<int64_t>(h->retained.size() / h->d) : -1;
   return -1;
 }
