@@ -19,11 +19,14 @@
 #include <vector>
 
 #include "../../include/sgic.h"
+#include "zstd_lit.cuh"
 
 namespace sgic {
 void set_error(const std::string& msg);  // defined in sgic_api.cu
 
 namespace {
+
+constexpr size_t kZlMaxFrameBytes = 2560;  // = kZlMaxFrame of the decode kernel (ingest.cuh)
 
 struct ZstdApi {
   void* lib = nullptr;
@@ -280,8 +283,12 @@ int walk_one(const uint8_t* data, size_t n, Found* f) {
   return SGIC_C2DF_OK;
 }
 
+// dev_frame != nullptr: frames inside the device decoder's profile (csrc/zstd_lit.cuh) are not decoded here;
+// their position is reported instead (*dev_frame = stream start, *dev_len = its length) and the row is filled
+// in by zstd_lit_decode_kernel.  libzstd stays the judge of everything else.
 int parse_one(const ZstdApi& z, void* dctx, const uint8_t* data, size_t n, int want_dim, uint8_t* out_row,
-              int32_t* dim_out, std::vector<uint8_t>& scratch) {
+              int32_t* dim_out, std::vector<uint8_t>& scratch, const uint8_t** dev_frame = nullptr,
+              uint32_t* dev_len = nullptr) {
   *dim_out = 0;
   Found f;
   int st = walk_one(data, n, &f);
@@ -303,6 +310,15 @@ int parse_one(const ZstdApi& z, void* dctx, const uint8_t* data, size_t n, int w
   if (fcs == ~0ull || fcs == ~0ull - 1) return SGIC_C2DF_ZSTD;
   if (fcs > (1ull << 26)) return SGIC_C2DF_ZSTD;
   if (static_cast<long long>(fcs) == dim && dim == want_dim) {
+    if (dev_frame != nullptr && f.stream_len <= kZlMaxFrameBytes) {
+      zl::FrameInfo fi;
+      if (zl::parse_frame(f.stream, static_cast<uint32_t>(f.stream_len), fi) == zl::ZL_OK &&
+          fi.content_size == static_cast<uint32_t>(dim)) {
+        *dev_frame = f.stream;
+        *dev_len = static_cast<uint32_t>(f.stream_len);
+        return SGIC_C2DF_OK;
+      }
+    }
     const size_t r = z.decompressDCtx(dctx, out_row, static_cast<size_t>(dim), f.stream, f.stream_len);
     if (z.isError(r)) return SGIC_C2DF_ZSTD;
     if (static_cast<long long>(r) != dim) return SGIC_C2DF_DIM_MISMATCH;
@@ -318,8 +334,10 @@ int parse_one(const ZstdApi& z, void* dctx, const uint8_t* data, size_t n, int w
 
 }  // namespace
 
+// frame_off / frame_len (both or neither): per file, the offset into `blob` and length of a clip_stream frame
+// left for the device decoder, or -1 / 0 when the row was decoded here.
 int c2df_parse_batch(const uint8_t* blob, const int64_t* offsets, int64_t n, int dim, uint8_t* out_u8,
-                     int32_t* status_out, int32_t* dim_out, int n_threads) {
+                     int32_t* status_out, int32_t* dim_out, int n_threads, int64_t* frame_off, uint32_t* frame_len) {
   const ZstdApi& z = zstd_api();
   if (!z.ok) {
     set_error("libzstd.so.1 could not be loaded (dlopen) — required for clip_stream decoding");
@@ -346,11 +364,17 @@ int c2df_parse_batch(const uint8_t* blob, const int64_t* offsets, int64_t n, int
         const int64_t o0 = offsets[i], o1 = offsets[i + 1];
         int32_t dd = 0;
         int st;
+        const uint8_t* dfr = nullptr;
+        uint32_t dlen = 0;
         if (o1 < o0) {
           st = SGIC_C2DF_TRUNCATED;
         } else {
           st = parse_one(z, dctx, blob + o0, static_cast<size_t>(o1 - o0), dim,
-                         out_u8 + static_cast<size_t>(i) * dim, &dd, scratch);
+                         out_u8 + static_cast<size_t>(i) * dim, &dd, scratch, frame_off ? &dfr : nullptr, &dlen);
+        }
+        if (frame_off) {
+          frame_off[i] = dfr ? static_cast<int64_t>(dfr - blob) : -1;
+          frame_len[i] = dlen;
         }
         status_out[i] = st;
         if (dim_out) dim_out[i] = dd;

@@ -6,8 +6,12 @@
 //                        same fp32 operation order, eps = 1e-9).
 //   unpack_rows_kernel : 16-bit rows -> fp32 (write_index / reconstruct).
 // All three are HBM/PCIe-bound byte movers: 128-bit accesses, grid-stride.
+//   K0 zstd_lit_decode_kernel: clip_stream zstd frames -> u8 rows on the device (replaces the
+//                        ZstdDecompressor().decompress of src/search.py:35 for frames in the profile of
+//                        zstd_lit.cuh), feeding K1.
 #pragma once
 #include "ptx.cuh"
+#include "zstd_lit.cuh"
 
 namespace sgic {
 
@@ -102,6 +106,99 @@ __global__ void __launch_bounds__(256) dequant_u8_kernel(const uint8_t* __restri
       v.w = pack2_rn<T>(z[6], z[7]);
       o[g] = v;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K0
+constexpr uint32_t kZlMaxFrame = 2560;      // frame bytes staged per warp (d <= 2048 raw worst case + headers)
+constexpr int kZlWarpsPerBlock = 4;
+
+struct ZlDesc {
+  uint32_t row;  // destination row in the u8 matrix
+  uint32_t off;  // frame start in the packed frame buffer (16-byte aligned)
+  uint32_t len;
+  uint32_t pad;
+};
+
+struct __align__(16) ZlWarpSmem {
+  uint8_t frame[kZlMaxFrame];
+  uint16_t tab[1u << zl::kHufMaxLog];
+  uint8_t w[256];
+  uint8_t nb[256];
+  zl::FseTable ft;
+  uint32_t info[12];
+};
+
+// One warp per frame.  The frame is staged in shared memory with 16-byte loads; lane 0 parses the headers and
+// decodes the Huffman tree description (FSE-compressed weights: inherently serial, ~100 symbols); all lanes
+// fill the 2^max_bits decoding table; lanes 0..3 decode the four backward bitstreams in parallel straight into
+// the u8 row.  status[f] = zl::ZL_OK or the reason the frame has to go back to libzstd on the host.
+__global__ void __launch_bounds__(kZlWarpsPerBlock * 32)
+zstd_lit_decode_kernel(const uint8_t* __restrict__ frames, const ZlDesc* __restrict__ desc, uint32_t n_frames,
+                       uint32_t d, uint8_t* __restrict__ rows, int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t zl_smem_raw[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ZlWarpSmem& S = reinterpret_cast<ZlWarpSmem*>(zl_smem_raw)[warp];
+  const uint32_t n_warps = gridDim.x * kZlWarpsPerBlock;
+  for (uint32_t f = blockIdx.x * kZlWarpsPerBlock + warp; f < n_frames; f += n_warps) {
+    const ZlDesc de = desc[f];
+    if (de.len > kZlMaxFrame) {  // the host never sends one; defensive
+      if (lane == 0) status[f] = zl::ZL_HOST;
+      continue;
+    }
+    for (uint32_t i = lane * 16; i < de.len; i += 32 * 16)
+      *reinterpret_cast<uint4*>(S.frame + i) = __ldg(reinterpret_cast<const uint4*>(frames + de.off + i));
+    __syncwarp();
+    if (lane == 0) {
+      zl::FrameInfo fi;
+      int rc = zl::parse_frame(S.frame, de.len, fi);
+      if (rc == zl::ZL_OK && fi.content_size != d) rc = zl::ZL_HOST;
+      uint32_t td = 0, nsym = 0, max_bits = 0;
+      const bool huf = rc == zl::ZL_OK && fi.block_type == 2 && fi.lit_type == 2;
+      if (huf) {
+        td = zl::huf_read_lengths(S.frame + fi.lit_off, fi.comp, S.w, S.nb, nsym, max_bits, S.ft);
+        if (td == 0) rc = zl::ZL_CORRUPT;
+      }
+      S.info[0] = static_cast<uint32_t>(rc);
+      S.info[1] = huf ? 2u : (fi.block_type == 1 || (fi.block_type == 2 && fi.lit_type == 1)) ? 1u : 0u;  // 0 raw 1 rle 2 huffman
+      S.info[2] = (fi.block_type == 2) ? fi.lit_off : fi.block_off;  // payload start
+      S.info[3] = fi.comp;
+      S.info[4] = fi.n_streams;
+      S.info[5] = td;
+      S.info[6] = nsym;
+      S.info[7] = max_bits;
+    }
+    __syncwarp();
+    const int rc = static_cast<int>(S.info[0]);
+    if (rc != zl::ZL_OK) {
+      if (lane == 0) status[f] = rc;
+      __syncwarp();
+      continue;
+    }
+    uint8_t* dst = rows + static_cast<size_t>(de.row) * d;
+    const uint32_t kind = S.info[1], pay = S.info[2];
+    bool ok = true;
+    if (kind == 0) {
+      for (uint32_t i = lane; i < d; i += 32) dst[i] = S.frame[pay + i];
+    } else if (kind == 1) {
+      const uint8_t b = S.frame[pay];
+      for (uint32_t i = lane; i < d; i += 32) dst[i] = b;
+    } else {
+      const uint32_t comp = S.info[3], n_streams = S.info[4], td = S.info[5], nsym = S.info[6], max_bits = S.info[7];
+      ok = zl::huf_fill_table(S.nb, nsym, max_bits, S.tab, lane, 32);
+      __syncwarp();
+      uint32_t soff[4], slen[4], scnt[4];
+      const uint8_t* ss = S.frame + pay + td;
+      ok = ok && zl::huf_stream_layout(ss, comp - td, n_streams, d, soff, slen, scnt);
+      if (ok && lane < n_streams) {
+        uint32_t o = 0;
+        for (uint32_t i = 0; i < lane; ++i) o += scnt[i];
+        ok = zl::huf_decode_stream(S.tab, max_bits, ss + soff[lane], slen[lane], dst + o, scnt[lane]);
+      }
+    }
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) status[f] = all_ok ? zl::ZL_OK : zl::ZL_CORRUPT;
+    __syncwarp();  // the next frame overwrites this warp's shared memory
   }
 }
 

@@ -22,7 +22,8 @@ static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 
 int c2df_parse_batch(const uint8_t* blob, const int64_t* offsets, int64_t n, int dim, uint8_t* out_u8,
-                     int32_t* status_out, int32_t* dim_out, int n_threads);
+                     int32_t* status_out, int32_t* dim_out, int n_threads, int64_t* frame_off = nullptr,
+                     uint32_t* frame_len = nullptr);
 
 #define SGIC_CUDA(call)                                                                         \
   do {                                                                                          \
@@ -78,8 +79,19 @@ struct sgic_index {
   size_t ws_bytes = 0;
   void* qh = nullptr;  // queries rounded to the storage dtype (dense path operand A)
   size_t qh_bytes = 0;
-  void* lists_ws = nullptr;  // dense path: per-CTA top-k lists when they do not fit in shared memory
+  void* lists_ws = nullptr;  // dense path, k > 32: per-query reservoirs
   size_t lists_ws_bytes = 0;
+  // device-side clip_stream decode (K0): u8 row matrix, packed frames, descriptors, per-frame status
+  void* zl_rows = nullptr;
+  size_t zl_rows_bytes = 0;
+  void* zl_frames = nullptr;
+  size_t zl_frames_bytes = 0;
+  void* zl_desc = nullptr;
+  size_t zl_desc_bytes = 0;
+  void* zl_status = nullptr;
+  size_t zl_status_bytes = 0;
+  void* zl_status_host = nullptr;
+  size_t zl_status_host_bytes = 0;
   void* qdev = nullptr;  // queries / outputs for the host-buffer search
   size_t qdev_bytes = 0;
   void* odev = nullptr;
@@ -91,7 +103,8 @@ struct sgic_index {
   std::vector<float> retained;
   bool retain_ok = false;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 5, opt_debug = 0, opt_dense_mode = 0;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 5, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1;
+  int64_t stat_zl_device_frames = 0, stat_zl_host_rows = 0, stat_zl_fallback_slabs = 0;
   int64_t stat_launches = 0, stat_last_search_ns = 0, stat_last_scan_ns = 0, stat_last_grid = 0, stat_last_stages = 0;
 };
 
@@ -678,6 +691,11 @@ int sgic_index_destroy(sgic_index* h) {
   if (h->qdev) cudaFree(h->qdev);
   if (h->qh) cudaFree(h->qh);
   if (h->lists_ws) cudaFree(h->lists_ws);
+  if (h->zl_rows) cudaFree(h->zl_rows);
+  if (h->zl_frames) cudaFree(h->zl_frames);
+  if (h->zl_desc) cudaFree(h->zl_desc);
+  if (h->zl_status) cudaFree(h->zl_status);
+  if (h->zl_status_host) cudaFreeHost(h->zl_status_host);
   if (h->odev) cudaFree(h->odev);
   if (h->opin) cudaFreeHost(h->opin);
   if (h->db) cudaFree(h->db);
@@ -833,6 +851,57 @@ int sgic_c2df_parse(const uint8_t* blob, const int64_t* offsets, int64_t n, int 
   return c2df_parse_batch(blob, offsets, n, dim, out_u8, status_out, dim_out, n_threads);
 }
 
+// Appends `w` rows: rows named by `desc` are clip_stream frames decoded on the device (K0) into the u8 matrix,
+// the others are already in `rows` (decoded by libzstd on the host); then K1 expands the matrix into the
+// database.  *bad = true (and nothing appended) if the device rejects a frame: the caller redoes the slab with
+// libzstd, which stays the judge of malformed input.
+static int add_u8_with_frames(sgic_index* h, int64_t w, const uint8_t* rows, int64_t n_host_rows,
+                              const std::vector<uint8_t>& frames, const std::vector<sgic::ZlDesc>& desc, bool* bad) {
+  using namespace sgic;
+  *bad = false;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->stream;
+  int rc = ensure_capacity(h, h->ntotal + w, st);
+  if (rc) return rc;
+  const size_t d = static_cast<size_t>(h->d);
+  const uint32_t nf = static_cast<uint32_t>(desc.size());
+  if ((rc = ensure_buf(&h->zl_rows, &h->zl_rows_bytes, static_cast<size_t>(w) * d, false))) return rc;
+  if ((rc = ensure_buf(&h->zl_frames, &h->zl_frames_bytes, frames.size() + 16, false))) return rc;
+  if ((rc = ensure_buf(&h->zl_desc, &h->zl_desc_bytes, desc.size() * sizeof(ZlDesc), false))) return rc;
+  if ((rc = ensure_buf(&h->zl_status, &h->zl_status_bytes, static_cast<size_t>(nf) * 4, false))) return rc;
+  if ((rc = ensure_buf(&h->zl_status_host, &h->zl_status_host_bytes, static_cast<size_t>(nf) * 4, true))) return rc;
+  if (n_host_rows > 0)
+    SGIC_CUDA(cudaMemcpyAsync(h->zl_rows, rows, static_cast<size_t>(w) * d, cudaMemcpyHostToDevice, st));
+  SGIC_CUDA(cudaMemcpyAsync(h->zl_frames, frames.data(), frames.size(), cudaMemcpyHostToDevice, st));
+  SGIC_CUDA(cudaMemcpyAsync(h->zl_desc, desc.data(), desc.size() * sizeof(ZlDesc), cudaMemcpyHostToDevice, st));
+  const size_t smem = static_cast<size_t>(kZlWarpsPerBlock) * sizeof(ZlWarpSmem);
+  const unsigned grid = std::min<unsigned>((nf + kZlWarpsPerBlock - 1) / kZlWarpsPerBlock,
+                                           static_cast<unsigned>(h->sm_count) * 7u);
+  zstd_lit_decode_kernel<<<grid, kZlWarpsPerBlock * 32, smem, st>>>(
+      static_cast<const uint8_t*>(h->zl_frames), static_cast<const ZlDesc*>(h->zl_desc), nf, static_cast<uint32_t>(d),
+      static_cast<uint8_t*>(h->zl_rows), static_cast<int32_t*>(h->zl_status));
+  h->stat_launches++;
+  SGIC_CUDA(cudaGetLastError());
+  SGIC_CUDA(cudaMemcpyAsync(h->zl_status_host, h->zl_status, static_cast<size_t>(nf) * 4, cudaMemcpyDeviceToHost, st));
+  SGIC_CUDA(cudaStreamSynchronize(st));
+  const int32_t* stt = static_cast<const int32_t*>(h->zl_status_host);
+  for (uint32_t i = 0; i < nf; ++i)
+    if (stt[i] != zl::ZL_OK) {
+      *bad = true;
+      return 0;
+    }
+  rc = launch_dequant_u8(h, static_cast<const uint8_t*>(h->zl_rows), h->ntotal, w, st);
+  if (rc) return rc;
+  SGIC_CUDA(cudaStreamSynchronize(st));
+  h->retain_ok = false;
+  h->retained.clear();
+  h->ntotal += w;
+  h->stat_zl_device_frames += nf;
+  h->stat_zl_host_rows += n_host_rows;
+  return 0;
+}
+
 int sgic_index_add_c2df(sgic_index* h, const uint8_t* blob, const int64_t* offsets, int64_t n, int32_t* status_out,
                         int64_t* n_added, int n_threads) {
   SGIC_REQUIRE(h != nullptr, "index is NULL");
@@ -840,28 +909,72 @@ int sgic_index_add_c2df(sgic_index* h, const uint8_t* blob, const int64_t* offse
   if (n_added) *n_added = 0;
   if (n == 0) return 0;
   const size_t d = static_cast<size_t>(h->d);
-  // Decode in slabs so that host memory stays bounded and zstd overlaps the H2D + K1 of the
-  // previous slab (stream_rows_h2d is asynchronous until its final synchronise).
-  const int64_t slab = std::max<int64_t>(1, static_cast<int64_t>((256u << 20) / d));
-  std::vector<uint8_t> rows;
+  const bool dev_dec = h->opt_device_zstd != 0;
+  // Slabs keep host memory bounded.  Host-only decode: 256 MB of rows per slab (zstd overlaps the H2D + K1 of the
+  // previous chunk inside add_u8).  Device decode: the host only walks the TLV container and copies ~300-byte
+  // frames, so slabs are smaller and the decode kernel + K1 of a slab run while nothing else is pending.
+  const int64_t slab = dev_dec ? 131072 : std::max<int64_t>(1, static_cast<int64_t>((256u << 20) / d));
+  std::vector<uint8_t> rows, frames;
+  std::vector<int64_t> foff;
+  std::vector<uint32_t> flen;
+  std::vector<sgic::ZlDesc> desc;
   int64_t added = 0;
   for (int64_t s0 = 0; s0 < n; s0 += slab) {
     const int64_t cnt = std::min(slab, n - s0);
     rows.resize(static_cast<size_t>(cnt) * d);
-    int rc = c2df_parse_batch(blob, offsets + s0, cnt, h->d, rows.data(), status_out + s0, nullptr, n_threads);
+    if (dev_dec) {
+      foff.resize(static_cast<size_t>(cnt));
+      flen.resize(static_cast<size_t>(cnt));
+    }
+    int rc = c2df_parse_batch(blob, offsets + s0, cnt, h->d, rows.data(), status_out + s0, nullptr, n_threads,
+                              dev_dec ? foff.data() : nullptr, dev_dec ? flen.data() : nullptr);
     if (rc) return rc;
-    // compact the good rows in place (order preserved, as build.py's `keep` list does)
-    int64_t w = 0;
+    // compact the good rows in place (order preserved, as build.py's `keep` list does); frames left for the
+    // device are packed back to back (16-byte aligned) and keep their slot in the row matrix
+    int64_t w = 0, n_host_rows = 0;
+    frames.clear();
+    desc.clear();
     for (int64_t i = 0; i < cnt; ++i) {
       if (status_out[s0 + i] != SGIC_C2DF_OK) continue;
-      if (w != i) std::memmove(rows.data() + static_cast<size_t>(w) * d, rows.data() + static_cast<size_t>(i) * d, d);
+      if (dev_dec && foff[static_cast<size_t>(i)] >= 0) {
+        const uint32_t len = flen[static_cast<size_t>(i)];
+        const size_t off = frames.size();
+        frames.insert(frames.end(), blob + foff[static_cast<size_t>(i)], blob + foff[static_cast<size_t>(i)] + len);
+        frames.resize((frames.size() + 15) & ~static_cast<size_t>(15));
+        desc.push_back(sgic::ZlDesc{static_cast<uint32_t>(w), static_cast<uint32_t>(off), len, 0u});
+      } else {
+        if (w != i)
+          std::memmove(rows.data() + static_cast<size_t>(w) * d, rows.data() + static_cast<size_t>(i) * d, d);
+        ++n_host_rows;
+      }
       ++w;
     }
-    if (w > 0) {
+    if (w == 0) continue;
+    if (desc.empty()) {
       rc = sgic_index_add_u8(h, w, rows.data());
       if (rc) return rc;
-      added += w;
+    } else {
+      bool bad = false;
+      rc = add_u8_with_frames(h, w, rows.data(), n_host_rows, frames, desc, &bad);
+      if (rc) return rc;
+      if (bad) {  // a frame the device could not decode: libzstd decides for the whole slab
+        h->stat_zl_fallback_slabs++;
+        rc = c2df_parse_batch(blob, offsets + s0, cnt, h->d, rows.data(), status_out + s0, nullptr, n_threads);
+        if (rc) return rc;
+        w = 0;
+        for (int64_t i = 0; i < cnt; ++i) {
+          if (status_out[s0 + i] != SGIC_C2DF_OK) continue;
+          if (w != i)
+            std::memmove(rows.data() + static_cast<size_t>(w) * d, rows.data() + static_cast<size_t>(i) * d, d);
+          ++w;
+        }
+        if (w > 0) {
+          rc = sgic_index_add_u8(h, w, rows.data());
+          if (rc) return rc;
+        }
+      }
     }
+    added += w;
   }
   if (n_added) *n_added = added;
   return 0;
@@ -1078,6 +1191,7 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "dense_min_nq") h->opt_dense_min_nq = value;
   else if (n == "debug") h->opt_debug = value;
   else if (n == "dense_mode") h->opt_dense_mode = value;
+  else if (n == "device_zstd") h->opt_device_zstd = value;
   else if (n == "drop_retained") {
     std::lock_guard<std::mutex> lk(h->mu);
     h->retain_ok = false;
@@ -1102,6 +1216,9 @@ int64_t sgic_index_get_stat(const sgic_index* h, const char* name) {
   if (n == "capacity") return h->capacity;
   if (n == "sm_count") return h->sm_count;
   if (n == "dense_min_nq") return h->opt_dense_min_nq;
+  if (n == "zl_device_frames") return h->stat_zl_device_frames;
+  if (n == "zl_host_rows") return h->stat_zl_host_rows;
+  if (n == "zl_fallback_slabs") return h->stat_zl_fallback_slabs;
   if (n == "retained_rows") return h->retain_ok ? static_cast<int64_t>(h->retained.size() / h->d) : -1;
   return -1;
 }

@@ -184,3 +184,98 @@ def test_from_npy_dir_matches_sorted_glob_order(tmp_path):
     order = sorted(range(25), key=lambda i: f"im{(i * 7) % 25:03d}")
     want = vecs[order] / (np.linalg.norm(vecs[order], axis=1, keepdims=True) + 1e-12)
     assert np.array_equal(x, want.astype(np.float32))         # fp32 rows kept bit-exact on disk
+
+
+def _c2df_blobs(vecs, rng, full_size=True):
+    """Reference-style .c2df files (src/compress.py:250-275: codec streams + clip_stream + clip_meta)."""
+    from sgic_b200 import c2df
+    from sgic_b200.index_build import quantize_u8_and_compress
+    blobs = []
+    for z in vecs:
+        payload, meta = quantize_u8_and_compress(z)
+        enc = {}
+        if full_size:
+            enc["z_bit_stream"] = bytes(rng.integers(0, 256, 700, dtype=np.uint8))
+            enc["h_bit_stream"] = bytes(rng.integers(0, 256, 800, dtype=np.uint8))
+            enc["img_shape"] = [1, 3, 256, 256]
+            enc["token_length"] = 256
+        enc["clip_stream"] = payload
+        enc["clip_meta"] = meta
+        blobs.append(c2df.pack_c2df(enc, {"version": 2, "note": "synthetic"}))
+    return blobs
+
+
+@pytest.mark.parametrize("d", [512, 768, 128])
+def test_device_zstd_decode_equals_host_decode(d):
+    """K0: clip_stream frames decoded on the device give bit-identical rows and statuses to
+    libzstd on the host (src/search.py:35), frame by frame, including the files that stay on the host (frames
+    with match sequences) and the files that are skipped."""
+    from sgic_b200 import faiss_compat as faiss, c2df
+    rng = np.random.default_rng(d)
+    n = 3000
+    vecs = rng.standard_normal((n, d)).astype(np.float32)
+    vecs[::3] = vecs[::3] / np.linalg.norm(vecs[::3], axis=1, keepdims=True) + 1.0 / np.sqrt(d)   # CLIP-cone third
+    vecs /= np.linalg.norm(vecs, axis=1, keepdims=True)
+    blobs = _c2df_blobs(vecs, rng, full_size=(d == 512))
+    # malformed / foreign files sprinkled in: they must be skipped identically on both routes
+    blobs[10] = b"XXXXnot a container"
+    blobs[500] = c2df.pack_c2df({"token_length": 1}, {"version": 2})
+    blobs[501] = blobs[501][:len(blobs[501]) // 2]
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in blobs], out=offs[1:])
+    blob = np.frombuffer(b"".join(blobs), dtype=np.uint8)
+    out = {}
+    for mode in (1, 0):
+        idx = faiss.IndexFlatIP(d, device=0)
+        idx.set_option("device_zstd", mode)
+        added, status = idx.add_c2df(blob, offs, n_threads=4)
+        out[mode] = (added, status.copy(), idx.reconstruct_n(0, added), idx.stat("zl_device_frames"),
+                     idx.stat("zl_host_rows"), idx.stat("zl_fallback_slabs"))
+        idx.close()
+    assert out[1][0] == out[0][0] == n - 3
+    assert np.array_equal(out[1][1], out[0][1])
+    assert np.array_equal(out[1][2], out[0][2])            # bit-identical database rows
+    assert out[0][3] == 0                                  # host mode never launches K0
+    dev, host = out[1][3], out[1][4]
+    assert dev + host == n - 3 and out[1][5] == 0
+    assert dev > (0.5 if d == 768 else 0.7) * n, (dev, host)   # most frames carry no sequences (F1z)
+    # and the rows are what the reference decodes
+    want = c2df_ref.dequantize_clip_u8(
+        np.stack([np.frombuffer(__import__("sgic_b200").zstd.decompress(c2df.unpack_c2df(b)[0]["clip_stream"]),
+                                dtype=np.uint8) for b in blobs[:8]]))
+    assert fp16_ulp_diff(out[1][2][:8], want).max() <= 1
+
+
+def test_device_zstd_corrupt_frame_falls_back_to_libzstd():
+    """A damaged entropy stream inside an in-profile frame: the device refuses it, the slab is redone by
+    libzstd (the decoder the reference uses), and the outcome (status codes, rows, order) equals the host-only
+    route."""
+    from sgic_b200 import faiss_compat as faiss, c2df
+    rng = np.random.default_rng(99)
+    n, d = 600, 512
+    vecs = rng.standard_normal((n, d)).astype(np.float32)
+    vecs /= np.linalg.norm(vecs, axis=1, keepdims=True)
+    blobs = _c2df_blobs(vecs, rng, full_size=False)
+    damaged = 0
+    for i in range(0, n, 37):
+        enc, hdr = c2df.unpack_c2df(blobs[i])
+        fr = bytearray(enc["clip_stream"])
+        fr[len(fr) - 2 - (i % 40)] ^= 0x5A            # inside the Huffman streams
+        enc["clip_stream"] = bytes(fr)
+        blobs[i] = c2df.pack_c2df(enc, hdr)
+        damaged += 1
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in blobs], out=offs[1:])
+    blob = np.frombuffer(b"".join(blobs), dtype=np.uint8)
+    res = {}
+    for mode in (1, 0):
+        idx = faiss.IndexFlatIP(d, device=0)
+        idx.set_option("device_zstd", mode)
+        added, status = idx.add_c2df(blob, offs, n_threads=2)
+        res[mode] = (added, status.copy(), idx.reconstruct_n(0, added), idx.stat("zl_fallback_slabs"))
+        idx.close()
+    assert res[1][0] == res[0][0] and np.array_equal(res[1][1], res[0][1]) and np.array_equal(res[1][2], res[0][2])
+    # libzstd 1.5.5 regenerates (different) bytes from these frames without complaint; the device decoder checks
+    # that every stream is consumed exactly (RFC 8878 4.2.2), refuses, and hands the slab to libzstd — so the
+    # reference's behaviour is reproduced either way
+    assert res[1][3] >= 1
