@@ -382,6 +382,54 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def ingest_extra(faiss, dev, n_distinct=20_000, tile=10, d=512):
+    """North-star item (a): batched .c2df ingest (TLV walk on the host cores, clip_stream decode, K1 on the
+    device) in files/s — device-side zstd decode (K0) against the libzstd-on-host route, same corpus: `n_distinct`
+    reference-style files (~2.3 KB: codec streams + clip_stream + clip_meta) repeated `tile` times."""
+    import numpy as np
+    from sgic_b200 import c2df
+    from sgic_b200.index_build import quantize_u8_and_compress
+    rng = np.random.default_rng(5)
+    vecs = rng.standard_normal((n_distinct, d)).astype(np.float32)
+    vecs /= np.linalg.norm(vecs, axis=1, keepdims=True)
+    filler_z = bytes(rng.integers(0, 256, 769, dtype=np.uint8))
+    filler_h = bytes(rng.integers(0, 256, 807, dtype=np.uint8))
+    blobs = []
+    for z in vecs:
+        payload, meta = quantize_u8_and_compress(z)
+        blobs.append(c2df.pack_c2df({"z_bit_stream": filler_z, "h_bit_stream": filler_h, "img_shape": [1, 3, 256, 256],
+                                     "token_length": 256, "clip_stream": payload, "clip_meta": meta}, {"version": 2}))
+    one = b"".join(blobs)
+    lens = np.array([len(b) for b in blobs], dtype=np.int64)
+    blob = np.frombuffer(one * tile, dtype=np.uint8)
+    offs = np.zeros(n_distinct * tile + 1, dtype=np.int64)
+    np.cumsum(np.tile(lens, tile), out=offs[1:])
+    n = n_distinct * tile
+    out = {"workload": f"{n} .c2df files ({blob.size / 1e6:.0f} MB, mean {blob.size / n:.0f} B), d={d}, host threads = all",
+           "host_threads": os.cpu_count()}
+    for mode, name in ((1, "device_zstd"), (0, "host_zstd")):
+        idx = faiss.IndexFlatIP(d, device=dev.index, retain_fp32=False)
+        idx.set_option("device_zstd", mode)
+        idx.set_option("timing", 1)
+        nw = min(n, 140_000)
+        idx.add_c2df(blob[:offs[nw]], offs[:nw + 1])   # warm-up with a full slab: buffers, libzstd contexts, kernels
+        ph0 = [idx.stat(k) for k in ("ingest_parse_ns", "ingest_pack_ns", "ingest_gpu_ns")]
+        t0 = time.perf_counter()
+        added, status = idx.add_c2df(blob, offs)
+        dt = time.perf_counter() - t0
+        out[name] = {"files_per_s": n / dt, "MB_per_s": blob.size / dt / 1e6, "seconds": dt, "added": int(added),
+                     "frames_decoded_on_device": idx.stat("zl_device_frames"), "rows_decoded_on_host": idx.stat("zl_host_rows")}
+        if mode:
+            ph1 = [idx.stat(k) for k in ("ingest_parse_ns", "ingest_pack_ns", "ingest_gpu_ns")]
+            out[name]["phase_ms"] = {"walk_classify_hostzstd": (ph1[0] - ph0[0]) / 1e6, "pack_pinned": (ph1[1] - ph0[1]) / 1e6,
+                                     "h2d_k0_k1": (ph1[2] - ph0[2]) / 1e6,
+                                     "device_h2d_incl_warmup": idx.stat("ingest_h2d_ns") / 1e6,
+                                     "device_k0_decode_incl_warmup": idx.stat("ingest_k0_ns") / 1e6,
+                                     "device_k1_dequant_incl_warmup": idx.stat("ingest_k1_ns") / 1e6}
+        idx.close()
+    return out
+
+
 def extras(faiss, fill_index_random, random_unit_queries, torch, dev, pk):
     """Other BASELINE.json configs that fit one GPU, measured the same way (not the headline)."""
     res = []
@@ -408,6 +456,10 @@ def extras(faiss, fill_index_random, random_unit_queries, torch, dev, pk):
         res.append({"workload": name, "ms_per_step": m, "queries_per_s": nq / m * 1e3, "GBs": gbs,
                     "frac_of_measured_hbm": gbs / pk["hbm_gbs"], "l2": "flushed between iterations (256 MB memset)"})
         idx.close()
+    try:
+        res.append({"ingest": ingest_extra(faiss, dev)})
+    except Exception as e:   # the ingest figure is a side measurement: never lose the headline line over it
+        res.append({"ingest": {"error": repr(e)}})
     return res
 
 

@@ -393,4 +393,74 @@ int c2df_parse_batch(const uint8_t* blob, const int64_t* offsets, int64_t n, int
   return 0;
 }
 
+// Second half of the device-decode route: after c2df_parse_batch has classified a slab, lay the good files out
+// for the GPU.  Row w of the u8 matrix belongs to the w-th good file; a file decoded on the host has its row
+// copied to rows_out[w], a file left to the device has its frame copied (16-byte aligned) into frames_out and
+// gets a descriptor.  The prefix sums are serial (a few ns per file); the copies run on `n_threads` threads.
+int c2df_pack_batch(const uint8_t* blob, int64_t cnt, int dim, const int32_t* status, const int64_t* frame_off,
+                    const uint32_t* frame_len, const uint8_t* rows_in, uint8_t* rows_out, uint8_t* frames_out,
+                    size_t frames_cap, ZlDesc* desc_out, int64_t* n_rows_out, int64_t* n_frames_out,
+                    int64_t* n_host_rows_out, size_t* frames_bytes_out, int n_threads) {
+  std::vector<int64_t> wi(static_cast<size_t>(cnt));      // output row of file i (-1: skipped)
+  std::vector<uint32_t> fo(static_cast<size_t>(cnt));     // frame offset (device files)
+  std::vector<uint32_t> fk(static_cast<size_t>(cnt));     // descriptor index (device files)
+  int64_t w = 0, nf = 0, nh = 0;
+  size_t fbytes = 0;
+  for (int64_t i = 0; i < cnt; ++i) {
+    if (status[i] != SGIC_C2DF_OK) {
+      wi[static_cast<size_t>(i)] = -1;
+      continue;
+    }
+    wi[static_cast<size_t>(i)] = w++;
+    if (frame_off[i] >= 0) {
+      fo[static_cast<size_t>(i)] = static_cast<uint32_t>(fbytes);
+      fk[static_cast<size_t>(i)] = static_cast<uint32_t>(nf++);
+      fbytes += (static_cast<size_t>(frame_len[i]) + 15u) & ~static_cast<size_t>(15);
+    } else {
+      ++nh;
+    }
+  }
+  if (fbytes + 16 > frames_cap) {
+    set_error("c2df_pack: frame buffer too small");
+    return 1;
+  }
+  *n_rows_out = w;
+  *n_frames_out = nf;
+  *n_host_rows_out = nh;
+  *frames_bytes_out = fbytes;
+  if (n_threads <= 0) n_threads = static_cast<int>(std::thread::hardware_concurrency());
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 64) n_threads = 64;
+  std::atomic<int64_t> next{0};
+  constexpr int64_t kGrain = 1024;
+  const size_t d = static_cast<size_t>(dim);
+  auto work = [&]() {
+    for (;;) {
+      const int64_t b = next.fetch_add(kGrain);
+      if (b >= cnt) break;
+      const int64_t e = (b + kGrain < cnt) ? b + kGrain : cnt;
+      for (int64_t i = b; i < e; ++i) {
+        const int64_t r = wi[static_cast<size_t>(i)];
+        if (r < 0) continue;
+        if (frame_off[i] >= 0) {
+          std::memcpy(frames_out + fo[static_cast<size_t>(i)], blob + frame_off[i], frame_len[i]);
+          desc_out[fk[static_cast<size_t>(i)]] =
+              ZlDesc{static_cast<uint32_t>(r), fo[static_cast<size_t>(i)], frame_len[i], 0u};
+        } else {
+          std::memcpy(rows_out + static_cast<size_t>(r) * d, rows_in + static_cast<size_t>(i) * d, d);
+        }
+      }
+    }
+  };
+  if (n_threads == 1 || cnt < 4 * kGrain) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    th.reserve(n_threads);
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work);
+    for (auto& t : th) t.join();
+  }
+  return 0;
+}
+
 }  // namespace sgic

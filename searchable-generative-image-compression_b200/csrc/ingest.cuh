@@ -113,13 +113,6 @@ __global__ void __launch_bounds__(256) dequant_u8_kernel(const uint8_t* __restri
 constexpr uint32_t kZlMaxFrame = 2560;      // frame bytes staged per warp (d <= 2048 raw worst case + headers)
 constexpr int kZlWarpsPerBlock = 4;
 
-struct ZlDesc {
-  uint32_t row;  // destination row in the u8 matrix
-  uint32_t off;  // frame start in the packed frame buffer (16-byte aligned)
-  uint32_t len;
-  uint32_t pad;
-};
-
 struct __align__(16) ZlWarpSmem {
   uint8_t frame[kZlMaxFrame];
   uint16_t tab[1u << zl::kHufMaxLog];

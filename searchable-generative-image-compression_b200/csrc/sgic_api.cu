@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -24,6 +26,10 @@ void set_error(const std::string& msg) { g_err = msg; }
 int c2df_parse_batch(const uint8_t* blob, const int64_t* offsets, int64_t n, int dim, uint8_t* out_u8,
                      int32_t* status_out, int32_t* dim_out, int n_threads, int64_t* frame_off = nullptr,
                      uint32_t* frame_len = nullptr);
+int c2df_pack_batch(const uint8_t* blob, int64_t cnt, int dim, const int32_t* status, const int64_t* frame_off,
+                    const uint32_t* frame_len, const uint8_t* rows_in, uint8_t* rows_out, uint8_t* frames_out,
+                    size_t frames_cap, ZlDesc* desc_out, int64_t* n_rows_out, int64_t* n_frames_out,
+                    int64_t* n_host_rows_out, size_t* frames_bytes_out, int n_threads);
 
 #define SGIC_CUDA(call)                                                                         \
   do {                                                                                          \
@@ -92,6 +98,12 @@ struct sgic_index {
   size_t zl_status_bytes = 0;
   void* zl_status_host = nullptr;
   size_t zl_status_host_bytes = 0;
+  void* zl_pin_rows = nullptr;  // pinned staging of a slab: u8 matrix, packed frames, descriptors
+  size_t zl_pin_rows_bytes = 0;
+  void* zl_pin_frames = nullptr;
+  size_t zl_pin_frames_bytes = 0;
+  void* zl_pin_desc = nullptr;
+  size_t zl_pin_desc_bytes = 0;
   void* qdev = nullptr;  // queries / outputs for the host-buffer search
   size_t qdev_bytes = 0;
   void* odev = nullptr;
@@ -104,6 +116,8 @@ struct sgic_index {
   bool retain_ok = false;
   // options / stats
   int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 5, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1;
+  int64_t stat_ingest_h2d_ns = 0, stat_ingest_k0_ns = 0, stat_ingest_k1_ns = 0;
+  int64_t stat_ingest_parse_ns = 0, stat_ingest_pack_ns = 0, stat_ingest_gpu_ns = 0;
   int64_t stat_zl_device_frames = 0, stat_zl_host_rows = 0, stat_zl_fallback_slabs = 0;
   int64_t stat_launches = 0, stat_last_search_ns = 0, stat_last_scan_ns = 0, stat_last_grid = 0, stat_last_stages = 0;
 };
@@ -696,6 +710,9 @@ int sgic_index_destroy(sgic_index* h) {
   if (h->zl_desc) cudaFree(h->zl_desc);
   if (h->zl_status) cudaFree(h->zl_status);
   if (h->zl_status_host) cudaFreeHost(h->zl_status_host);
+  if (h->zl_pin_rows) cudaFreeHost(h->zl_pin_rows);
+  if (h->zl_pin_frames) cudaFreeHost(h->zl_pin_frames);
+  if (h->zl_pin_desc) cudaFreeHost(h->zl_pin_desc);
   if (h->odev) cudaFree(h->odev);
   if (h->opin) cudaFreeHost(h->opin);
   if (h->db) cudaFree(h->db);
@@ -851,12 +868,12 @@ int sgic_c2df_parse(const uint8_t* blob, const int64_t* offsets, int64_t n, int 
   return c2df_parse_batch(blob, offsets, n, dim, out_u8, status_out, dim_out, n_threads);
 }
 
-// Appends `w` rows: rows named by `desc` are clip_stream frames decoded on the device (K0) into the u8 matrix,
-// the others are already in `rows` (decoded by libzstd on the host); then K1 expands the matrix into the
-// database.  *bad = true (and nothing appended) if the device rejects a frame: the caller redoes the slab with
-// libzstd, which stays the judge of malformed input.
-static int add_u8_with_frames(sgic_index* h, int64_t w, const uint8_t* rows, int64_t n_host_rows,
-                              const std::vector<uint8_t>& frames, const std::vector<sgic::ZlDesc>& desc, bool* bad) {
+// Appends `w` rows staged in the index's pinned slab buffers: rows named by the `nf` descriptors are clip_stream
+// frames decoded on the device (K0) into the u8 matrix, the others were decoded by libzstd on the host and sit
+// in the matrix already; then K1 expands the matrix into the database.  *bad = true (and nothing appended) if
+// the device rejects a frame: the caller redoes the slab with libzstd, which stays the judge of malformed input.
+static int add_u8_with_frames(sgic_index* h, int64_t w, int64_t n_host_rows, size_t frames_bytes, int64_t nf64,
+                              bool* bad) {
   using namespace sgic;
   *bad = false;
   std::lock_guard<std::mutex> lk(h->mu);
@@ -865,16 +882,20 @@ static int add_u8_with_frames(sgic_index* h, int64_t w, const uint8_t* rows, int
   int rc = ensure_capacity(h, h->ntotal + w, st);
   if (rc) return rc;
   const size_t d = static_cast<size_t>(h->d);
-  const uint32_t nf = static_cast<uint32_t>(desc.size());
+  const uint32_t nf = static_cast<uint32_t>(nf64);
   if ((rc = ensure_buf(&h->zl_rows, &h->zl_rows_bytes, static_cast<size_t>(w) * d, false))) return rc;
-  if ((rc = ensure_buf(&h->zl_frames, &h->zl_frames_bytes, frames.size() + 16, false))) return rc;
-  if ((rc = ensure_buf(&h->zl_desc, &h->zl_desc_bytes, desc.size() * sizeof(ZlDesc), false))) return rc;
+  if ((rc = ensure_buf(&h->zl_frames, &h->zl_frames_bytes, frames_bytes + 16, false))) return rc;
+  if ((rc = ensure_buf(&h->zl_desc, &h->zl_desc_bytes, static_cast<size_t>(nf) * sizeof(ZlDesc), false))) return rc;
   if ((rc = ensure_buf(&h->zl_status, &h->zl_status_bytes, static_cast<size_t>(nf) * 4, false))) return rc;
   if ((rc = ensure_buf(&h->zl_status_host, &h->zl_status_host_bytes, static_cast<size_t>(nf) * 4, true))) return rc;
+  const bool tm = h->opt_timing != 0;  // per-phase device times (bench / probes only)
+  if (tm) SGIC_CUDA(cudaEventRecord(h->t0, st));
   if (n_host_rows > 0)
-    SGIC_CUDA(cudaMemcpyAsync(h->zl_rows, rows, static_cast<size_t>(w) * d, cudaMemcpyHostToDevice, st));
-  SGIC_CUDA(cudaMemcpyAsync(h->zl_frames, frames.data(), frames.size(), cudaMemcpyHostToDevice, st));
-  SGIC_CUDA(cudaMemcpyAsync(h->zl_desc, desc.data(), desc.size() * sizeof(ZlDesc), cudaMemcpyHostToDevice, st));
+    SGIC_CUDA(cudaMemcpyAsync(h->zl_rows, h->zl_pin_rows, static_cast<size_t>(w) * d, cudaMemcpyHostToDevice, st));
+  SGIC_CUDA(cudaMemcpyAsync(h->zl_frames, h->zl_pin_frames, frames_bytes, cudaMemcpyHostToDevice, st));
+  SGIC_CUDA(cudaMemcpyAsync(h->zl_desc, h->zl_pin_desc, static_cast<size_t>(nf) * sizeof(ZlDesc),
+                            cudaMemcpyHostToDevice, st));
+  if (tm) SGIC_CUDA(cudaEventRecord(h->tm, st));
   const size_t smem = static_cast<size_t>(kZlWarpsPerBlock) * sizeof(ZlWarpSmem);
   const unsigned grid = std::min<unsigned>((nf + kZlWarpsPerBlock - 1) / kZlWarpsPerBlock,
                                            static_cast<unsigned>(h->sm_count) * 7u);
@@ -883,17 +904,32 @@ static int add_u8_with_frames(sgic_index* h, int64_t w, const uint8_t* rows, int
       static_cast<uint8_t*>(h->zl_rows), static_cast<int32_t*>(h->zl_status));
   h->stat_launches++;
   SGIC_CUDA(cudaGetLastError());
+  if (tm) SGIC_CUDA(cudaEventRecord(h->t1, st));
   SGIC_CUDA(cudaMemcpyAsync(h->zl_status_host, h->zl_status, static_cast<size_t>(nf) * 4, cudaMemcpyDeviceToHost, st));
   SGIC_CUDA(cudaStreamSynchronize(st));
+  if (tm) {
+    float ms = 0.f;
+    SGIC_CUDA(cudaEventElapsedTime(&ms, h->t0, h->tm));
+    h->stat_ingest_h2d_ns += static_cast<int64_t>(ms * 1e6);
+    SGIC_CUDA(cudaEventElapsedTime(&ms, h->tm, h->t1));
+    h->stat_ingest_k0_ns += static_cast<int64_t>(ms * 1e6);
+  }
   const int32_t* stt = static_cast<const int32_t*>(h->zl_status_host);
   for (uint32_t i = 0; i < nf; ++i)
     if (stt[i] != zl::ZL_OK) {
       *bad = true;
       return 0;
     }
+  if (tm) SGIC_CUDA(cudaEventRecord(h->t0, st));
   rc = launch_dequant_u8(h, static_cast<const uint8_t*>(h->zl_rows), h->ntotal, w, st);
   if (rc) return rc;
+  if (tm) SGIC_CUDA(cudaEventRecord(h->t1, st));
   SGIC_CUDA(cudaStreamSynchronize(st));
+  if (tm) {
+    float ms = 0.f;
+    SGIC_CUDA(cudaEventElapsedTime(&ms, h->t0, h->t1));
+    h->stat_ingest_k1_ns += static_cast<int64_t>(ms * 1e6);
+  }
   h->retain_ok = false;
   h->retained.clear();
   h->ntotal += w;
@@ -911,70 +947,107 @@ int sgic_index_add_c2df(sgic_index* h, const uint8_t* blob, const int64_t* offse
   const size_t d = static_cast<size_t>(h->d);
   const bool dev_dec = h->opt_device_zstd != 0;
   // Slabs keep host memory bounded.  Host-only decode: 256 MB of rows per slab (zstd overlaps the H2D + K1 of the
-  // previous chunk inside add_u8).  Device decode: the host only walks the TLV container and copies ~300-byte
-  // frames, so slabs are smaller and the decode kernel + K1 of a slab run while nothing else is pending.
+  // previous chunk inside add_u8).  Device decode: the host walks the TLV container, lets libzstd decode only the
+  // frames outside the device profile, and packs ~300-byte frames into pinned memory (all on n_threads threads);
+  // one H2D + K0 + K1 per slab.
   const int64_t slab = dev_dec ? 131072 : std::max<int64_t>(1, static_cast<int64_t>((256u << 20) / d));
-  std::vector<uint8_t> rows, frames;
+  struct RawBuf {  // uninitialised host rows (a std::vector would memset 64 MB per slab)
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    ~RawBuf() { std::free(p); }
+    uint8_t* data() { return p; }
+    bool resize(size_t n) {
+      if (n <= cap) return true;
+      std::free(p);
+      p = static_cast<uint8_t*>(std::malloc(n));
+      cap = p ? n : 0;
+      return p != nullptr;
+    }
+  } rows;
   std::vector<int64_t> foff;
   std::vector<uint32_t> flen;
-  std::vector<sgic::ZlDesc> desc;
   int64_t added = 0;
-  for (int64_t s0 = 0; s0 < n; s0 += slab) {
-    const int64_t cnt = std::min(slab, n - s0);
-    rows.resize(static_cast<size_t>(cnt) * d);
-    if (dev_dec) {
-      foff.resize(static_cast<size_t>(cnt));
-      flen.resize(static_cast<size_t>(cnt));
+  auto host_route = [&](int64_t s0, int64_t cnt, bool reparse) -> int {
+    int rc = 0;
+    if (reparse) {
+      rc = sgic::c2df_parse_batch(blob, offsets + s0, cnt, h->d, rows.data(), status_out + s0, nullptr, n_threads);
+      if (rc) return rc;
     }
-    int rc = c2df_parse_batch(blob, offsets + s0, cnt, h->d, rows.data(), status_out + s0, nullptr, n_threads,
-                              dev_dec ? foff.data() : nullptr, dev_dec ? flen.data() : nullptr);
-    if (rc) return rc;
-    // compact the good rows in place (order preserved, as build.py's `keep` list does); frames left for the
-    // device are packed back to back (16-byte aligned) and keep their slot in the row matrix
-    int64_t w = 0, n_host_rows = 0;
-    frames.clear();
-    desc.clear();
+    // compact the good rows in place (order preserved, as build.py's `keep` list does)
+    int64_t w = 0;
     for (int64_t i = 0; i < cnt; ++i) {
       if (status_out[s0 + i] != SGIC_C2DF_OK) continue;
-      if (dev_dec && foff[static_cast<size_t>(i)] >= 0) {
-        const uint32_t len = flen[static_cast<size_t>(i)];
-        const size_t off = frames.size();
-        frames.insert(frames.end(), blob + foff[static_cast<size_t>(i)], blob + foff[static_cast<size_t>(i)] + len);
-        frames.resize((frames.size() + 15) & ~static_cast<size_t>(15));
-        desc.push_back(sgic::ZlDesc{static_cast<uint32_t>(w), static_cast<uint32_t>(off), len, 0u});
-      } else {
-        if (w != i)
-          std::memmove(rows.data() + static_cast<size_t>(w) * d, rows.data() + static_cast<size_t>(i) * d, d);
-        ++n_host_rows;
-      }
+      if (w != i) std::memmove(rows.data() + static_cast<size_t>(w) * d, rows.data() + static_cast<size_t>(i) * d, d);
       ++w;
     }
-    if (w == 0) continue;
-    if (desc.empty()) {
+    if (w > 0) {
       rc = sgic_index_add_u8(h, w, rows.data());
       if (rc) return rc;
-    } else {
-      bool bad = false;
-      rc = add_u8_with_frames(h, w, rows.data(), n_host_rows, frames, desc, &bad);
-      if (rc) return rc;
-      if (bad) {  // a frame the device could not decode: libzstd decides for the whole slab
-        h->stat_zl_fallback_slabs++;
-        rc = c2df_parse_batch(blob, offsets + s0, cnt, h->d, rows.data(), status_out + s0, nullptr, n_threads);
-        if (rc) return rc;
-        w = 0;
-        for (int64_t i = 0; i < cnt; ++i) {
-          if (status_out[s0 + i] != SGIC_C2DF_OK) continue;
-          if (w != i)
-            std::memmove(rows.data() + static_cast<size_t>(w) * d, rows.data() + static_cast<size_t>(i) * d, d);
-          ++w;
-        }
-        if (w > 0) {
-          rc = sgic_index_add_u8(h, w, rows.data());
-          if (rc) return rc;
-        }
-      }
+      added += w;
     }
-    added += w;
+    return 0;
+  };
+  for (int64_t s0 = 0; s0 < n; s0 += slab) {
+    const int64_t cnt = std::min(slab, n - s0);
+    SGIC_REQUIRE(rows.resize(static_cast<size_t>(cnt) * d), "out of host memory for the row slab");
+    if (!dev_dec) {
+      int rc = host_route(s0, cnt, true);
+      if (rc) return rc;
+      continue;
+    }
+    foff.resize(static_cast<size_t>(cnt));
+    flen.resize(static_cast<size_t>(cnt));
+    auto now_ns = [] {
+      return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch())
+          .count();
+    };
+    const int64_t t_a = now_ns();
+    int rc = sgic::c2df_parse_batch(blob, offsets + s0, cnt, h->d, rows.data(), status_out + s0, nullptr, n_threads,
+                                    foff.data(), flen.data());
+    if (rc) return rc;
+    const int64_t t_b = now_ns();
+    h->stat_ingest_parse_ns += t_b - t_a;
+    int64_t w = 0, nf = 0, nh = 0;
+    size_t fbytes = 0;
+    {
+      std::lock_guard<std::mutex> lk(h->mu);
+      sgic::DeviceGuard g(h->device);
+      // pinned slab buffers: sized once for a full slab of typical frames (grown only if a slab needs more)
+      const size_t frames_need = static_cast<size_t>(slab) * 640 + (1u << 20);
+      if ((rc = sgic::ensure_buf(&h->zl_pin_rows, &h->zl_pin_rows_bytes, static_cast<size_t>(slab) * d, true))) return rc;
+      if ((rc = sgic::ensure_buf(&h->zl_pin_desc, &h->zl_pin_desc_bytes, static_cast<size_t>(slab) * sizeof(sgic::ZlDesc), true)))
+        return rc;
+      size_t need = 0;
+      for (int64_t i = 0; i < cnt; ++i)
+        if (status_out[s0 + i] == SGIC_C2DF_OK && foff[static_cast<size_t>(i)] >= 0)
+          need += (static_cast<size_t>(flen[static_cast<size_t>(i)]) + 15u) & ~static_cast<size_t>(15);
+      if ((rc = sgic::ensure_buf(&h->zl_pin_frames, &h->zl_pin_frames_bytes, std::max(need + 16, frames_need), true)))
+        return rc;
+    }
+    rc = sgic::c2df_pack_batch(blob, cnt, h->d, status_out + s0, foff.data(), flen.data(), rows.data(),
+                               static_cast<uint8_t*>(h->zl_pin_rows), static_cast<uint8_t*>(h->zl_pin_frames),
+                               h->zl_pin_frames_bytes, static_cast<sgic::ZlDesc*>(h->zl_pin_desc), &w, &nf, &nh, &fbytes,
+                               n_threads);
+    if (rc) return rc;
+    const int64_t t_c = now_ns();
+    h->stat_ingest_pack_ns += t_c - t_b;
+    if (w == 0) continue;
+    if (nf == 0) {  // nothing for the device in this slab
+      rc = host_route(s0, cnt, false);
+      if (rc) return rc;
+      continue;
+    }
+    bool bad = false;
+    rc = add_u8_with_frames(h, w, nh, fbytes, nf, &bad);
+    if (rc) return rc;
+    h->stat_ingest_gpu_ns += now_ns() - t_c;
+    if (bad) {  // a frame the device could not decode: libzstd decides for the whole slab
+      h->stat_zl_fallback_slabs++;
+      rc = host_route(s0, cnt, true);
+      if (rc) return rc;
+    } else {
+      added += w;
+    }
   }
   if (n_added) *n_added = added;
   return 0;
@@ -1216,6 +1289,12 @@ int64_t sgic_index_get_stat(const sgic_index* h, const char* name) {
   if (n == "capacity") return h->capacity;
   if (n == "sm_count") return h->sm_count;
   if (n == "dense_min_nq") return h->opt_dense_min_nq;
+  if (n == "ingest_h2d_ns") return h->stat_ingest_h2d_ns;
+  if (n == "ingest_k0_ns") return h->stat_ingest_k0_ns;
+  if (n == "ingest_k1_ns") return h->stat_ingest_k1_ns;
+  if (n == "ingest_parse_ns") return h->stat_ingest_parse_ns;
+  if (n == "ingest_pack_ns") return h->stat_ingest_pack_ns;
+  if (n == "ingest_gpu_ns") return h->stat_ingest_gpu_ns;
   if (n == "zl_device_frames") return h->stat_zl_device_frames;
   if (n == "zl_host_rows") return h->stat_zl_host_rows;
   if (n == "zl_fallback_slabs") return h->stat_zl_fallback_slabs;

@@ -23,6 +23,15 @@
 #endif
 
 namespace sgic {
+
+// one frame handed to the decode kernel (K0, ingest.cuh)
+struct ZlDesc {
+  uint32_t row;  // destination row in the u8 matrix
+  uint32_t off;  // frame start in the packed frame buffer (16-byte aligned)
+  uint32_t len;
+  uint32_t pad;
+};
+
 namespace zl {
 
 enum : int {
