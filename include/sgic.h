@@ -116,6 +116,16 @@ int sgic_merge_topk_dev(int device, int64_t nq, int n_lists, int64_t k, const fl
 int sgic_index_write(sgic_index* h, const char* path);
 int sgic_index_read(const char* path, int dtype, int device, int flags, sgic_index** out);
 
+/* On-disk format v2 "SGI2" (additive): a 4 KB header page followed by the rows exactly as
+ * they sit in HBM (fp16 / bf16).  Half the bytes of the fp32 IxFI file that src/search.py:69,76 re-reads for
+ * every query process, no conversion on load.  sgic_index_read recognises both formats by their magic, so
+ * load_index (src/search.py:65-88) works on either file.  row_start / total_rows / shard / n_shards describe
+ * where the rows sit in a row-sharded logical index (single file: 0, -1, 0, 1). */
+int sgic_index_write_v2(sgic_index* h, const char* path, int64_t row_start, int64_t total_rows, int shard,
+                        int n_shards);
+/* out4 = {row_start, total_rows, shard, n_shards} of an index loaded from an SGI2 file. */
+int sgic_index_shard_info(const sgic_index* h, int64_t* out4);
+
 /* rows [i0, i0+n) up-cast to fp32 (faiss reconstruct_n); host buffer. */
 int sgic_index_reconstruct(sgic_index* h, int64_t i0, int64_t n, float* host_out);
 

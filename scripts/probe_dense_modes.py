@@ -40,6 +40,13 @@ for nq in nqs:
                 samples.append(e0.elapsed_time(e1) / reps)
             samples.sort()
             ms, best = samples[len(samples) // 2], samples[0]
+            idx.set_option("timing", 1)
+            sc, tot = [], []
+            for _ in range(5):
+                idx.search_torch(q, k, out=(D, I))
+                sc.append(idx.stat("last_scan_ns") / 1e6)
+                tot.append(idx.stat("last_search_ns") / 1e6)
+            idx.set_option("timing", 0)
             tf = 2 * nq * n * d / ms / 1e9
             print(f"nq={nq:5d} mode={names[mode]:12s} skipEpi={dbg >> 2} ms={ms:8.3f} (best {best:8.3f}) TF={tf:7.0f} "
-                  f"({tf / 1404.9:.3f} of sustained)  GB/s={n * d * 2 / ms / 1e6:6.0f}  qps={nq / ms * 1e3:9.0f}", flush=True)
+                  f"({tf / 1404.9:.3f} of sustained)  GB/s={n * d * 2 / ms / 1e6:6.0f}  qps={nq / ms * 1e3:9.0f}  [timed alone: scan {min(sc):.3f} total {min(tot):.3f}]", flush=True)

@@ -47,6 +47,8 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "sgic_index_write": (C.c_int, [C.c_void_p, C.c_char_p]),
     "sgic_index_read": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "sgic_index_write_v2": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "sgic_index_shard_info": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sgic_index_reconstruct": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "sgic_index_data_dev": (C.c_void_p, [C.c_void_p]),
     "sgic_index_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),

@@ -114,6 +114,9 @@ struct sgic_index {
   // retained fp32 rows (SGIC_RETAIN_F32)
   std::vector<float> retained;
   bool retain_ok = false;
+  // shard placement recorded in / restored from an SGI2 file (single index: 0, ntotal, 0, 1)
+  int64_t shard_row_start = 0, shard_total_rows = -1;
+  int shard_id = 0, shard_count = 1;
   // options / stats
   int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 5, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1;
   int64_t stat_ingest_h2d_ns = 0, stat_ingest_k0_ns = 0, stat_ingest_k1_ns = 0;
@@ -1198,6 +1201,143 @@ int sgic_index_write(sgic_index* h, const char* path) {
   return 0;
 }
 
+
+// ---- on-disk format v2 "SGI2"  ------------------------------------------------------------
+// The rows exactly as they sit in HBM (fp16 / bf16, row-major) behind a 4 KB header page, so that loading a
+// shard is read() into pinned memory + one H2D copy per chunk — half the bytes of the fp32 "IxFI" file and no
+// conversion.  IxFI stays the interchange format (sgic_index_write); sgic_index_read recognises both.
+struct Sgi2Header {
+  char magic[4];          // "SGI2"
+  uint32_t version;       // 1
+  uint32_t dtype;         // SGIC_F16 | SGIC_BF16
+  uint32_t d;
+  int64_t ntotal;         // rows in this file
+  int64_t row_start;      // global number of this file's first row
+  int64_t total_rows;     // rows of the whole logical index
+  uint32_t shard, n_shards;
+  uint64_t payload_offset;  // 4096
+  uint8_t reserved[8];
+};
+static_assert(sizeof(Sgi2Header) == 64, "SGI2 header is 64 bytes");
+constexpr uint64_t kSgi2Payload = 4096;
+
+int sgic_index_write_v2(sgic_index* h, const char* path, int64_t row_start, int64_t total_rows, int shard,
+                        int n_shards) {
+  SGIC_REQUIRE(h != nullptr && path != nullptr, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  int rc = ensure_staging(h);
+  if (rc) return rc;
+  FILE* f = std::fopen(path, "wb");
+  if (!f) {
+    set_error(std::string("could not open ") + path + " for writing");
+    return 3;
+  }
+  std::vector<uint8_t> page(kSgi2Payload, 0);
+  Sgi2Header hd;
+  std::memset(&hd, 0, sizeof(hd));
+  std::memcpy(hd.magic, "SGI2", 4);
+  hd.version = 1;
+  hd.dtype = static_cast<uint32_t>(h->dtype);
+  hd.d = static_cast<uint32_t>(h->d);
+  hd.ntotal = h->ntotal;
+  hd.row_start = row_start;
+  hd.total_rows = total_rows < 0 ? h->ntotal : total_rows;
+  hd.shard = static_cast<uint32_t>(shard);
+  hd.n_shards = static_cast<uint32_t>(n_shards < 1 ? 1 : n_shards);
+  hd.payload_offset = kSgi2Payload;
+  std::memcpy(page.data(), &hd, sizeof(hd));
+  bool ok = std::fwrite(page.data(), 1, page.size(), f) == page.size();
+  // D2H through the pinned double buffer: the copy of chunk i+1 runs while chunk i is written
+  const size_t total = elt_rows_bytes(h, h->ntotal);
+  size_t issued = 0, written = 0;
+  size_t len[2] = {0, 0};
+  int b = 0;
+  SGIC_CUDA(cudaStreamSynchronize(h->stream));
+  if (total > 0) {
+    len[0] = std::min(total, kStageChunkBytes);
+    SGIC_CUDA(cudaMemcpyAsync(h->pin[0], static_cast<const uint8_t*>(h->db), len[0], cudaMemcpyDeviceToHost, h->stream));
+    SGIC_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    issued = len[0];
+  }
+  while (ok && written < total) {
+    if (issued < total) {
+      len[b ^ 1] = std::min(total - issued, kStageChunkBytes);
+      SGIC_CUDA(cudaMemcpyAsync(h->pin[b ^ 1], static_cast<const uint8_t*>(h->db) + issued, len[b ^ 1],
+                                cudaMemcpyDeviceToHost, h->stream));
+      SGIC_CUDA(cudaEventRecord(h->ev[b ^ 1], h->stream));
+      issued += len[b ^ 1];
+    }
+    SGIC_CUDA(cudaEventSynchronize(h->ev[b]));
+    ok = std::fwrite(h->pin[b], 1, len[b], f) == len[b];
+    written += len[b];
+    b ^= 1;
+  }
+  ok = (std::fclose(f) == 0) && ok;
+  if (!ok) {
+    set_error(std::string("write error on ") + path);
+    return 3;
+  }
+  return 0;
+}
+
+static int read_v2_body(FILE* f, const char* path, const Sgi2Header& hd, int device, int flags, sgic_index** out) {
+  if (hd.version != 1 || hd.dtype > 1 || hd.d == 0 || hd.ntotal < 0 || hd.payload_offset < sizeof(Sgi2Header)) {
+    set_error(std::string("corrupt SGI2 header in ") + path);
+    return 3;
+  }
+  sgic_index* h = nullptr;
+  int rc = sgic_index_create(static_cast<int>(hd.d), static_cast<int>(hd.dtype), device, hd.ntotal, flags & ~SGIC_RETAIN_F32, &h);
+  if (rc) return rc;
+  auto fail = [&](const std::string& msg, int code) {
+    sgic_index_destroy(h);
+    set_error(msg);
+    return code;
+  };
+  if (std::fseek(f, static_cast<long>(hd.payload_offset), SEEK_SET) != 0) return fail(std::string("seek error in ") + path, 3);
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    rc = ensure_staging(h);
+    if (rc) {
+      sgic_index_destroy(h);
+      return rc;
+    }
+    const size_t total = elt_rows_bytes(h, hd.ntotal);
+    size_t done = 0;
+    int b = 0;
+    while (done < total) {
+      const size_t n = std::min(total - done, kStageChunkBytes);
+      if (cudaEventSynchronize(h->ev[b]) != cudaSuccess) return fail("cudaEventSynchronize failed while loading", 2);
+      if (std::fread(h->pin[b], 1, n, f) != n)
+        return fail(std::string("read error in ") + path + ": file shorter than its header says", 3);
+      if (cudaMemcpyAsync(static_cast<uint8_t*>(h->db) + done, h->pin[b], n, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+          cudaEventRecord(h->ev[b], h->stream) != cudaSuccess)
+        return fail("H2D copy failed while loading", 2);
+      done += n;
+      b ^= 1;
+    }
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail("stream synchronise failed while loading", 2);
+    h->ntotal = hd.ntotal;
+    h->retain_ok = false;
+    h->shard_row_start = hd.row_start;
+    h->shard_total_rows = hd.total_rows;
+    h->shard_id = static_cast<int>(hd.shard);
+    h->shard_count = static_cast<int>(hd.n_shards);
+  }
+  *out = h;
+  return 0;
+}
+
+int sgic_index_shard_info(const sgic_index* h, int64_t* out4) {
+  SGIC_REQUIRE(h != nullptr && out4 != nullptr, "NULL argument");
+  out4[0] = h->shard_row_start;
+  out4[1] = h->shard_total_rows < 0 ? h->ntotal : h->shard_total_rows;
+  out4[2] = h->shard_id;
+  out4[3] = h->shard_count;
+  return 0;
+}
+
 int sgic_index_read(const char* path, int dtype, int device, int flags, sgic_index** out) {
   SGIC_REQUIRE(path != nullptr && out != nullptr, "NULL argument");
   *out = nullptr;
@@ -1206,6 +1346,20 @@ int sgic_index_read(const char* path, int dtype, int device, int flags, sgic_ind
     set_error(std::string("could not open ") + path + " for reading");
     return 3;
   }
+  char magic[4] = {0, 0, 0, 0};
+  if (std::fread(magic, 1, 4, f) == 4 && std::memcmp(magic, "SGI2", 4) == 0) {  // v2 shard file: rows as stored in HBM
+    Sgi2Header h2;
+    std::rewind(f);
+    if (std::fread(&h2, sizeof(h2), 1, f) != 1) {
+      std::fclose(f);
+      set_error(std::string("read error in ") + path + ": truncated header");
+      return 3;
+    }
+    const int rc2 = read_v2_body(f, path, h2, device, flags, out);
+    std::fclose(f);
+    return rc2;
+  }
+  std::rewind(f);
   IxfiHeader hd;
   if (std::fread(&hd, sizeof(hd), 1, f) != 1) {
     std::fclose(f);

@@ -257,6 +257,21 @@ class IndexFlatIP(Index):
             check(self._lib.sgic_index_set_option(self._h, b"drop_retained", 1))
 
 
+def write_shard(index: IndexFlatIP, path: str, *, row_start: int = 0, total_rows: int = -1, shard: int = 0,
+                n_shards: int = 1) -> None:
+    """Additive: write the rows as they sit in HBM (fp16 / bf16) in the "SGI2" layout —
+    half the bytes of ``write_index`` and no conversion on load.  ``read_index`` loads either format."""
+    check(index._lib.sgic_index_write_v2(index._h, os.fsencode(str(path)), int(row_start), int(total_rows),
+                                         int(shard), int(n_shards)))
+
+
+def shard_info(index: IndexFlatIP) -> dict:
+    """Placement recorded in the SGI2 file an index was loaded from."""
+    out = (C.c_int64 * 4)()
+    check(index._lib.sgic_index_shard_info(index._h, out))
+    return {"row_start": int(out[0]), "total_rows": int(out[1]), "shard": int(out[2]), "n_shards": int(out[3])}
+
+
 def write_index(index: IndexFlatIP, path: str) -> None:
     """``faiss.write_index(index, path)`` — src/build.py:95,99; src/compress.py:111."""
     check(index._lib.sgic_index_write(index._h, os.fsencode(str(path))))

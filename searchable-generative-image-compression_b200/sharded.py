@@ -168,3 +168,38 @@ class ShardedIndexFlatIP(Index):
         q = torch.from_numpy(x).to(self._dev, non_blocking=False)
         D, I = self.search_torch(q, k)
         return D.cpu().numpy(), I.cpu().numpy()
+
+    # ---------------------------------------------------------------- persistence (SGI2 shard files)
+    @staticmethod
+    def shard_path(directory, rank: int, world: int) -> str:
+        import os
+        return os.path.join(str(directory), f"shard-{rank:05d}-of-{world:05d}.sgi2")
+
+    def save(self, directory) -> None:
+        """Collective.  Every rank writes the rows it holds, as they sit in HBM, to its own SGI2 file
+        (``faiss_compat.write_shard``); the header records where the rows sit in the logical index."""
+        import os
+        from .faiss_compat import write_shard
+        if len(self._segments) > 1:
+            raise RuntimeError("save() needs one contiguous row range per rank (build with add_local / one add)")
+        os.makedirs(str(directory), exist_ok=True)
+        start = self._segments[0][0] if self._segments else 0
+        write_shard(self.local, self.shard_path(directory, self.rank, self.world), row_start=start,
+                    total_rows=self._ntotal, shard=self.rank, n_shards=self.world)
+        if self.world > 1:
+            self._dist.barrier(group=self._group)
+
+    @classmethod
+    def load(cls, directory, *, group=None, device: Optional[int] = None) -> "ShardedIndexFlatIP":
+        """Collective.  Rank g loads ``shard-g-of-G.sgi2`` straight into its HBM (no conversion)."""
+        import torch.distributed as dist
+        from .faiss_compat import read_index, shard_info
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        local = read_index(cls.shard_path(directory, rank, world), device=device, retain_fp32=False)
+        info = shard_info(local)
+        if info["n_shards"] != world or info["shard"] != rank:
+            raise RuntimeError(f"{directory}: shard file written for {info['n_shards']} ranks, loaded with {world}")
+        self = cls(local.d, dtype=local.dtype, group=group, device=device, local_factory=lambda d: local)
+        self._segments = [(info["row_start"], 0, local.ntotal)] if local.ntotal else []
+        self._ntotal = info["total_rows"]
+        return self

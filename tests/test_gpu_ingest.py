@@ -279,3 +279,42 @@ def test_device_zstd_corrupt_frame_falls_back_to_libzstd():
     # that every stream is consumed exactly (RFC 8878 4.2.2), refuses, and hands the slab to libzstd — so the
     # reference's behaviour is reproduced either way
     assert res[1][3] >= 1
+
+
+def test_sgi2_shard_file_round_trip(tmp_path):
+    """N3: the v2 on-disk layout holds the rows exactly as they sit in HBM — write, read back through the
+    faiss-named `read_index` (format recognised by its magic), same bits, same answers; IxFI keeps working."""
+    import os
+    from sgic_b200 import faiss_compat as faiss
+    rng = np.random.default_rng(77)
+    for dtype in ("fp16", "bf16"):
+        n, d = 70_001, 512                     # > one 32 MB staging chunk, ragged
+        xb = rng.standard_normal((n, d)).astype(np.float32)
+        xb /= np.linalg.norm(xb, axis=1, keepdims=True)
+        idx = faiss.IndexFlatIP(d, dtype=dtype, device=0)
+        idx.add(xb)
+        p2 = tmp_path / f"rows-{dtype}.sgi2"
+        faiss.write_shard(idx, p2, row_start=1000, total_rows=500_000, shard=3, n_shards=8)
+        assert os.path.getsize(p2) == 4096 + n * d * 2
+        raw = np.fromfile(p2, dtype=np.uint8)
+        assert bytes(raw[:4]) == b"SGI2"
+        back = faiss.read_index(str(p2), device=0)
+        assert back.ntotal == n and back.d == d and back.dtype == dtype
+        assert faiss.shard_info(back) == {"row_start": 1000, "total_rows": 500_000, "shard": 3, "n_shards": 8}
+        assert np.array_equal(back.reconstruct_n(0, n), idx.reconstruct_n(0, n))       # bit-identical rows
+        q = xb[:7] + 0.01
+        D0, I0 = idx.search(q, 10)
+        D1, I1 = back.search(q, 10)
+        assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
+        # payload bytes are the HBM rows: fp16 file == numpy's fp16 rounding of the input
+        if dtype == "fp16":
+            assert np.array_equal(raw[4096:].view(np.float16).reshape(n, d), xb.astype(np.float16))
+        # a truncated file is rejected like a short IxFI file
+        (tmp_path / "short.sgi2").write_bytes(raw[:4096 + 1000].tobytes())
+        with pytest.raises(RuntimeError):
+            faiss.read_index(str(tmp_path / "short.sgi2"), device=0)
+        # the interchange format still round-trips
+        p1 = tmp_path / f"rows-{dtype}.faiss"
+        faiss.write_index(idx, str(p1))
+        again = faiss.read_index(str(p1), dtype=dtype, device=0)
+        assert again.ntotal == n
