@@ -13,6 +13,7 @@ k = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 nqs = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [1, 4, 8, 16, 64, 128, 256, 1024, 4096]
 modes = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0]
 dbgs = [int(x) for x in sys.argv[6].split(",")] if len(sys.argv) > 6 else [0, 4]
+l2s = [int(x) for x in sys.argv[7].split(",")] if len(sys.argv) > 7 else [0]
 names = {0: "auto", 1: "1cta", 2: "pairs+stream", 3: "pairs"}
 idx = faiss.IndexFlatIP(d, device=0, retain_fp32=False)
 fill_index_random(idx, n)
@@ -22,7 +23,10 @@ for nq in nqs:
     D = torch.empty((nq, k), device="cuda")
     I = torch.empty((nq, k), dtype=torch.int64, device="cuda")
     for mode in modes:
+      for l2 in l2s:
         for dbg in dbgs:
+            if l2:
+                idx.set_option("dense_l2_mb", l2)
             idx.set_option("dense_mode", mode)
             idx.set_option("debug", dbg)
             for _ in range(2):
@@ -48,5 +52,5 @@ for nq in nqs:
                 tot.append(idx.stat("last_search_ns") / 1e6)
             idx.set_option("timing", 0)
             tf = 2 * nq * n * d / ms / 1e9
-            print(f"nq={nq:5d} mode={names[mode]:12s} skipEpi={dbg >> 2} ms={ms:8.3f} (best {best:8.3f}) TF={tf:7.0f} "
+            print(f"nq={nq:5d} mode={names[mode]:12s} l2={l2:3d} skipEpi={dbg >> 2} ms={ms:8.3f} (best {best:8.3f}) TF={tf:7.0f} "
                   f"({tf / 1404.9:.3f} of sustained)  GB/s={n * d * 2 / ms / 1e6:6.0f}  qps={nq / ms * 1e3:9.0f}  [timed alone: scan {min(sc):.3f} total {min(tot):.3f}]", flush=True)

@@ -15,9 +15,13 @@
 //               always fresh.  k > 32: reservoir selection — survivors are appended to the query's reservoir
 //               in an L2-resident workspace and the warp compacts a full reservoir to its k best by bisection
 //               over the key bits.  No score matrix ever leaves the SM.
-// Work split: items = (query tile m, database slice s), m fastest, so CTAs that run concurrently share a
-// slice and each database tile is fetched from HBM once and re-used from L2 by the other query tiles.
-// Every item writes k keys per query; merge_keys_small_kernel merges the slices.
+// Work split: items = (query tile m, database slice s), m fastest, dealt round-robin to the CTAs (pairs), so the
+// CTAs that run concurrently share a few slices and re-use each other's database tiles from L2 while they stay
+// close (10M rows: 12.7 GB read from DRAM for a 10.2 GB database; 100M rows: the query tiles drift apart over
+// 10.5k tiles and DRAM reads grow to 988 GB — 34 % of DRAM peak, not the bound; a lockstep or TMA multicast
+// across pairs is what would fix it, shorter slices alone do not, see the host's slice comment).  A CTA parks
+// a query tile's top-k list in its own slot of `partial` at the end of an item and resumes it — threshold
+// included — if it visits that tile again; merge_keys_*_kernel merges the CTAs' lists at the end.
 //
 // Two kernels:
 //   scan_dense_kernel   cta_group::1 — 128 queries x 256 rows per CTA; A and B both streamed per K chunk.
@@ -38,11 +42,12 @@ constexpr int kDenseBM = 128;       // queries per CTA (TMEM lanes)
 constexpr int kDenseBK = 64;        // K chunk: 64 x 16-bit = one 128-byte swizzle row
 
 struct DenseParams {
-  uint64_t* partial;   // [nq][n_slices][k] keys
+  uint64_t* partial;   // [nq][n_lists][k] keys: list `u` of a query belongs to CTA (pair) u, zeroed before the launch
   uint64_t* lists_ws;  // k > 32: [grid][128][res_cap] reservoirs (L2-resident workspace)
   uint32_t n_rows, nq, k, res_cap;
   uint32_t m_tiles;        // query tiles: of 128 (1-CTA kernel) or 256 (2-CTA kernel)
   uint32_t n_slices, tiles_per_slice, n_tiles;
+  uint32_t n_lists;        // = number of CTAs (CTA pairs) launched
   uint32_t kc;             // K chunks of 64 elements (ceil(d/64); TMA zero-fills the tail)
   uint32_t tp;             // k <= 32: thread-private lists [k][128] in shared memory; else reservoirs
   uint32_t a_rows;         // rows of the query box (1-CTA kernel; < 128 for small batches)
@@ -157,10 +162,26 @@ struct DenseEpiTP {
     }
   }
 
-  __device__ __forceinline__ void store(uint64_t* partial, uint32_t q, uint32_t nq, uint32_t n_slices, uint32_t slice) {
+  // Items are short (a few dozen tiles, so that the query tiles sharing a database slice stay together in L2)
+  // and a CTA meets the same query tile again many items later: the list is parked in the CTA's own slot of
+  // `partial` between visits and picked up — with its threshold — at the next one.
+  __device__ __forceinline__ void load(const uint64_t* partial, uint32_t q, uint32_t nq, uint32_t n_lists, uint32_t slot) {
+    if (q >= nq) {
+      reset();
+      return;
+    }
+    const uint64_t* src = partial + (static_cast<size_t>(q) * n_lists + slot) * k;
+    uint64_t kth = 0ull;
+    for (uint32_t i = 0; i < k; ++i) {
+      kth = __ldcg(src + i);
+      lst[i * kDenseBM] = kth;
+    }
+    thr = (kth == 0ull) ? -INFINITY : key_score(kth);
+  }
+  __device__ __forceinline__ void store(uint64_t* partial, uint32_t q, uint32_t nq, uint32_t n_lists, uint32_t slot) {
     if (q >= nq) return;
-    uint64_t* dst = partial + (static_cast<size_t>(q) * n_slices + slice) * k;
-    for (uint32_t i = 0; i < k; ++i) dst[i] = lst[i * kDenseBM];
+    uint64_t* dst = partial + (static_cast<size_t>(q) * n_lists + slot) * k;
+    for (uint32_t i = 0; i < k; ++i) __stcg(dst + i, lst[i * kDenseBM]);
   }
 };
 
@@ -332,6 +353,40 @@ struct DenseEpiRes {
     }
   }
 
+  // item start: pick up the (unsorted, front-compacted) top-k parked in this CTA's slot of `partial` by its
+  // previous visit of the query tile; the threshold is the smallest of k keys, or -inf while fewer are known
+  __device__ __forceinline__ void load(const uint64_t* partial, uint32_t q0w, uint32_t nq, uint32_t n_lists,
+                                       uint32_t slot) {
+    reset();
+    for (int L = 0; L < 32; ++L) {
+      const uint32_t q = q0w + L;
+      if (q >= nq) break;
+      const uint64_t* src = partial + (static_cast<size_t>(q) * n_lists + slot) * k;
+      uint64_t* R = res_warp + static_cast<size_t>(L) * C;
+      uint32_t n = 0;
+      uint64_t mn = ~0ull;
+      for (uint32_t i = lane; i < k; i += 32) {
+        const uint64_t x = __ldcg(src + i);
+        __stcg(R + i, x);
+        if (x != 0ull) {
+          ++n;
+          mn = x < mn ? x : mn;
+        }
+      }
+      n = __reduce_add_sync(0xffffffffu, n);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, mn, off);
+        mn = o < mn ? o : mn;
+      }
+      if (lane == L) {
+        cnt = n;
+        thr = (n == k) ? key_score(mn) : -INFINITY;
+      }
+    }
+    __syncwarp();
+  }
+
   // item finished: reservoirs down to k keys, then the warp copies each query's keys out (coalesced)
   __device__ __forceinline__ void store(uint64_t* partial, uint32_t q0w, uint32_t nq, uint32_t n_slices,
                                         uint32_t slice) {
@@ -344,7 +399,7 @@ struct DenseEpiRes {
       const uint32_t n = __shfl_sync(0xffffffffu, cnt, L);
       const uint64_t* R = res_warp + static_cast<size_t>(L) * C;
       uint64_t* dst = partial + (static_cast<size_t>(q) * n_slices + slice) * k;
-      for (uint32_t i = lane; i < k; i += 32) dst[i] = i < n ? __ldcg(R + i) : 0ull;
+      for (uint32_t i = lane; i < k; i += 32) __stcg(dst + i, i < n ? __ldcg(R + i) : 0ull);
     }
     __syncwarp();
   }
@@ -371,7 +426,7 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
       const uint32_t q0 = m_tile * q_tile + q_off;
       const bool q_valid = q0 + t < p.nq;
       const bool warp_valid = q0 + row0w < p.nq;
-      epi.reset();
+      epi.load(p.partial, q0 + t, p.nq, p.n_lists, unit);
       for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
         const uint32_t as = tc & 1;
         ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
@@ -383,7 +438,7 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
         __syncwarp();
         if (lane == 0) arrive(as);
       }
-      epi.store(p.partial, q0 + t, p.nq, p.n_slices, slice);
+      epi.store(p.partial, q0 + t, p.nq, p.n_lists, unit);
     }
   } else {
     DenseEpiRes epi;
@@ -397,7 +452,8 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
       const uint32_t q0 = m_tile * q_tile + q_off;
       const bool q_valid = q0 + t < p.nq;
       const bool warp_valid = q0 + row0w < p.nq;
-      epi.reset();
+      if (warp_valid) epi.load(p.partial, q0 + row0w, p.nq, p.n_lists, unit);
+      else epi.reset();
       for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
         const uint32_t as = tc & 1;
         ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
@@ -409,7 +465,7 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
         __syncwarp();
         if (lane == 0) arrive(as);
       }
-      if (warp_valid) epi.store(p.partial, q0 + row0w, p.nq, p.n_slices, slice);
+      if (warp_valid) epi.store(p.partial, q0 + row0w, p.nq, p.n_lists, unit);
     }
   }
 }

@@ -118,7 +118,7 @@ struct sgic_index {
   int64_t shard_row_start = 0, shard_total_rows = -1;
   int shard_id = 0, shard_count = 1;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 5, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 5, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0;
   int64_t stat_ingest_h2d_ns = 0, stat_ingest_k0_ns = 0, stat_ingest_k1_ns = 0;
   int64_t stat_ingest_parse_ns = 0, stat_ingest_pack_ns = 0, stat_ingest_gpu_ns = 0;
   int64_t stat_zl_device_frames = 0, stat_zl_host_rows = 0, stat_zl_fallback_slabs = 0;
@@ -434,16 +434,30 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
   for (int64_t q0 = 0; q0 < nq; q0 += kDenseQueryBlock) {
     const uint32_t nqb = static_cast<uint32_t>(std::min<int64_t>(kDenseQueryBlock, nq - q0));
     const uint32_t m_tiles = (nqb + q_tile - 1) / q_tile;
-    // slices: items = m_tiles * n_slices is a multiple of the number of CTAs (CTA pairs) whenever the
-    // database is big enough, so every CTA gets the same number of (equal-sized) items
-    uint32_t n_slices = n_units / gcd_u32(m_tiles, n_units);
-    n_slices = std::max<uint32_t>(1, std::min(n_slices, n_tiles));
+    // Slices.  Default: the fewest slices that make the items a multiple of the CTAs (pairs) — every CTA gets
+    // the same number of equal items and visits each of its query tiles once.  "dense_l2_mb" > 0 switches to
+    // SHORT slices sized so that the ~units/m_tiles slices in flight fit that L2 budget (a CTA then resumes a
+    // query tile's list many times, see scan_dense.cuh).  Measured on 30M x 512, nq = 4096 (profiles/): short
+    // slices read MORE from DRAM (144.8 GB vs 84.2 GB; L2 hit 64.6 % vs 77.6 %) because the CTAs drift over
+    // thousands of items without a lockstep, and are 5 % slower — so it is off by default.
+    const uint32_t step = n_units / gcd_u32(m_tiles, n_units);
+    uint32_t n_slices = std::max<uint32_t>(1, std::min(step, n_tiles));
+    const size_t tile_bytes = static_cast<size_t>(kDenseBN) * h->d * 2;
+    const size_t l2_budget = static_cast<size_t>(h->opt_dense_l2_mb) << 20;
+    if (l2_budget > 0 && m_tiles > 1 && static_cast<size_t>(n_tiles) * tile_bytes > l2_budget) {
+      const uint32_t in_flight = (n_units + m_tiles - 1) / m_tiles + 1;
+      const uint32_t tps0 = std::max<uint32_t>(8, static_cast<uint32_t>(l2_budget / (in_flight * tile_bytes)));
+      n_slices = (n_tiles + tps0 - 1) / tps0;
+      n_slices = ((n_slices + step - 1) / step) * step;  // items stay a multiple of the CTAs
+      n_slices = std::max<uint32_t>(1, std::min(n_slices, n_tiles));
+    }
     const uint32_t tiles_per_slice = (n_tiles + n_slices - 1) / n_slices;
     n_slices = (n_tiles + tiles_per_slice - 1) / tiles_per_slice;
     const uint32_t n_items = m_tiles * n_slices;
-    const uint32_t grid = std::min<uint32_t>(n_units, n_items) * (pairs ? 2u : 1u);
+    const uint32_t grid_units = std::min<uint32_t>(n_units, n_items);
+    const uint32_t grid = grid_units * (pairs ? 2u : 1u);
 
-    const size_t partial_bytes = static_cast<size_t>(nqb) * n_slices * static_cast<size_t>(k) * 8;
+    const size_t partial_bytes = static_cast<size_t>(nqb) * grid_units * static_cast<size_t>(k) * 8;
     if (partial_bytes + 16 > h->ws_bytes) {
       SGIC_CUDA(cudaStreamSynchronize(st));
       rc = ensure_buf(&h->ws, &h->ws_bytes, partial_bytes + 16, false);
@@ -475,12 +489,14 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.n_slices = n_slices;
     p.tiles_per_slice = tiles_per_slice;
     p.n_tiles = n_tiles;
+    p.n_lists = grid_units;
     p.kc = (static_cast<uint32_t>(h->d) + kDenseBK - 1) / kDenseBK;
     p.tp = tp ? 1u : 0u;
     p.a_rows = pairs ? static_cast<uint32_t>(kDenseBM) : std::min<uint32_t>(kDenseBM, (nqb + 7u) & ~7u);
     p.idesc = ptx::umma_idesc_f16(q_tile, kDenseBN, h->dtype == SGIC_BF16 ? 1u : 0u);
     p.db_evict_first = (m_tiles == 1 && h->opt_evict_first) ? 1u : 0u;
     p.debug = static_cast<uint32_t>(h->opt_debug);
+    SGIC_CUDA(cudaMemsetAsync(h->ws, 0, partial_bytes, st));  // empty lists: every CTA resumes its own
     if (!pairs) kern<<<grid, kDenseThreads, kSmemBudget, st>>>(tm_q, tm_db, p);
     else if (a_resident) kern2r<<<grid, kDenseThreads, kSmemBudget, st>>>(tm_q, tm_db, p);
     else kern2s<<<grid, kDenseThreads, kSmemBudget, st>>>(tm_q, tm_db, p);
@@ -489,7 +505,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     h->stat_last_grid = grid;
     h->stat_last_stages = kDenseStages;
     if (h->opt_timing && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));
-    rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nqb, n_slices, static_cast<uint32_t>(k),
+    rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nqb, grid_units, static_cast<uint32_t>(k),
                            dev_D + static_cast<size_t>(q0) * k, dev_I + static_cast<size_t>(q0) * k, id_base, st,
                            /*sorted_lists=*/tp);
     if (rc) return rc;
@@ -1419,6 +1435,7 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "debug") h->opt_debug = value;
   else if (n == "dense_mode") h->opt_dense_mode = value;
   else if (n == "device_zstd") h->opt_device_zstd = value;
+  else if (n == "dense_l2_mb") h->opt_dense_l2_mb = std::max<int64_t>(0, value);
   else if (n == "drop_retained") {
     std::lock_guard<std::mutex> lk(h->mu);
     h->retain_ok = false;
