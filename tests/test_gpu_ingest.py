@@ -318,3 +318,43 @@ def test_sgi2_shard_file_round_trip(tmp_path):
         faiss.write_index(idx, str(p1))
         again = faiss.read_index(str(p1), dtype=dtype, device=0)
         assert again.ntotal == n
+
+
+def test_resident_service_over_the_real_index(tmp_path):
+    """N2 end to end on the GPU: build from .c2df files, keep the index resident, answer concurrent .c2df
+    queries through one batched search, emit the reference's stdout document."""
+    import threading
+    from sgic_b200 import index_build, retrieval
+    from sgic_b200.service import SearchService
+    rng = np.random.default_rng(3)
+    vecs = rng.standard_normal((300, 512)).astype(np.float32)
+    vecs /= np.linalg.norm(vecs, axis=1, keepdims=True)
+    src = tmp_path / "bitstreams"
+    src.mkdir()
+    _write_corpus(src, vecs, rng)
+    out = tmp_path / "faiss"
+    index_build.build_index_from_c2df_dir(src, out)
+    svc = SearchService(out, max_batch=64, max_wait_ms=30.0)
+    try:
+        paths = svc.paths
+        n = 40
+        res = [None] * n
+        bar = threading.Barrier(n)
+
+        def work(i):
+            bar.wait()
+            res[i] = svc.search_c2df(paths[i], topk=5)
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        index, _, _ = retrieval.load_index(out)
+        for i in range(n):
+            want = retrieval.do_search(retrieval.encode_c2df_query(paths[i]), index, paths, topk=5)
+            assert [p for p, _ in res[i]] == [p for p, _ in want] and res[i][0][0] == paths[i]
+            assert np.allclose([s for _, s in res[i]], [s for _, s in want], atol=2e-5)   # K4 batch vs K3 single
+        assert svc.stats["batches"] < n / 2 and svc.stats["max_batch_seen"] >= 5, svc.stats
+        doc = json.loads(svc.cli_json(res[0]))
+        assert doc[0]["path"] == paths[0] and set(doc[0]) == {"path", "score"}
+    finally:
+        svc.close()

@@ -1,0 +1,107 @@
+"""Host logic of the resident search service on CPU: micro-batching, the reference's stdout
+document (src/search.py:163-166) and NDJSON event stream (webapp.py:243-261).  The index is a stand-in backed
+by the oracle; the GPU tier runs the same service over the real index."""
+import json
+import socket
+import threading
+
+import numpy as np
+import pytest
+
+from oracle.flat_ip import flat_ip_search
+from sgic_b200.service import SearchService, serve
+
+
+class OracleIndex:
+    """IndexFlatIP stand-in (test infrastructure): counts calls and batch sizes."""
+
+    def __init__(self, xb):
+        self.xb, self.d, self.ntotal = xb, xb.shape[1], xb.shape[0]
+        self.calls = []
+
+    def search(self, q, k):
+        self.calls.append((q.shape[0], k))
+        return flat_ip_search(self.xb, q, k)
+
+
+@pytest.fixture()
+def svc():
+    rng = np.random.default_rng(0)
+    xb = rng.standard_normal((500, 64)).astype(np.float32)
+    xb /= np.linalg.norm(xb, axis=1, keepdims=True)
+    idx = OracleIndex(xb)
+    s = SearchService(index=idx, paths=[f"IO/bitstreams/img{i:04d}.c2df" for i in range(500)],
+                      meta={"dim": 64, "model_id": None}, max_batch=64, max_wait_ms=20.0)
+    yield s, idx, xb
+    s.close()
+
+
+def test_single_query_equals_do_search(svc):
+    s, idx, xb = svc
+    res = s.search_vec(xb[7], topk=5)
+    D, I = flat_ip_search(xb, xb[7:8], 5)
+    assert [p for p, _ in res] == [f"IO/bitstreams/img{i:04d}.c2df" for i in I[0]]
+    assert np.allclose([sc for _, sc in res], D[0])
+    assert res[0][0].endswith("img0007.c2df") and abs(res[0][1] - 1.0) < 1e-5
+    # topk larger than the index is clamped like src/search.py:114
+    assert len(s.search_vec(xb[0], topk=10_000)) == 500
+    with pytest.raises(ValueError):
+        s.search_vec(np.zeros(63, np.float32))
+
+
+def test_concurrent_requests_are_batched_into_one_search(svc):
+    s, idx, xb = svc
+    n = 48
+    out = [None] * n
+    barrier = threading.Barrier(n)
+
+    def worker(i):
+        barrier.wait()
+        out[i] = s.search_vec(xb[i], topk=3 + (i % 4))
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(n)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(n):
+        assert out[i][0][0].endswith(f"img{i:04d}.c2df") and len(out[i]) == 3 + (i % 4)
+    assert s.stats["requests"] == n
+    assert s.stats["batches"] < n / 4 and s.stats["max_batch_seen"] >= 8, s.stats   # far fewer searches than requests
+    assert all(k == 6 or nq == 1 or k <= 6 for nq, k in idx.calls)
+
+
+def test_cli_json_is_the_reference_stdout_document(svc):
+    s, idx, xb = svc
+    res = s.search_vec(xb[3], topk=2)
+    doc = s.cli_json(res)
+    assert doc == json.dumps([{"path": p, "score": sc} for p, sc in res], ensure_ascii=False, indent=2)
+    assert [set(e) for e in json.loads(doc)] == [{"path", "score"}] * 2
+
+
+def test_ndjson_event_stream_and_socket_front_end(svc):
+    s, idx, xb = svc
+    ev = list(s.ndjson_events({"type": "text", "text": "a red apple", "vec": xb[11].tolist(), "topk": 4}))
+    assert ev[0] == {"type": "meta", "stage": "start", "query_type": "text", "topk": 4, "query": "a red apple"}
+    assert ev[1]["type"] == "meta" and ev[1]["stage"] == "searched" and ev[1]["count"] == 4 and "elapsed_ms" in ev[1]
+    assert [e["type"] for e in ev[2:6]] == ["item"] * 4 and set(ev[2]) == {"type", "path", "score", "preview_url"}
+    assert ev[2]["path"].endswith("img0011.c2df") and ev[-1]["type"] == "done"
+    # a text query without an embedding cannot be served by this path: reported like webapp.py:258-259
+    bad = list(s.ndjson_events({"type": "text", "text": "x"}))
+    assert bad[-1]["type"] == "error"
+    srv = serve(s, port=0)
+    try:
+        with socket.create_connection(srv.server_address, timeout=10) as c:
+            f = c.makefile("rwb")
+            f.write((json.dumps({"type": "image", "filename": "q.png", "vec": xb[21].tolist(), "topk": 2}) + "\n").encode())
+            f.write(b"not json\n")
+            f.flush()
+            lines = []
+            while True:
+                lines.append(json.loads(f.readline()))
+                if lines[-1]["type"] == "error":
+                    break
+        kinds = [l["type"] for l in lines]
+        assert kinds == ["meta", "meta", "item", "item", "done", "error"]
+        assert lines[0]["filename"] == "q.png" and lines[2]["path"].endswith("img0021.c2df")
+    finally:
+        srv.shutdown()
+        srv.server_close()
