@@ -322,7 +322,7 @@ def run_ours(args):
             achieved = alg_bytes / (scan_ms / 1e3) / 1e9
             roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                        "kernel": "scan_dense_kernel" if dense else "scan_small_kernel",
+                        "kernel": "scan_dense_t_kernel" if dense else "scan_small_kernel",
                         "algorithmic_bytes_per_launch": alg_bytes,
                         "kernel_ms": scan_ms, "frac_of_nominal_8TBs": achieved / 8000.0}
             traffic_file = ROOT / "profiles" / "traffic.json"

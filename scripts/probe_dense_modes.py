@@ -14,10 +14,18 @@ nqs = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [1, 4, 
 modes = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0]
 dbgs = [int(x) for x in sys.argv[6].split(",")] if len(sys.argv) > 6 else [0, 4]
 l2s = [int(x) for x in sys.argv[7].split(",")] if len(sys.argv) > 7 else [0]
+if len(sys.argv) > 8:
+    min_nq = int(sys.argv[8])
+else:
+    min_nq = None
 names = {0: "auto", 1: "1cta", 2: "pairs+stream", 3: "pairs"}
 idx = faiss.IndexFlatIP(d, device=0, retain_fp32=False)
 fill_index_random(idx, n)
-print(f"n={n} d={d} k={k}", flush=True)
+if min_nq is not None:
+    idx.set_option("dense_min_nq", min_nq)
+if len(sys.argv) > 9:
+    idx.set_option("stages", int(sys.argv[9]))
+print(f"n={n} d={d} k={k} dense_min_nq={min_nq}", flush=True)
 for nq in nqs:
     q = torch.from_numpy(random_unit_queries(nq, d)).cuda()
     D = torch.empty((nq, k), device="cuda")

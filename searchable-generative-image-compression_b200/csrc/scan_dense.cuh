@@ -51,6 +51,8 @@ struct DenseParams {
   uint32_t kc;             // K chunks of 64 elements (ceil(d/64); TMA zero-fills the tail)
   uint32_t tp;             // k <= 32: thread-private lists [k][128] in shared memory; else reservoirs
   uint32_t a_rows;         // rows of the query box (1-CTA kernel; < 128 for small batches)
+  uint32_t a_region;       // 1-CTA kernel: bytes reserved per stage for the query box (1 KB granularity)
+  uint32_t n_stages;       // 1-CTA kernel: ring depth
   uint32_t idesc;          // UMMA instruction descriptor
   uint32_t db_evict_first; // single query tile: the database is streamed once -> evict_first
   uint32_t debug;          // timing experiments only (wrong results): 1 skip A loads, 2 skip B loads, 4 skip epilogue
@@ -471,7 +473,11 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
 }
 
 // ================================================================================================ 1-CTA kernel
-template <int BN, int NS>
+constexpr int kDenseMaxStages = 8;
+
+// Ring of p.n_stages stages; a stage = the query box of this K chunk (p.a_region bytes, 1 KB granularity — the box
+// is cut to the batch, so small batches get a deeper ring of database tiles) + a 256-row database box.
+template <int BN>
 __global__ void __launch_bounds__(kDenseThreads, 1)
 scan_dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
                   const DenseParams p) {
@@ -480,20 +486,21 @@ scan_dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = dense_smem_raw + ((1024u - (ptx::smem_u32(dense_smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = smem;
-  uint8_t* epi_smem = smem + static_cast<size_t>(NS) * Cfg::kStageBytes;
+  const uint32_t ns = p.n_stages, stage_bytes = p.a_region + Cfg::kBBytes;
+  uint8_t* epi_smem = smem + static_cast<size_t>(ns) * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + dense_epi_bytes(p.k, p.tp));
   uint64_t* full = bars;
-  uint64_t* empty = bars + NS;
-  uint64_t* acc_full = bars + 2 * NS;
-  uint64_t* acc_empty = bars + 2 * NS + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
+  uint64_t* empty = bars + kDenseMaxStages;
+  uint64_t* acc_full = bars + 2 * kDenseMaxStages;
+  uint64_t* acc_empty = bars + 2 * kDenseMaxStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kDenseMaxStages + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_q);
     ptx::prefetch_tmap(&tm_db);
-    for (int s = 0; s < NS; ++s) {
+    for (uint32_t s = 0; s < ns; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
     }
@@ -516,23 +523,26 @@ scan_dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     if (lane == 0) {
       const uint64_t pol_q = ptx::policy_evict_last();
       const uint64_t pol_db = p.db_evict_first ? ptx::policy_evict_first() : ptx::policy_evict_last();
-      uint32_t it = 0;
+      uint32_t s = 0, round = 0;  // ring position; `round` counts completed trips around the ring
       for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t m_tile = item % p.m_tiles, slice = item / p.m_tiles;
         const uint32_t t0 = slice * p.tiles_per_slice, t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
         for (uint32_t tile = t0; tile < t1; ++tile) {
-          for (uint32_t kc = 0; kc < p.kc; ++kc, ++it) {
-            const uint32_t s = it % NS, u = it / NS;
-            if (u > 0) ptx::mbar_wait(&empty[s], (u - 1) & 1);
-            uint8_t* a_dst = stages + static_cast<size_t>(s) * Cfg::kStageBytes;
-            const bool ld_a = !(p.debug & 1u) || it < NS, ld_b = !(p.debug & 2u) || it < NS;
+          for (uint32_t kc = 0; kc < p.kc; ++kc) {
+            if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
+            uint8_t* a_dst = stages + static_cast<size_t>(s) * stage_bytes;
+            const bool ld_a = !(p.debug & 1u) || round == 0, ld_b = !(p.debug & 2u) || round == 0;
             ptx::mbar_expect_tx(&full[s], (ld_a ? p.a_rows * (kDenseBK * 2u) : 0u) + (ld_b ? Cfg::kBBytes : 0u));
             if (ld_a)
               ptx::tma_load_2d(a_dst, &tm_q, static_cast<int32_t>(kc * kDenseBK),
                                static_cast<int32_t>(m_tile * kDenseBM), &full[s], pol_q);
             if (ld_b)
-              ptx::tma_load_2d(a_dst + Cfg::kABytes, &tm_db, static_cast<int32_t>(kc * kDenseBK),
+              ptx::tma_load_2d(a_dst + p.a_region, &tm_db, static_cast<int32_t>(kc * kDenseBK),
                                static_cast<int32_t>(tile * BN), &full[s], pol_db);
+            if (++s == ns) {
+              s = 0;
+              ++round;
+            }
           }
         }
       }
@@ -540,7 +550,7 @@ scan_dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     if (lane == 0) {
-      uint32_t it = 0, tc = 0;
+      uint32_t s = 0, round = 0, tc = 0;
       for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t slice = item / p.m_tiles;
         const uint32_t t0 = slice * p.tiles_per_slice, t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
@@ -549,17 +559,20 @@ scan_dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
           if (ua > 0) ptx::mbar_wait(&acc_empty[as], (ua - 1) & 1);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * BN;
-          for (uint32_t kc = 0; kc < p.kc; ++kc, ++it) {
-            const uint32_t s = it % NS;
-            ptx::mbar_wait(&full[s], (it / NS) & 1);
+          for (uint32_t kc = 0; kc < p.kc; ++kc) {
+            ptx::mbar_wait(&full[s], round & 1);
             ptx::tc_fence_after();
-            const uint32_t a_addr = ptx::smem_u32(stages + static_cast<size_t>(s) * Cfg::kStageBytes);
+            const uint32_t a_addr = ptx::smem_u32(stages + static_cast<size_t>(s) * stage_bytes);
             const uint64_t a_desc = ptx::umma_desc_k_sw128(a_addr);
-            const uint64_t b_desc = ptx::umma_desc_k_sw128(a_addr + Cfg::kABytes);
+            const uint64_t b_desc = ptx::umma_desc_k_sw128(a_addr + p.a_region);
 #pragma unroll
             for (uint32_t kk = 0; kk < kDenseBK / 16; ++kk)
               ptx::tc_mma_f16(d_tmem, a_desc + kk * 2, b_desc + kk * 2, p.idesc, (kc | kk) != 0 ? 1u : 0u);
             ptx::tc_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
+            if (++s == ns) {
+              s = 0;
+              ++round;
+            }
           }
           ptx::tc_commit(&acc_full[as]);  // accumulator of this tile complete
         }
@@ -574,6 +587,223 @@ scan_dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ================================================================================================ transposed kernel
+// Small batches (HBM regime).  With the queries on M the tensor cores always multiply a 128-row query tile, so a
+// batch of 8 burns 16x the useful tensor energy; measured on a 1000 W B200 that drives the SM clock to 637 MHz
+// under the power cap and the scan to 5.5 TB/s, while K3 streams the same rows at 7.3 TB/s.  Here the DATABASE
+// rows sit on M (one TMEM lane = one database row, M = 128) and the queries on N = ceil16(nq), so the tensor work
+// is proportional to the batch.  The query matrix is loaded once and stays in shared memory; every stage is one
+// 256-row x 64-element database box (two M = 128 MMAs per K step, two accumulators of N columns).
+//
+// Epilogue: warp w owns lanes 32w.. (32 database rows per sub-tile), thread = row, column = query.  Per chunk of
+// 16 queries: one tcgen05.ld.x16, the 16 per-query thresholds from shared memory (4 broadcast LDS.128), 16
+// compares OR-ed into one predicate and ONE vote rejects 32 rows x 16 queries.  Survivors (rare) are found with
+// one ballot per query and inserted warp-cooperatively into the (warp, query) list; the four warps' lists of a
+// query are merged when the CTA's slice is done.
+struct DenseTParams {
+  uint64_t* partial;  // [nq][n_lists][k] keys
+  uint32_t n_rows, nq, k;
+  uint32_t n_pad;     // ceil16(nq): MMA N, query box rows
+  uint32_t n_slices, tiles_per_slice, n_tiles, n_lists;
+  uint32_t kc, n_stages, idesc, db_evict_first, debug;
+};
+
+constexpr uint32_t kDtStageBytes = 256u * kDenseBK * 2u;  // 32 KB: 256 database rows x 128 B
+
+__host__ __device__ __forceinline__ uint32_t dense_t_fixed_bytes(uint32_t n_pad, uint32_t kc, uint32_t k) {
+  // resident query chunks + (query, warp) lists + thresholds
+  return kc * n_pad * (kDenseBK * 2u) + n_pad * 4u * k * 8u + 4u * n_pad * 4u;
+}
+
+__global__ void __launch_bounds__(kDenseThreads, 1)
+scan_dense_t_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
+                    const DenseTParams p) {
+  extern __shared__ uint8_t dense_smem_raw[];
+  uint8_t* smem = dense_smem_raw + ((1024u - (ptx::smem_u32(dense_smem_raw) & 1023u)) & 1023u);
+  const uint32_t ns = p.n_stages, q_chunk = p.n_pad * (kDenseBK * 2u);
+  uint8_t* stages = smem;
+  uint8_t* q_res = smem + static_cast<size_t>(ns) * kDtStageBytes;  // kc chunks of [n_pad][128 B], SWIZZLE_128B
+  uint64_t* lists = reinterpret_cast<uint64_t*>(q_res + static_cast<size_t>(p.kc) * q_chunk);  // [n_pad][4][k]
+  float* thr = reinterpret_cast<float*>(lists + static_cast<size_t>(p.n_pad) * 4 * p.k);      // [4][n_pad]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(thr + 4 * p.n_pad);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kDenseMaxStages;
+  uint64_t* acc_full = bars + 2 * kDenseMaxStages;
+  uint64_t* acc_empty = bars + 2 * kDenseMaxStages + 2;
+  uint64_t* q_full = bars + 2 * kDenseMaxStages + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kDenseMaxStages + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_q);
+    ptx::prefetch_tmap(&tm_db);
+    for (uint32_t s = 0; s < ns; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&acc_full[a], 1);
+      ptx::mbar_init(&acc_empty[a], 4);
+    }
+    ptx::mbar_init(q_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t n_items = p.n_slices;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      const uint64_t pol_q = ptx::policy_evict_last();
+      const uint64_t pol_db = p.db_evict_first ? ptx::policy_evict_first() : ptx::policy_evict_last();
+      ptx::mbar_expect_tx(q_full, p.kc * q_chunk);
+      for (uint32_t kc = 0; kc < p.kc; ++kc)
+        ptx::tma_load_2d(q_res + static_cast<size_t>(kc) * q_chunk, &tm_q, static_cast<int32_t>(kc * kDenseBK), 0, q_full,
+                         pol_q);
+      uint32_t s = 0, round = 0;
+      for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t t0 = item * p.tiles_per_slice, t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+        for (uint32_t tile = t0; tile < t1; ++tile) {
+          for (uint32_t kc = 0; kc < p.kc; ++kc) {
+            if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
+            ptx::mbar_expect_tx(&full[s], kDtStageBytes);
+            ptx::tma_load_2d(stages + static_cast<size_t>(s) * kDtStageBytes, &tm_db, static_cast<int32_t>(kc * kDenseBK),
+                             static_cast<int32_t>(tile * 256u), &full[s], pol_db);
+            if (++s == ns) {
+              s = 0;
+              ++round;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      ptx::mbar_wait(q_full, 0);
+      ptx::tc_fence_after();
+      uint32_t s = 0, round = 0, tc = 0;
+      for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t t0 = item * p.tiles_per_slice, t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+        for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
+          const uint32_t as = tc & 1, ua = tc >> 1;
+          if (ua > 0) ptx::mbar_wait(&acc_empty[as], (ua - 1) & 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * 256u;
+          for (uint32_t kc = 0; kc < p.kc; ++kc) {
+            ptx::mbar_wait(&full[s], round & 1);
+            ptx::tc_fence_after();
+            const uint32_t db_addr = ptx::smem_u32(stages + static_cast<size_t>(s) * kDtStageBytes);
+            const uint64_t q_desc = ptx::umma_desc_k_sw128(ptx::smem_u32(q_res + static_cast<size_t>(kc) * q_chunk));
+#pragma unroll
+            for (uint32_t sub = 0; sub < 2; ++sub) {
+              const uint64_t db_desc = ptx::umma_desc_k_sw128(db_addr + sub * (128u * kDenseBK * 2u));
+#pragma unroll
+              for (uint32_t kk = 0; kk < kDenseBK / 16; ++kk)
+                ptx::tc_mma_f16(d_tmem + sub * p.n_pad, db_desc + kk * 2, q_desc + kk * 2, p.idesc,
+                                (kc | kk) != 0 ? 1u : 0u);
+            }
+            ptx::tc_commit(&empty[s]);
+            if (++s == ns) {
+              s = 0;
+              ++round;
+            }
+          }
+          ptx::tc_commit(&acc_full[as]);
+        }
+      }
+    }
+  } else {
+    // ================================================================ epilogue
+    const uint32_t w = warp & 3;  // TMEM lane quadrant of this warp
+    float* thr_w = thr + w * p.n_pad;
+    const uint32_t k = p.k;
+    for (uint32_t q = lane; q < p.n_pad; q += 32) thr_w[q] = q < p.nq ? -INFINITY : INFINITY;
+    for (uint32_t q = 0; q < p.n_pad; ++q)
+      for (uint32_t i = lane; i < k; i += 32) lists[(static_cast<size_t>(q) * 4 + w) * k + i] = 0ull;
+    __syncwarp();
+    const uint32_t tq = tmem_base + ((w * 32u) << 16);
+    uint32_t tc = 0;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const uint32_t t0 = item * p.tiles_per_slice, t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
+      for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
+        const uint32_t as = tc & 1;
+        ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
+        ptx::tc_fence_after();
+        if (!(p.debug & 4u)) {
+#pragma unroll 1
+          for (uint32_t sub = 0; sub < 2; ++sub) {
+            const uint32_t row0w = tile * 256u + sub * 128u + w * 32u;  // database row of lane 0
+            if (row0w >= p.n_rows) break;
+            const bool rvalid = row0w + lane < p.n_rows;
+#pragma unroll 1
+            for (uint32_t c = 0; c < p.n_pad; c += 16) {
+              float v[16];
+              ptx::tmem_ld_32x32b_x16(tq + as * 256u + sub * p.n_pad + c, v);
+              float t[16];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const float4 x = *reinterpret_cast<const float4*>(thr_w + c + 4 * g);
+                t[4 * g] = x.x;
+                t[4 * g + 1] = x.y;
+                t[4 * g + 2] = x.z;
+                t[4 * g + 3] = x.w;
+              }
+              bool hit = false;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) hit |= v[j] > t[j];
+              if (__any_sync(0xffffffffu, hit && rvalid)) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  uint32_t b = __ballot_sync(0xffffffffu, rvalid && v[j] > t[j]);
+                  while (b) {
+                    const int L = __ffs(b) - 1;
+                    b &= b - 1;
+                    const float sc = __shfl_sync(0xffffffffu, v[j], L);
+                    const uint32_t q = c + j;
+                    if (sc > thr_w[q]) {  // the threshold may have moved since the chunk's copy was read
+                      const uint64_t kth =
+                          warp_list_insert(lists + (static_cast<size_t>(q) * 4 + w) * k, static_cast<int>(k),
+                                           make_key(sc, row0w + L), lane);
+                      if (lane == 0) thr_w[q] = (kth == 0ull) ? -INFINITY : key_score(kth);
+                      __syncwarp();
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[as]);
+      }
+      // slice done: the four warps' lists of a query -> k keys in this CTA's slot
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (uint32_t q = w; q < p.nq; q += 4) {
+        uint64_t* dst = p.partial + (static_cast<size_t>(q) * p.n_lists + blockIdx.x) * k;
+        warp_multiway_merge<1>(lists + static_cast<size_t>(q) * 4 * k, 4u, k, k, lane,
+                               [=](uint32_t r, uint64_t key) { dst[r] = key; });
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (item + gridDim.x < n_items) {  // another slice for this CTA: start its lists afresh
+        for (uint32_t q = lane; q < p.n_pad; q += 32) thr_w[q] = q < p.nq ? -INFINITY : INFINITY;
+        for (uint32_t q = 0; q < p.n_pad; ++q)
+          for (uint32_t i = lane; i < k; i += 32) lists[(static_cast<size_t>(q) * 4 + w) * k + i] = 0ull;
+        __syncwarp();
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 // ================================================================================================ 2-CTA kernel

@@ -118,7 +118,7 @@ struct sgic_index {
   int64_t shard_row_start = 0, shard_total_rows = -1;
   int shard_id = 0, shard_count = 1;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 5, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0;
   int64_t stat_ingest_h2d_ns = 0, stat_ingest_k0_ns = 0, stat_ingest_k1_ns = 0;
   int64_t stat_ingest_parse_ns = 0, stat_ingest_pack_ns = 0, stat_ingest_gpu_ns = 0;
   int64_t stat_zl_device_frames = 0, stat_zl_host_rows = 0, stat_zl_fallback_slabs = 0;
@@ -373,7 +373,6 @@ static uint32_t gcd_u32(uint32_t a, uint32_t b) {
 }
 
 constexpr int kDenseBN = 256;
-constexpr int kDenseStages = 4;
 constexpr int64_t kDenseQueryBlock = 4096;  // queries per launch (FAISS blocks queries by 4096 too)
 
 static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
@@ -387,12 +386,12 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
   const uint32_t res_cap = std::max<uint32_t>(256, 2 * kp);
   const size_t epi_bytes = dense_epi_bytes(static_cast<uint32_t>(k), tp);
   // the three kernels' shared memory: alignment slack + operand ring (+ resident query tile) + epilogue + barriers
-  const size_t smem_1cta = 1024 + static_cast<size_t>(kDenseStages) * Cfg::kStageBytes + epi_bytes + 256;
+  const size_t smem_1cta = 1024 + Cfg::kStageBytes + epi_bytes + 256;  // at least one full stage (ring sized below)
   const size_t smem_2r = 1024 + static_cast<size_t>(kD2MaxKc + 4) * kD2HalfBytes + epi_bytes + 256;
   const size_t smem_2s = 1024 + static_cast<size_t>(6) * 2 * kD2HalfBytes + epi_bytes + 256;
   SGIC_REQUIRE(std::max(smem_1cta, std::max(smem_2r, smem_2s)) <= kSmemBudget,
                "dense path: shared memory budget exceeded");
-  auto kern = scan_dense_kernel<kDenseBN, kDenseStages>;
+  auto kern = scan_dense_kernel<kDenseBN>;
   auto kern2r = scan_dense2_kernel<true, 4>;   // CTA pairs, query tile resident (d <= 512)
   auto kern2s = scan_dense2_kernel<false, 6>;  // CTA pairs, query tile streamed with the database
   static bool configured[64] = {false};
@@ -473,9 +472,24 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
       }
     }
     CUtensorMap tm_q;
+    // Small batches with thread-private-sized k: the transposed kernel (database rows on M, queries on N), as
+    // long as the resident query matrix + lists leave room for a ring of at least 3 database stages.
+    // "dense_mode" = 1 keeps the queries-on-M single-CTA kernel (A/B comparisons).
+    const uint32_t kc_chunks = (static_cast<uint32_t>(h->d) + kDenseBK - 1) / kDenseBK;
+    const uint32_t n_pad = (nqb + 15u) & ~15u;
+    uint32_t t_stages = 0;
+    if (!pairs && tp && h->opt_dense_mode != 1) {
+      const size_t fixed = dense_t_fixed_bytes(n_pad, kc_chunks, static_cast<uint32_t>(k)) + 1024 + 256;
+      // measured at 100M x 512, nq = 8: 3-4 stages (96-128 KB in flight) 14.2 ms, 5 stages 15.2 ms, 6 stages 15.5 ms
+      if (fixed < kSmemBudget) t_stages = static_cast<uint32_t>(std::min<size_t>((kSmemBudget - fixed) / kDtStageBytes, 4));
+      if (h->opt_stages > 0) t_stages = std::min<uint32_t>(t_stages, static_cast<uint32_t>(h->opt_stages));
+      if (t_stages < 3) t_stages = 0;
+    }
+    const bool transposed = t_stages > 0;
     rc = make_tmap_rows(&tm_q, static_cast<const uint8_t*>(h->qh) + static_cast<size_t>(q0) * h->d * 2, nqb,
                         static_cast<uint32_t>(h->d),
-                        pairs ? static_cast<uint32_t>(kDenseBM) : std::min<uint32_t>(kDenseBM, (nqb + 7u) & ~7u),
+                        transposed ? n_pad
+                                   : pairs ? static_cast<uint32_t>(kDenseBM) : std::min<uint32_t>(kDenseBM, (nqb + 7u) & ~7u),
                         h->dtype);
     if (rc) return rc;
     DenseParams p;
@@ -493,17 +507,50 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.kc = (static_cast<uint32_t>(h->d) + kDenseBK - 1) / kDenseBK;
     p.tp = tp ? 1u : 0u;
     p.a_rows = pairs ? static_cast<uint32_t>(kDenseBM) : std::min<uint32_t>(kDenseBM, (nqb + 7u) & ~7u);
+    // single-CTA ring: the query box only reserves what the batch needs, the rest of shared memory goes to
+    // database stages ("stages" option overrides the depth for experiments)
+    p.a_region = (p.a_rows * static_cast<uint32_t>(kDenseBK * 2) + 1023u) & ~1023u;
+    {
+      const size_t per_stage = p.a_region + Cfg::kBBytes;
+      size_t ns = (kSmemBudget - 1024 - epi_bytes - 256) / per_stage;
+      ns = std::min<size_t>(ns, kDenseMaxStages);
+      if (h->opt_stages > 0) ns = std::min<size_t>(ns, static_cast<size_t>(h->opt_stages));
+      p.n_stages = static_cast<uint32_t>(std::max<size_t>(ns, 1));
+    }
     p.idesc = ptx::umma_idesc_f16(q_tile, kDenseBN, h->dtype == SGIC_BF16 ? 1u : 0u);
     p.db_evict_first = (m_tiles == 1 && h->opt_evict_first) ? 1u : 0u;
     p.debug = static_cast<uint32_t>(h->opt_debug);
     SGIC_CUDA(cudaMemsetAsync(h->ws, 0, partial_bytes, st));  // empty lists: every CTA resumes its own
-    if (!pairs) kern<<<grid, kDenseThreads, kSmemBudget, st>>>(tm_q, tm_db, p);
+    if (transposed) {
+      DenseTParams tp_;
+      tp_.partial = p.partial;
+      tp_.n_rows = n_rows;
+      tp_.nq = nqb;
+      tp_.k = static_cast<uint32_t>(k);
+      tp_.n_pad = n_pad;
+      tp_.n_slices = n_slices;  // m_tiles == 1: one slice per CTA
+      tp_.tiles_per_slice = tiles_per_slice;
+      tp_.n_tiles = n_tiles;
+      tp_.n_lists = grid_units;
+      tp_.kc = kc_chunks;
+      tp_.n_stages = t_stages;
+      tp_.idesc = ptx::umma_idesc_f16(128, n_pad, h->dtype == SGIC_BF16 ? 1u : 0u);
+      tp_.db_evict_first = p.db_evict_first;
+      tp_.debug = p.debug;
+      static bool t_configured[64] = {false};
+      if (!t_configured[h->device & 63]) {
+        SGIC_CUDA(cudaFuncSetAttribute(scan_dense_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kSmemBudget)));
+        t_configured[h->device & 63] = true;
+      }
+      scan_dense_t_kernel<<<grid, kDenseThreads, kSmemBudget, st>>>(tm_q, tm_db, tp_);
+    } else if (!pairs) kern<<<grid, kDenseThreads, kSmemBudget, st>>>(tm_q, tm_db, p);
     else if (a_resident) kern2r<<<grid, kDenseThreads, kSmemBudget, st>>>(tm_q, tm_db, p);
     else kern2s<<<grid, kDenseThreads, kSmemBudget, st>>>(tm_q, tm_db, p);
     h->stat_launches++;
     SGIC_CUDA(cudaGetLastError());
     h->stat_last_grid = grid;
-    h->stat_last_stages = kDenseStages;
+    h->stat_last_stages = transposed ? t_stages : pairs ? 4 : p.n_stages;
     if (h->opt_timing && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));
     rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nqb, grid_units, static_cast<uint32_t>(k),
                            dev_D + static_cast<size_t>(q0) * k, dev_I + static_cast<size_t>(q0) * k, id_base, st,
@@ -534,7 +581,12 @@ static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_
   SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
   if (nq == 0) return 0;
   SGIC_REQUIRE(h->ntotal < (1ll << 32) - 1, "more than 2^32-2 rows in one shard");
-  if (h->ntotal > 0 && nq >= h->opt_dense_min_nq) return search_dense_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st);
+  // Regime choice (measured, 512-d fp16): one query -> K3.  Two queries -> K3 on small shards (one launch), the
+  // transposed tensor-core kernel from ~8M rows (100M rows: 14.2 ms against K3's 15.8 ms).  Three or more ->
+  // tensor cores always (K3 with 4 queries is FMA-bound: 18.5 ms at 100M rows against 15.4 ms).
+  int64_t min_nq = h->opt_dense_min_nq;
+  if (min_nq == 0) min_nq = (h->ntotal >= (8ll << 20)) ? 2 : 3;
+  if (h->ntotal > 0 && nq >= min_nq) return search_dense_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st);
   return search_small_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st);
 }
 
@@ -1459,7 +1511,7 @@ int64_t sgic_index_get_stat(const sgic_index* h, const char* name) {
   if (n == "last_stages") return h->stat_last_stages;
   if (n == "capacity") return h->capacity;
   if (n == "sm_count") return h->sm_count;
-  if (n == "dense_min_nq") return h->opt_dense_min_nq;
+  if (n == "dense_min_nq") return h->opt_dense_min_nq ? h->opt_dense_min_nq : ((h->ntotal >= (8ll << 20)) ? 2 : 3);
   if (n == "ingest_h2d_ns") return h->stat_ingest_h2d_ns;
   if (n == "ingest_k0_ns") return h->stat_ingest_k0_ns;
   if (n == "ingest_k1_ns") return h->stat_ingest_k1_ns;

@@ -27,7 +27,8 @@ def make_index(xb, dtype="fp16", **kw):
     return idx
 
 
-# dense_mode: 0 = automatic (single CTA up to 128 queries, pairs beyond), 1 = single CTA, 2 = pairs with the
+# dense_mode: 0 = automatic (up to 128 queries: the transposed kernel when k <= 32 and shared memory allows, else
+# the queries-on-M single-CTA kernel; CTA pairs beyond), 1 = queries-on-M single-CTA kernel, 2 = pairs with the
 # query tile streamed, 3 = pairs forced
 CASES = [
     (256, 64, 5, 4),          # smallest: one tile, d = one K chunk
@@ -46,6 +47,10 @@ CASES = [
     (100000, 128, 4096, 5),   # a full query block
     (20000, 512, 64, 1024),   # k at the supported maximum (reservoirs of 2048 keys)
     (60000, 256, 129, 500),
+    (33000, 512, 2, 10),      # transposed kernel: smallest batch, ragged last tile
+    (33000, 768, 33, 32),     # transposed: 48 query columns, largest thread-private k
+    (33000, 1024, 64, 7),     # transposed: 64 columns, d = 1024
+    (100, 64, 3, 10),         # fewer rows than one sub-tile
 ]
 
 

@@ -43,10 +43,17 @@ def make_index(xb, dtype="fp16"):
     (50000, 512, 7, 10),    # > 4 queries: several passes
     (20000, 512, 1, 1024),
 ])
-def test_search_matches_oracle(n, d, nq, k):
+@pytest.mark.parametrize("force_k3", [True, False])
+def test_search_matches_oracle(n, d, nq, k, force_k3):
+    """force_k3: every batch size through the CUDA-core streaming kernel (its 2- and 4-query variants); otherwise
+    the library's own regime choice (batches of 3+ go to the tensor-core kernels)."""
+    if nq == 1 and not force_k3:
+        pytest.skip("one query is always K3")
     rng = np.random.default_rng(n * 31 + d + nq + k)
     xb, xq = unit(rng, n, d), unit(rng, nq, d)
     idx = make_index(xb)
+    if force_k3:
+        idx.set_option("dense_min_nq", 1 << 30)
     assert idx.ntotal == n and idx.d == d
     D, I = idx.search(xq, k)
     # O-exact: oracle on the values the GPU holds (fp16-rounded db and queries)
