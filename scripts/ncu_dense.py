@@ -11,6 +11,7 @@ k = int(sys.argv[4]) if len(sys.argv) > 4 else 10
 idx = faiss.IndexFlatIP(d, device=0, retain_fp32=False); fill_index_random(idx, n)
 if len(sys.argv) > 5:
     idx.set_option("dense_l2_mb", int(sys.argv[5]))
+
 q = torch.from_numpy(random_unit_queries(nq, d)).cuda()
 for _ in range(3):
     D, I = idx.search_torch(q, k)

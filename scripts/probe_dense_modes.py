@@ -25,6 +25,7 @@ if min_nq is not None:
     idx.set_option("dense_min_nq", min_nq)
 if len(sys.argv) > 9:
     idx.set_option("stages", int(sys.argv[9]))
+
 print(f"n={n} d={d} k={k} dense_min_nq={min_nq}", flush=True)
 for nq in nqs:
     q = torch.from_numpy(random_unit_queries(nq, d)).cuda()

@@ -18,8 +18,10 @@
 // Work split: items = (query tile m, database slice s), m fastest, dealt round-robin to the CTAs (pairs), so the
 // CTAs that run concurrently share a few slices and re-use each other's database tiles from L2 while they stay
 // close (10M rows: 12.7 GB read from DRAM for a 10.2 GB database; 100M rows: the query tiles drift apart over
-// 10.5k tiles and DRAM reads grow to 988 GB — 34 % of DRAM peak, not the bound; a lockstep or TMA multicast
-// across pairs is what would fix it, shorter slices alone do not, see the host's slice comment).  A CTA parks
+// 10.5k tiles and DRAM reads grow to 988 GB — 34 % of DRAM peak, not the bound.  Two attempts to restore the
+// sharing were measured and dropped: shorter slices (host's slice comment) and a bounded soft lockstep of the
+// producers through progress counters in global memory (nq = 4096: 358-373 ms against 370 ms, nq = 1024: 17 %
+// slower) — the batch regime is limited by the power cap on the tensor pipe, not by DRAM).  A CTA parks
 // a query tile's top-k list in its own slot of `partial` at the end of an item and resumes it — threshold
 // included — if it visits that tile again; merge_keys_*_kernel merges the CTAs' lists at the end.
 //

@@ -520,6 +520,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.idesc = ptx::umma_idesc_f16(q_tile, kDenseBN, h->dtype == SGIC_BF16 ? 1u : 0u);
     p.db_evict_first = (m_tiles == 1 && h->opt_evict_first) ? 1u : 0u;
     p.debug = static_cast<uint32_t>(h->opt_debug);
+    h->ws_counter = nullptr;  // this launch overwrites the workspace: K3 must re-zero its "CTAs done" counter
     SGIC_CUDA(cudaMemsetAsync(h->ws, 0, partial_bytes, st));  // empty lists: every CTA resumes its own
     if (transposed) {
       DenseTParams tp_;

@@ -133,3 +133,18 @@ def test_dense_self_queries_full_block():
     assert np.all(np.abs(D[:, 0] - 1.0) < 2e-3)
     assert np.all(D[:, 1:] < 0.5)  # random unit vectors in 512 dimensions are nearly orthogonal
     assert np.all(D[:, :-1] >= D[:, 1:])
+
+
+def test_mixed_batch_sizes_share_the_workspace():
+    """A resident service alternates batch sizes on one index: the streaming kernel's grid counter and the dense
+    kernels' partial lists live in the same workspace and must not disturb each other (K3 -> K4 -> K3 -> K4t)."""
+    rng = np.random.default_rng(41)
+    xb, xq = unit(rng, 60_000, 512), unit(rng, 300, 512)
+    idx = make_index(xb)
+    ref = {}
+    for nq in (1, 300, 1, 7, 1, 64, 2, 1):
+        D, I = idx.search(xq[:nq], 10)
+        check_topk(D[:8], I[:8], f16(xb), f16(xq[:min(nq, 8)]), 10, score_tol=3e-5, tie_tol=1e-6)
+        if nq in ref:
+            assert np.array_equal(ref[nq][1], I) and np.array_equal(ref[nq][0], D)
+        ref[nq] = (D, I)
