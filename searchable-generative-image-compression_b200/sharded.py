@@ -121,6 +121,27 @@ class ShardedIndexFlatIP(Index):
         self._note_segment(self._ntotal + global_start, count)
         self._ntotal += total
 
+    def add_c2df_paths(self, paths, n_threads: int = 0):
+        """Collective ingest of ``.c2df`` files (config C5: header ingestion straight to the owning GPU).
+
+        Every rank passes the SAME path list (``sorted(glob)`` order, as build.py:74 produces); rank g reads,
+        walks and decodes the g-th contiguous slice of it on its own host threads and GPU
+        (``IndexFlatIP.add_c2df_paths``).  Files that fail are skipped as ``[SKIP]`` does (build.py:87-88), so the
+        global row number of a file is the number of good files before it: one ``all_gather`` of the per-rank
+        counts (and statuses) places every shard.  Returns the status of every file, identical on all ranks."""
+        paths = list(paths)
+        lo, hi = shard_range(len(paths), self.world, self.rank)
+        before = self.local.ntotal
+        st_local = np.asarray(self.local.add_c2df_paths(paths[lo:hi], n_threads), dtype=np.int32)
+        count = self.local.ntotal - before
+        gathered = [None] * self.world
+        self._dist.all_gather_object(gathered, (int(count), st_local.tolist()), group=self._group)
+        start = sum(c for c, _ in gathered[:self.rank])
+        total = sum(c for c, _ in gathered)
+        self._note_segment(self._ntotal + start, count)
+        self._ntotal += total
+        return np.concatenate([np.asarray(st, dtype=np.int32) for _, st in gathered]) if paths else np.zeros(0, np.int32)
+
     # ---------------------------------------------------------------- search
     def _to_global(self, I_local):
         """local row numbers → global row numbers (identity + base for a single segment)."""

@@ -73,12 +73,47 @@ def _worker(rank, world, port, out_dir):
             xb16 = xb.astype(np.float16).astype(np.float64)
             check_topk(D, I, xb16, xq.astype(np.float16).astype(np.float64), k, score_tol=2e-5, tie_tol=1e-6)
             assert I[0, 0] == 0 and I[0, 1] == 40_000      # exact tie -> lower global id first
+        # collective .c2df ingest (config C5's loader) + SGI2 shard files: save, reload, same answers
+        from oracle import c2df_ref
+        paths = sorted(str(p) for p in Path(out_dir).glob("corpus/*.c2df"))
+        idx2 = ShardedIndexFlatIP(d)
+        status = idx2.add_c2df_paths(paths, n_threads=2)
+        good = [i for i, p in enumerate(paths) if "bad" not in Path(p).name]
+        assert list(np.nonzero(status == 0)[0]) == good and idx2.ntotal == len(good)
+        rows = np.stack([c2df_ref.decode_clip(Path(paths[i]).read_bytes())[1] for i in good])
+        qs = rows[[0, len(good) // 2, len(good) - 1]]
+        D2, I2 = idx2.search(qs, 5)
+        assert list(I2[:, 0]) == [0, len(good) // 2, len(good) - 1] and np.all(np.abs(D2[:, 0] - 1.0) < 2e-3)
+        check_topk(D2, I2, rows.astype(np.float16).astype(np.float64), qs.astype(np.float16).astype(np.float64), 5,
+                   score_tol=1e-3)
+        idx2.save(Path(out_dir) / "shards")
+        idx3 = ShardedIndexFlatIP.load(Path(out_dir) / "shards")
+        assert idx3.ntotal == idx2.ntotal and idx3.local_ntotal == idx2.local_ntotal
+        D3, I3 = idx3.search(qs, 5)
+        assert np.array_equal(I3, I2) and np.array_equal(D3, D2)
         (Path(out_dir) / f"ok{rank}").write_text("ok")
     finally:
         dist.destroy_process_group()
 
 
+def _write_c2df_corpus(root, d=512, n=301):
+    from sgic_b200 import c2df
+    from sgic_b200.index_build import quantize_u8_and_compress
+    rng = np.random.default_rng(5)
+    (root / "corpus").mkdir()
+    for i in range(n):
+        v = rng.standard_normal(d).astype(np.float32)
+        v /= np.linalg.norm(v)
+        payload, meta = quantize_u8_and_compress(v)
+        name = f"img_{i:04d}.c2df"
+        blob = c2df.pack_c2df({"clip_stream": payload, "clip_meta": meta}, {"version": 2})
+        if i in (2, 140, 170, 171):                            # broken files in both ranks' slices
+            name, blob = f"img_{i:04d}_bad.c2df", b"XXXX" + blob[4:]
+        (root / "corpus" / name).write_bytes(blob)
+
+
 def test_two_gpu_nccl_sharded_search(tmp_path):
+    _write_c2df_corpus(tmp_path)
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")

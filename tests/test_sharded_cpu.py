@@ -42,6 +42,21 @@ class _FakeLocal:
     def add(self, x):
         self.rows = np.concatenate([self.rows, np.asarray(x, dtype=np.float32)])
 
+    def add_c2df_paths(self, paths, n_threads=0):
+        """oracle decode of each file; status 0 = added, 1 = skipped (any reference exception)"""
+        from oracle import c2df_ref
+        st = []
+        for p in paths:
+            try:
+                _, z = c2df_ref.decode_clip(Path(p).read_bytes())
+                if z.shape[0] != self.d:
+                    raise ValueError("dim")
+                self.add(z[None, :])
+                st.append(0)
+            except Exception:
+                st.append(1)
+        return np.asarray(st, dtype=np.int32)
+
     def search_torch(self, q, k, id_base=0):
         from oracle.flat_ip import flat_ip_search
         D, I = flat_ip_search(self.rows, q.numpy(), k)
@@ -92,12 +107,41 @@ def _worker(rank, world, port, seed, out_dir):
         assert np.allclose(D, Dref, atol=1e-6)
         D2, I2 = idx.search(q[:1], 400)                          # k > ntotal: -1 padding survives the merge
         assert (I2[0] >= 0).sum() == full.shape[0] and np.all(I2[0, full.shape[0]:] == -1)
+        # collective .c2df ingest: every rank takes its slice of the sorted path list; skipped files shift the
+        # global row numbers of everything behind them, on every rank alike
+        paths = sorted(str(p) for p in Path(out_dir).glob("corpus/*.c2df"))
+        idx2 = ShardedIndexFlatIP(d, local_factory=_FakeLocal, merge_fn=_fake_merge)
+        status = idx2.add_c2df_paths(paths)
+        good = [i for i, p in enumerate(paths) if "bad" not in Path(p).name]
+        assert list(np.nonzero(status == 0)[0]) == good and idx2.ntotal == len(good)
+        from oracle import c2df_ref
+        rows = np.stack([c2df_ref.decode_clip(Path(paths[i]).read_bytes())[1] for i in good])
+        D3, I3 = idx2.search(rows[[0, len(good) - 1]], 5)
+        Dr, Ir = flat_ip_search(rows, rows[[0, len(good) - 1]], 5)
+        assert np.array_equal(I3, Ir) and I3[0, 0] == 0 and I3[1, 0] == len(good) - 1
         (Path(out_dir) / f"ok{rank}").write_text("ok")
     finally:
         dist.destroy_process_group()
 
 
+def _write_c2df_corpus(root, d=64, n=23):
+    from sgic_b200 import c2df
+    from sgic_b200.index_build import quantize_u8_and_compress
+    rng = np.random.default_rng(5)
+    (root / "corpus").mkdir()
+    for i in range(n):
+        v = rng.standard_normal(d).astype(np.float32)
+        v /= np.linalg.norm(v)
+        payload, meta = quantize_u8_and_compress(v)
+        name = f"img_{i:03d}.c2df"
+        blob = c2df.pack_c2df({"clip_stream": payload, "clip_meta": meta}, {"version": 2})
+        if i in (2, 11, 12):                                   # broken files land in both ranks' slices
+            name, blob = f"img_{i:03d}_bad.c2df", b"XXXX" + blob[4:]
+        (root / "corpus" / name).write_bytes(blob)
+
+
 def test_two_rank_gloo_matches_single_index(tmp_path):
+    _write_c2df_corpus(tmp_path)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
