@@ -115,17 +115,22 @@ constexpr int kZlWarpsPerBlock = 4;
 
 struct __align__(16) ZlWarpSmem {
   uint8_t frame[kZlMaxFrame];
+  uint8_t lit[2048];   // literals of a frame that also has sequences
+  uint8_t out[2048];   // its regenerated row, before the cooperative copy to global memory
   uint16_t tab[1u << zl::kHufMaxLog];
   uint8_t w[256];
   uint8_t nb[256];
   zl::FseTable ft;
-  uint32_t info[12];
+  zl::SeqTables seq;
+  uint32_t info[16];
 };
 
 // One warp per frame.  The frame is staged in shared memory with 16-byte loads; lane 0 parses the headers and
 // decodes the Huffman tree description (FSE-compressed weights: inherently serial, ~100 symbols); all lanes
-// fill the 2^max_bits decoding table; lanes 0..3 decode the four backward bitstreams in parallel straight into
-// the u8 row.  status[f] = zl::ZL_OK or the reason the frame has to go back to libzstd on the host.
+// fill the 2^max_bits decoding table; lanes 0..3 decode the four backward bitstreams in parallel — straight
+// into the u8 row when the block has no sequences, otherwise into shared memory, where lane 0 then decodes and
+// executes the (few) match sequences and the warp copies the finished row out.  status[f] = zl::ZL_OK or the
+// reason the frame has to go back to libzstd on the host.
 __global__ void __launch_bounds__(kZlWarpsPerBlock * 32)
 zstd_lit_decode_kernel(const uint8_t* __restrict__ frames, const ZlDesc* __restrict__ desc, uint32_t n_frames,
                        uint32_t d, uint8_t* __restrict__ rows, int32_t* __restrict__ status) {
@@ -135,7 +140,7 @@ zstd_lit_decode_kernel(const uint8_t* __restrict__ frames, const ZlDesc* __restr
   const uint32_t n_warps = gridDim.x * kZlWarpsPerBlock;
   for (uint32_t f = blockIdx.x * kZlWarpsPerBlock + warp; f < n_frames; f += n_warps) {
     const ZlDesc de = desc[f];
-    if (de.len > kZlMaxFrame) {  // the host never sends one; defensive
+    if (de.len > kZlMaxFrame || d > 2048u) {  // the host never sends one; defensive
       if (lane == 0) status[f] = zl::ZL_HOST;
       continue;
     }
@@ -146,20 +151,34 @@ zstd_lit_decode_kernel(const uint8_t* __restrict__ frames, const ZlDesc* __restr
       zl::FrameInfo fi;
       int rc = zl::parse_frame(S.frame, de.len, fi);
       if (rc == zl::ZL_OK && fi.content_size != d) rc = zl::ZL_HOST;
-      uint32_t td = 0, nsym = 0, max_bits = 0;
-      const bool huf = rc == zl::ZL_OK && fi.block_type == 2 && fi.lit_type == 2;
-      if (huf) {
-        td = zl::huf_read_lengths(S.frame + fi.lit_off, fi.comp, S.w, S.nb, nsym, max_bits, S.ft);
-        if (td == 0) rc = zl::ZL_CORRUPT;
+      uint32_t td = 0, nsym = 0, max_bits = 0, kind = 0, pay = 0, has_seq = 0, regen = d;
+      if (rc == zl::ZL_OK) {
+        if (fi.block_type != 2) {
+          kind = fi.block_type;  // 0 raw, 1 RLE block
+          pay = fi.block_off;
+        } else {
+          kind = fi.lit_type;    // literals: 0 raw, 1 RLE, 2 Huffman
+          pay = fi.lit_off;
+          regen = fi.regen;
+          has_seq = S.frame[fi.seq_off] != 0 ? 1u : 0u;
+          if (kind == 2) {
+            td = zl::huf_read_lengths(S.frame + fi.lit_off, fi.comp, S.w, S.nb, nsym, max_bits, S.ft);
+            if (td == 0) rc = zl::ZL_CORRUPT;
+          }
+        }
       }
       S.info[0] = static_cast<uint32_t>(rc);
-      S.info[1] = huf ? 2u : (fi.block_type == 1 || (fi.block_type == 2 && fi.lit_type == 1)) ? 1u : 0u;  // 0 raw 1 rle 2 huffman
-      S.info[2] = (fi.block_type == 2) ? fi.lit_off : fi.block_off;  // payload start
+      S.info[1] = kind;
+      S.info[2] = pay;
       S.info[3] = fi.comp;
       S.info[4] = fi.n_streams;
       S.info[5] = td;
       S.info[6] = nsym;
       S.info[7] = max_bits;
+      S.info[8] = has_seq;
+      S.info[9] = regen;
+      S.info[10] = fi.seq_off;
+      S.info[11] = fi.seq_size;
     }
     __syncwarp();
     const int rc = static_cast<int>(S.info[0]);
@@ -169,28 +188,40 @@ zstd_lit_decode_kernel(const uint8_t* __restrict__ frames, const ZlDesc* __restr
       continue;
     }
     uint8_t* dst = rows + static_cast<size_t>(de.row) * d;
-    const uint32_t kind = S.info[1], pay = S.info[2];
+    const uint32_t kind = S.info[1], pay = S.info[2], has_seq = S.info[8], regen = S.info[9];
+    uint8_t* lit = has_seq ? S.lit : dst;  // without sequences the literals are the row
     bool ok = true;
     if (kind == 0) {
-      for (uint32_t i = lane; i < d; i += 32) dst[i] = S.frame[pay + i];
+      for (uint32_t i = lane; i < regen; i += 32) lit[i] = S.frame[pay + i];
     } else if (kind == 1) {
       const uint8_t b = S.frame[pay];
-      for (uint32_t i = lane; i < d; i += 32) dst[i] = b;
+      for (uint32_t i = lane; i < regen; i += 32) lit[i] = b;
     } else {
       const uint32_t comp = S.info[3], n_streams = S.info[4], td = S.info[5], nsym = S.info[6], max_bits = S.info[7];
       ok = zl::huf_fill_table(S.nb, nsym, max_bits, S.tab, lane, 32);
       __syncwarp();
       uint32_t soff[4], slen[4], scnt[4];
       const uint8_t* ss = S.frame + pay + td;
-      ok = ok && zl::huf_stream_layout(ss, comp - td, n_streams, d, soff, slen, scnt);
+      ok = ok && zl::huf_stream_layout(ss, comp - td, n_streams, regen, soff, slen, scnt);
       if (ok && lane < n_streams) {
         uint32_t o = 0;
         for (uint32_t i = 0; i < lane; ++i) o += scnt[i];
-        ok = zl::huf_decode_stream(S.tab, max_bits, ss + soff[lane], slen[lane], dst + o, scnt[lane]);
+        ok = zl::huf_decode_stream(S.tab, max_bits, ss + soff[lane], slen[lane], lit + o, scnt[lane]);
       }
     }
-    const bool all_ok = __all_sync(0xffffffffu, ok);
-    if (lane == 0) status[f] = all_ok ? zl::ZL_OK : zl::ZL_CORRUPT;
+    bool all_ok = __all_sync(0xffffffffu, ok);
+    int final_rc = all_ok ? zl::ZL_OK : zl::ZL_CORRUPT;
+    if (all_ok && has_seq) {
+      __syncwarp();  // the literals are complete in shared memory
+      int src = zl::ZL_OK;
+      if (lane == 0) src = zl::decode_sequences(S.frame + S.info[10], S.info[11], S.lit, regen, S.out, d, S.seq);
+      final_rc = __shfl_sync(0xffffffffu, src, 0);
+      __syncwarp();
+      if (final_rc == zl::ZL_OK)
+        for (uint32_t i = lane; i < d / 8; i += 32)
+          reinterpret_cast<uint2*>(dst)[i] = reinterpret_cast<const uint2*>(S.out)[i];
+    }
+    if (lane == 0) status[f] = final_rc;
     __syncwarp();  // the next frame overwrites this warp's shared memory
   }
 }

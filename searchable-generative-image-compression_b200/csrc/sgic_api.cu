@@ -968,9 +968,15 @@ static int add_u8_with_frames(sgic_index* h, int64_t w, int64_t n_host_rows, siz
   SGIC_CUDA(cudaMemcpyAsync(h->zl_desc, h->zl_pin_desc, static_cast<size_t>(nf) * sizeof(ZlDesc),
                             cudaMemcpyHostToDevice, st));
   if (tm) SGIC_CUDA(cudaEventRecord(h->tm, st));
-  const size_t smem = static_cast<size_t>(kZlWarpsPerBlock) * sizeof(ZlWarpSmem);
+  const size_t smem = static_cast<size_t>(kZlWarpsPerBlock) * sizeof(ZlWarpSmem);  // ~71 KB: 3 CTAs per SM
+  static bool zl_configured[64] = {false};
+  if (!zl_configured[h->device & 63]) {
+    SGIC_CUDA(cudaFuncSetAttribute(zstd_lit_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+    zl_configured[h->device & 63] = true;
+  }
   const unsigned grid = std::min<unsigned>((nf + kZlWarpsPerBlock - 1) / kZlWarpsPerBlock,
-                                           static_cast<unsigned>(h->sm_count) * 7u);
+                                           static_cast<unsigned>(h->sm_count) * 3u);
   zstd_lit_decode_kernel<<<grid, kZlWarpsPerBlock * 32, smem, st>>>(
       static_cast<const uint8_t*>(h->zl_frames), static_cast<const ZlDesc*>(h->zl_desc), nf, static_cast<uint32_t>(d),
       static_cast<uint8_t*>(h->zl_rows), static_cast<int32_t*>(h->zl_status));

@@ -6,10 +6,11 @@
 // Huffman literals read backwards.
 //
 // Profile decoded here: single-block frames without dictionary / checksum whose block is raw, RLE, or
-// compressed with ZERO sequences (literals raw, RLE or Huffman-compressed).  Measured on u8-quantised unit
-// vectors at level 19: 84 % of d=512 frames and 69 % of d=768 frames are in the profile (the rest carry a few
-// match sequences); everything else — and anything malformed — is classified ZL_HOST and goes through libzstd
-// on the host exactly as before, so results never depend on which side decoded a frame.
+// compressed (literals raw, RLE or Huffman-compressed; sequences section with predefined, RLE or
+// FSE-compressed tables and the repeat-offset history).  That is every frame zstd level 19 produces for a
+// u8-quantised vector (16 % of d=512 and 31 % of d=768 frames carry a few match sequences); everything else —
+// and anything malformed — is classified ZL_HOST and goes through libzstd on the host exactly as before, so
+// results never depend on which side decoded a frame.
 //
 // Every function is __host__ __device__: tests/test_zstd_lit.py compiles this header for the CPU and checks it
 // against libzstd on thousands of frames; the GPU tests check the kernel that calls the same functions.
@@ -53,6 +54,8 @@ struct FrameInfo {
   uint32_t n_streams;     // 1 or 4
   uint32_t regen, comp;   // literals: regenerated / compressed size
   uint32_t lit_off;       // first byte after the literals section header
+  uint32_t seq_off;       // compressed block: first byte of the sequences section
+  uint32_t seq_size;      // its size (>= 1); a single zero byte = no sequences
 };
 
 SGIC_HD uint32_t hsb(uint32_t x) {  // index of the highest set bit, x > 0
@@ -137,9 +140,14 @@ SGIC_HD int parse_frame(const uint8_t* s, uint32_t n, FrameInfo& f) {
   }
   f.lit_off = p + hl;
   const uint32_t q = f.lit_off + f.comp;
-  if (q + 1 != end) return ZL_HOST;        // exactly one byte may follow the literals: Number_of_Sequences ...
-  if (s[q] != 0) return ZL_HOST;           // ... and it must be zero
-  if (f.regen != f.content_size) return ZL_HOST;
+  if (q >= end) return ZL_HOST;            // the sequences section header is mandatory
+  f.seq_off = q;
+  f.seq_size = end - q;
+  if (s[q] == 0) {                         // no sequences: the literals are the content
+    if (f.seq_size != 1 || f.regen != f.content_size) return ZL_HOST;
+  } else if (f.regen > f.content_size) {
+    return ZL_HOST;
+  }
   return ZL_OK;
 }
 
@@ -383,40 +391,289 @@ SGIC_HD bool huf_stream_layout(const uint8_t* s, uint32_t avail, uint32_t n_stre
   return l0 > 0 && l1 > 0 && l2 > 0 && scnt[3] > 0;
 }
 
+// ---------------------------------------------------------------------------------- sequences section
+// RFC 8878 3.1.1.3.2: Number_of_Sequences, Symbol_Compression_Modes, up to three FSE tables (literals lengths,
+// offsets, match lengths: predefined / RLE / FSE-compressed), then one backward bitstream with three interleaved
+// states.  Executed serially: copy `ll` literals, copy `ml` bytes from `offset` back (repeat-offset history
+// {1,4,8}), and the remaining literals at the end.
+constexpr uint32_t kSeqMaxLog = 9;
+constexpr uint32_t kSeqMaxSym = 53;
+
+struct FseSeqTable {
+  uint8_t sym[1u << kSeqMaxLog];
+  uint8_t nbits[1u << kSeqMaxLog];
+  uint16_t base[1u << kSeqMaxLog];
+  uint32_t log;
+};
+struct SeqTables {
+  FseSeqTable ll, of, ml;
+};
+
+// decoding table from normalised counts (shared by the predefined and the transmitted distributions)
+SGIC_HD bool fse_build_seq_table(const int16_t* freq, uint32_t nsym, uint32_t log, FseSeqTable& t) {
+  const uint32_t size = 1u << log;
+  uint16_t next[kSeqMaxSym];
+  uint32_t high = size;
+  for (uint32_t i = 0; i < nsym; ++i)
+    if (freq[i] == -1) {
+      t.sym[--high] = static_cast<uint8_t>(i);
+      next[i] = 1;
+    }
+  const uint32_t step = (size >> 1) + (size >> 3) + 3u, mask = size - 1u;
+  uint32_t p = 0;
+  for (uint32_t i = 0; i < nsym; ++i) {
+    if (freq[i] <= 0) continue;
+    next[i] = static_cast<uint16_t>(freq[i]);
+    for (int32_t j = 0; j < freq[i]; ++j) {
+      t.sym[p] = static_cast<uint8_t>(i);
+      do {
+        p = (p + step) & mask;
+      } while (p >= high);
+    }
+  }
+  if (p != 0) return false;
+  for (uint32_t i = 0; i < size; ++i) {
+    const uint32_t sy = t.sym[i];
+    const uint32_t nx = next[sy]++;
+    const uint32_t nb = log - hsb(nx);
+    t.nbits[i] = static_cast<uint8_t>(nb);
+    t.base[i] = static_cast<uint16_t>((nx << nb) - size);
+  }
+  t.log = log;
+  return true;
+}
+
+// FSE table description at s[0..n) -> table; returns its size in bytes (0 on error)
+SGIC_HD uint32_t fse_read_seq_table(const uint8_t* s, uint32_t n, uint32_t max_log, uint32_t max_sym, FseSeqTable& t) {
+  uint32_t pos = 0;
+  const uint32_t log = 5u + bits_le(s, n, pos, 4);
+  pos += 4;
+  if (log > max_log) return 0;
+  int32_t remaining = 1 << log;
+  int16_t freq[kSeqMaxSym];
+  uint32_t nsym = 0;
+  while (remaining > 0 && nsym < max_sym) {
+    const uint32_t nb = hsb(static_cast<uint32_t>(remaining + 1)) + 1;
+    uint32_t val = bits_le(s, n, pos, nb);
+    pos += nb;
+    const uint32_t lower = (1u << (nb - 1)) - 1u;
+    const uint32_t thr = (1u << nb) - 1u - static_cast<uint32_t>(remaining + 1);
+    if ((val & lower) < thr) {
+      pos -= 1;
+      val &= lower;
+    } else if (val > lower) {
+      val -= thr;
+    }
+    const int32_t proba = static_cast<int32_t>(val) - 1;
+    remaining -= proba < 0 ? -proba : proba;
+    freq[nsym++] = static_cast<int16_t>(proba);
+    if (proba == 0) {
+      uint32_t rep = bits_le(s, n, pos, 2);
+      pos += 2;
+      for (;;) {
+        for (uint32_t i = 0; i < rep && nsym < max_sym; ++i) freq[nsym++] = 0;
+        if (rep != 3) break;
+        rep = bits_le(s, n, pos, 2);
+        pos += 2;
+      }
+    }
+    if (pos > 8u * n + 16u) return 0;
+  }
+  if (remaining != 0) return 0;
+  const uint32_t bytes = (pos + 7u) >> 3;
+  if (bytes > n) return 0;
+  if (!fse_build_seq_table(freq, nsym, log, t)) return 0;
+  return bytes;
+}
+
+SGIC_HD void fse_seq_rle(FseSeqTable& t, uint8_t symbol) {
+  t.sym[0] = symbol;
+  t.nbits[0] = 0;
+  t.base[0] = 0;
+  t.log = 0;
+}
+
+// predefined distributions (RFC 8878 3.1.1.3.2.2)
+SGIC_HD bool fse_seq_predefined(int which, FseSeqTable& t) {
+  if (which == 0) {  // literals lengths, accuracy 6
+    const int16_t f[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1,
+                           -1, -1, -1, -1};
+    return fse_build_seq_table(f, 36, 6, t);
+  }
+  if (which == 1) {  // offsets, accuracy 5
+    const int16_t f[29] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1};
+    return fse_build_seq_table(f, 29, 5, t);
+  }
+  const int16_t f[53] = {1, 4, 3, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                         1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1};
+  return fse_build_seq_table(f, 53, 6, t);  // match lengths, accuracy 6
+}
+
+SGIC_HD void ll_code_value(uint32_t code, uint32_t& base, uint32_t& bits) {
+  if (code < 16) {
+    base = code;
+    bits = 0;
+    return;
+  }
+  const uint16_t b[20] = {16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65535};
+  const uint8_t n[20] = {1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+  base = (code == 35) ? 65536u : b[code - 16];
+  bits = n[code - 16];
+}
+SGIC_HD void ml_code_value(uint32_t code, uint32_t& base, uint32_t& bits) {
+  if (code < 32) {
+    base = code + 3;
+    bits = 0;
+    return;
+  }
+  const uint16_t b[21] = {35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 3};
+  const uint8_t n[21] = {1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+  base = (code == 52) ? 65539u : b[code - 32];
+  bits = n[code - 32];
+}
+
+// Decodes and executes the sequences section s[0..n) (n >= 1, s[0] != 0): literals lit[0..n_lit) -> dst[0..out_size).
+// Returns ZL_OK, ZL_HOST (valid-looking but outside what is handled here) or ZL_CORRUPT.
+SGIC_HD int decode_sequences(const uint8_t* s, uint32_t n, const uint8_t* lit, uint32_t n_lit, uint8_t* dst,
+                             uint32_t out_size, SeqTables& T) {
+  uint32_t p = 0, nseq;
+  const uint32_t b0 = s[0];
+  if (b0 < 128) {
+    nseq = b0;
+    p = 1;
+  } else if (b0 < 255) {
+    if (n < 2) return ZL_CORRUPT;
+    nseq = ((b0 - 128u) << 8) + s[1];
+    p = 2;
+  } else {
+    if (n < 3) return ZL_CORRUPT;
+    nseq = s[1] + (static_cast<uint32_t>(s[2]) << 8) + 0x7F00u;
+    p = 3;
+  }
+  if (nseq == 0 || p >= n) return ZL_CORRUPT;
+  const uint32_t modes = s[p++];
+  if (modes & 3u) return ZL_CORRUPT;  // reserved bits
+  const uint32_t mode[3] = {(modes >> 6) & 3u, (modes >> 4) & 3u, (modes >> 2) & 3u};  // LL, OF, ML
+  FseSeqTable* tab[3] = {&T.ll, &T.of, &T.ml};
+  const uint32_t max_log[3] = {9, 8, 9}, max_sym[3] = {36, 32, 53};
+  for (int i = 0; i < 3; ++i) {
+    if (mode[i] == 0) {
+      if (!fse_seq_predefined(i, *tab[i])) return ZL_CORRUPT;
+    } else if (mode[i] == 1) {
+      if (p >= n) return ZL_CORRUPT;
+      if (s[p] >= max_sym[i]) return ZL_CORRUPT;
+      fse_seq_rle(*tab[i], s[p++]);
+    } else if (mode[i] == 2) {
+      const uint32_t used = fse_read_seq_table(s + p, n - p, max_log[i], max_sym[i], *tab[i]);
+      if (used == 0) return ZL_CORRUPT;
+      p += used;
+    } else {
+      return ZL_CORRUPT;  // Repeat_Mode needs a previous block
+    }
+  }
+  if (p >= n) return ZL_CORRUPT;
+  const uint8_t* bs = s + p;
+  const uint32_t bn = n - p;
+  if (bs[bn - 1] == 0) return ZL_CORRUPT;
+  int32_t off = static_cast<int32_t>(8u * bn) - static_cast<int32_t>(8u - hsb(bs[bn - 1]));
+  uint32_t st_ll = bits_back(bs, bn, off, T.ll.log);
+  uint32_t st_of = bits_back(bs, bn, off, T.of.log);
+  uint32_t st_ml = bits_back(bs, bn, off, T.ml.log);
+  if (off < 0) return ZL_CORRUPT;
+  uint32_t rep0 = 1, rep1 = 4, rep2 = 8;
+  uint32_t o = 0, li = 0;
+  for (uint32_t i = 0; i < nseq; ++i) {
+    const uint32_t of_code = T.of.sym[st_of], ll_code = T.ll.sym[st_ll], ml_code = T.ml.sym[st_ml];
+    if (of_code > 16) return ZL_HOST;  // offsets beyond 64 KB cannot occur in a payload of at most a few KB
+    const uint32_t of_val = (1u << of_code) + bits_back(bs, bn, off, of_code);
+    uint32_t mb, mn, lb, ln;
+    ml_code_value(ml_code, mb, mn);
+    const uint32_t ml = mb + bits_back(bs, bn, off, mn);
+    ll_code_value(ll_code, lb, ln);
+    const uint32_t ll = lb + bits_back(bs, bn, off, ln);
+    if (off < 0) return ZL_CORRUPT;
+    uint32_t offset;
+    if (of_val > 3) {
+      offset = of_val - 3;
+      rep2 = rep1;
+      rep1 = rep0;
+      rep0 = offset;
+    } else {
+      uint32_t idx = of_val - 1 + (ll == 0 ? 1u : 0u);  // 0..3
+      if (idx == 0) {
+        offset = rep0;
+      } else {
+        offset = (idx == 1) ? rep1 : (idx == 2) ? rep2 : rep0 - 1;
+        if (offset == 0) return ZL_CORRUPT;
+        if (idx != 1) rep2 = rep1;
+        rep1 = rep0;
+        rep0 = offset;
+      }
+    }
+    if (i + 1 < nseq) {
+      st_ll = T.ll.base[st_ll] + bits_back(bs, bn, off, T.ll.nbits[st_ll]);
+      st_ml = T.ml.base[st_ml] + bits_back(bs, bn, off, T.ml.nbits[st_ml]);
+      st_of = T.of.base[st_of] + bits_back(bs, bn, off, T.of.nbits[st_of]);
+      if (off < 0) return ZL_CORRUPT;
+    }
+    // execute
+    if (ll > n_lit - li || ll > out_size - o) return ZL_CORRUPT;
+    for (uint32_t j = 0; j < ll; ++j) dst[o + j] = lit[li + j];
+    o += ll;
+    li += ll;
+    if (offset > o || ml > out_size - o) return ZL_CORRUPT;
+    for (uint32_t j = 0; j < ml; ++j) dst[o + j] = dst[o + j - offset];  // overlapping copies are byte-serial
+    o += ml;
+  }
+  if (off != 0) return ZL_CORRUPT;  // the bitstream must be consumed exactly
+  const uint32_t rest = n_lit - li;
+  if (rest != out_size - o) return ZL_CORRUPT;
+  for (uint32_t j = 0; j < rest; ++j) dst[o + j] = lit[li + j];
+  return ZL_OK;
+}
+
 // Whole frame on one thread (the CPU twin used by the tests, and the shape of what the kernel does with a warp).
 // `tab` needs 2^11 entries.  Returns ZL_OK / ZL_HOST / ZL_CORRUPT; on ZL_OK dst[0..content_size) is the payload.
 SGIC_HD int decode_frame_serial(const uint8_t* s, uint32_t n, uint8_t* dst, uint32_t dst_cap, uint16_t* tab,
-                                uint32_t* out_size) {
+                                uint32_t* out_size, uint8_t* lit_buf, uint32_t lit_cap, SeqTables* seq) {
   FrameInfo f;
   const int rc = parse_frame(s, n, f);
   if (rc != ZL_OK) return rc;
   if (f.content_size > dst_cap) return ZL_HOST;
   *out_size = f.content_size;
-  if (f.block_type == 0 || (f.block_type == 2 && f.lit_type == 0)) {
-    const uint32_t o = (f.block_type == 0) ? f.block_off : f.lit_off;
-    for (uint32_t i = 0; i < f.content_size; ++i) dst[i] = s[o + i];
+  if (f.block_type == 0) {
+    for (uint32_t i = 0; i < f.content_size; ++i) dst[i] = s[f.block_off + i];
     return ZL_OK;
   }
-  if (f.block_type == 1 || f.lit_type == 1) {
-    const uint8_t b = s[(f.block_type == 1) ? f.block_off : f.lit_off];
-    for (uint32_t i = 0; i < f.content_size; ++i) dst[i] = b;
+  if (f.block_type == 1) {
+    for (uint32_t i = 0; i < f.content_size; ++i) dst[i] = s[f.block_off];
     return ZL_OK;
   }
-  uint8_t w[256], nb[256];
-  FseTable ft;
-  uint32_t nsym = 0, max_bits = 0;
-  const uint32_t td = huf_read_lengths(s + f.lit_off, f.comp, w, nb, nsym, max_bits, ft);
-  if (td == 0) return ZL_CORRUPT;
-  if (!huf_fill_table(nb, nsym, max_bits, tab, 0, 1)) return ZL_CORRUPT;
-  uint32_t soff[4], slen[4], scnt[4];
-  const uint8_t* ss = s + f.lit_off + td;
-  if (!huf_stream_layout(ss, f.comp - td, f.n_streams, f.regen, soff, slen, scnt)) return ZL_CORRUPT;
-  uint32_t o = 0;
-  for (uint32_t i = 0; i < f.n_streams; ++i) {
-    if (!huf_decode_stream(tab, max_bits, ss + soff[i], slen[i], dst + o, scnt[i])) return ZL_CORRUPT;
-    o += scnt[i];
+  const bool has_seq = s[f.seq_off] != 0;
+  if (has_seq && (seq == nullptr || f.regen > lit_cap)) return ZL_HOST;
+  uint8_t* lit = has_seq ? lit_buf : dst;  // without sequences the literals ARE the content
+  if (f.lit_type == 0) {
+    for (uint32_t i = 0; i < f.regen; ++i) lit[i] = s[f.lit_off + i];
+  } else if (f.lit_type == 1) {
+    for (uint32_t i = 0; i < f.regen; ++i) lit[i] = s[f.lit_off];
+  } else {
+    uint8_t w[256], nb[256];
+    FseTable ft;
+    uint32_t nsym = 0, max_bits = 0;
+    const uint32_t td = huf_read_lengths(s + f.lit_off, f.comp, w, nb, nsym, max_bits, ft);
+    if (td == 0) return ZL_CORRUPT;
+    if (!huf_fill_table(nb, nsym, max_bits, tab, 0, 1)) return ZL_CORRUPT;
+    uint32_t soff[4], slen[4], scnt[4];
+    const uint8_t* ss = s + f.lit_off + td;
+    if (!huf_stream_layout(ss, f.comp - td, f.n_streams, f.regen, soff, slen, scnt)) return ZL_CORRUPT;
+    uint32_t o = 0;
+    for (uint32_t i = 0; i < f.n_streams; ++i) {
+      if (!huf_decode_stream(tab, max_bits, ss + soff[i], slen[i], lit + o, scnt[i])) return ZL_CORRUPT;
+      o += scnt[i];
+    }
   }
-  return ZL_OK;
+  if (!has_seq) return ZL_OK;
+  return decode_sequences(s + f.seq_off, f.seq_size, lit, f.regen, dst, f.content_size, *seq);
 }
 
 }  // namespace zl

@@ -60,8 +60,9 @@ def test_reference_style_frames_decode_bit_exactly(zl):
                 assert got == want and len(got) == dim
                 n_ok += 1
         stats[dim] = n_ok / 300
-    # most level-19 frames of quantised unit vectors carry no sequences
-    assert stats[512] > 0.7 and stats[768] > 0.55 and stats[128] > 0.9, stats
+    # every frame zstd level 19 makes of a quantised unit vector is inside the profile, including the 16-31 %
+    # that carry match sequences
+    assert all(v == 1.0 for v in stats.values()), stats
 
 
 @pytest.mark.parametrize("level", [1, 3, 19])
@@ -74,7 +75,7 @@ def test_other_block_shapes(zl, level):
         if kind == 0:
             raw = rng.integers(0, 256, dim, dtype=np.uint8)                 # incompressible: raw block
         elif kind == 1:
-            raw = np.full(dim, rng.integers(0, 256), dtype=np.uint8)         # one value: literal + one match -> host
+            raw = np.full(dim, rng.integers(0, 256), dtype=np.uint8)         # one value: a literal + one long match
         elif kind == 2:
             raw = rng.choice(np.array([3, 7, 200, 201], np.uint8), dim, p=[.7, .15, .1, .05])  # tiny alphabet
         elif kind == 3:
@@ -87,7 +88,7 @@ def test_other_block_shapes(zl, level):
         if rc == OK:
             assert got == raw.tobytes()
             seen.add(kind)
-    assert {0, 2, 3, 4} <= seen, seen
+    assert seen == {0, 1, 2, 3, 4}, seen
 
 
 def test_corrupted_frames_never_decode_to_something_libzstd_rejects(zl):
@@ -151,3 +152,37 @@ def test_handmade_rle_and_raw_shapes_agree_with_libzstd(zl):
         want = zstd.decompress(fr)
         rc, got = decode(zl, fr)
         assert rc == OK and got == want, name
+
+
+def test_sequence_heavy_payloads(zl):
+    """Frames dominated by match sequences (periodic data, runs, text, planted repeats; predefined, RLE and
+    FSE-compressed sequence tables, repeat offsets, overlapping matches) regenerate exactly what libzstd does."""
+    rng = np.random.default_rng(13)
+    text = b"the quick brown fox jumps over the lazy dog " * 80
+    n_ok = 0
+    for trial in range(900):
+        n = int(rng.integers(8, 3000))
+        kind = trial % 6
+        if kind == 0:
+            raw = np.tile(rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8), n)[:n]
+        elif kind == 1:
+            raw = np.repeat(rng.integers(0, 256, n // 7 + 1, dtype=np.uint8), 7)[:n]
+        elif kind == 2:
+            raw = np.frombuffer(text[:n], dtype=np.uint8)
+        elif kind == 3:
+            raw = rng.integers(0, 256, n, dtype=np.uint8)
+            if n > 64:
+                raw[n // 2:n // 2 + 30] = raw[5:35]
+        elif kind == 4:
+            raw = np.clip(rng.normal(128, 10, n), 0, 255).astype(np.uint8)
+            raw[::3] = 128
+        else:
+            raw = np.full(n, rng.integers(0, 256), np.uint8)
+        for level in (1, 19):
+            frame = zstd.compress(raw.tobytes(), level)
+            rc, got = decode(zl, frame, cap=8192)
+            assert rc in (OK, HOST), (kind, level, n)
+            if rc == OK:
+                assert got == raw.tobytes(), (kind, level, n)
+                n_ok += 1
+    assert n_ok > 1700, n_ok

@@ -4,8 +4,10 @@
 #include "../searchable-generative-image-compression_b200/csrc/zstd_lit.cuh"
 
 extern "C" int zl_decode(const uint8_t* s, uint32_t n, uint8_t* dst, uint32_t cap, uint32_t* out_size) {
-  uint16_t tab[1u << sgic::zl::kHufMaxLog];
-  return sgic::zl::decode_frame_serial(s, n, dst, cap, tab, out_size);
+  static thread_local uint16_t tab[1u << sgic::zl::kHufMaxLog];
+  static thread_local uint8_t lit[4096];
+  static thread_local sgic::zl::SeqTables seq;
+  return sgic::zl::decode_frame_serial(s, n, dst, cap, tab, out_size, lit, sizeof(lit), &seq);
 }
 extern "C" int zl_classify(const uint8_t* s, uint32_t n) {
   sgic::zl::FrameInfo f;
