@@ -472,13 +472,13 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
       }
     }
     CUtensorMap tm_q;
-    // Small batches with thread-private-sized k: the transposed kernel (database rows on M, queries on N), as
-    // long as the resident query matrix + lists leave room for a ring of at least 3 database stages.
+    // Small batches: the transposed kernel (database rows on M, queries on N), as long as the resident query
+    // matrix + the (warp, query) lists leave room for a ring of at least 3 database stages.
     // "dense_mode" = 1 keeps the queries-on-M single-CTA kernel (A/B comparisons).
     const uint32_t kc_chunks = (static_cast<uint32_t>(h->d) + kDenseBK - 1) / kDenseBK;
     const uint32_t n_pad = (nqb + 15u) & ~15u;
     uint32_t t_stages = 0;
-    if (!pairs && tp && h->opt_dense_mode != 1) {
+    if (!pairs && h->opt_dense_mode != 1) {  // any k whose (warp, query) lists fit next to the ring
       const size_t fixed = dense_t_fixed_bytes(n_pad, kc_chunks, static_cast<uint32_t>(k)) + 1024 + 256;
       // measured at 100M x 512, nq = 8: 3-4 stages (96-128 KB in flight) 14.2 ms, 5 stages 15.2 ms, 6 stages 15.5 ms
       if (fixed < kSmemBudget) t_stages = static_cast<uint32_t>(std::min<size_t>((kSmemBudget - fixed) / kDtStageBytes, 4));
@@ -555,7 +555,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     if (h->opt_timing && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));
     rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nqb, grid_units, static_cast<uint32_t>(k),
                            dev_D + static_cast<size_t>(q0) * k, dev_I + static_cast<size_t>(q0) * k, id_base, st,
-                           /*sorted_lists=*/tp);
+                           /*sorted_lists=*/tp || transposed);
     if (rc) return rc;
   }
   if (h->opt_timing) {

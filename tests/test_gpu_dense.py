@@ -51,6 +51,8 @@ CASES = [
     (33000, 768, 33, 32),     # transposed: 48 query columns, largest thread-private k
     (33000, 1024, 64, 7),     # transposed: 64 columns, d = 1024
     (100, 64, 3, 10),         # fewer rows than one sub-tile
+    (33000, 512, 9, 100),     # transposed with k > 32: lists of 100 keys per (warp, query)
+    (33000, 512, 3, 1024),    # transposed at the largest k that fits (n_pad = 16)
 ]
 
 
