@@ -11,6 +11,8 @@ k = int(sys.argv[4]) if len(sys.argv) > 4 else 10
 idx = faiss.IndexFlatIP(d, device=0, retain_fp32=False); fill_index_random(idx, n)
 if len(sys.argv) > 5:
     idx.set_option("dense_l2_mb", int(sys.argv[5]))
+if len(sys.argv) > 6:
+    idx.set_option("dense_mode", int(sys.argv[6]))
 
 q = torch.from_numpy(random_unit_queries(nq, d)).cuda()
 for _ in range(3):

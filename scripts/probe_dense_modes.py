@@ -18,7 +18,7 @@ if len(sys.argv) > 8:
     min_nq = int(sys.argv[8])
 else:
     min_nq = None
-names = {0: "auto", 1: "1cta", 2: "pairs+stream", 3: "pairs"}
+names = {0: "auto", 1: "1cta", 2: "pairs+stream", 3: "pairs", 4: "pairs+dbres"}
 idx = faiss.IndexFlatIP(d, device=0, retain_fp32=False)
 fill_index_random(idx, n)
 if min_nq is not None:

@@ -302,8 +302,73 @@ struct DenseEpiRes {
     return kth;
   }
 
+  // Small reservoirs (C = 32 * KPL keys, KPL keys per lane): rank sort in registers.  Every lane counts the keys
+  // larger than its own (32 * KPL shuffles of 64 bits); a key of rank r < k goes to slot r, so the k survivors come
+  // out SORTED and the k-th key is the one of rank k-1.  The next reservoir's keys are fetched from L2 while this
+  // one is ranked (the startup of a scan compacts all 32 lanes' reservoirs back to back).
+  template <int KPL>
+  __device__ __forceinline__ void fetch_small(const uint64_t* R, uint32_t n, uint64_t (&key)[KPL]) {
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const uint32_t idx = j * 32 + lane;
+      key[j] = idx < n ? __ldcg(R + idx) : 0ull;  // 0 = empty: below every real key, never stored
+    }
+  }
+  template <int KPL>
+  __device__ __forceinline__ void compact_small(uint32_t need) {
+    __syncwarp();
+    int L = __ffs(need) - 1;
+    uint32_t n = __shfl_sync(0xffffffffu, cnt, L);
+    uint64_t key[KPL];
+    fetch_small<KPL>(res_warp + static_cast<size_t>(L) * C, n, key);
+    while (true) {
+      need &= need - 1;
+      int Ln = 0;
+      uint32_t nn = 0;
+      uint64_t nk[KPL];
+      if (need) {
+        Ln = __ffs(need) - 1;
+        nn = __shfl_sync(0xffffffffu, cnt, Ln);
+        fetch_small<KPL>(res_warp + static_cast<size_t>(Ln) * C, nn, nk);
+      }
+      uint32_t rank[KPL];
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) rank[j] = 0;
+#pragma unroll 4
+      for (int src = 0; src < 32; ++src) {
+#pragma unroll
+        for (int jj = 0; jj < KPL; ++jj) {
+          const uint64_t o = __shfl_sync(0xffffffffu, key[jj], src);
+#pragma unroll
+          for (int j = 0; j < KPL; ++j) rank[j] += o > key[j] ? 1u : 0u;
+        }
+      }
+      uint64_t* R = res_warp + static_cast<size_t>(L) * C;
+      uint64_t kth = 0ull;
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        const bool real = key[j] != 0ull;
+        if (real && rank[j] < k) __stcg(R + rank[j], key[j]);
+        const uint32_t m = __ballot_sync(0xffffffffu, real && rank[j] == k - 1);
+        if (m) kth = __shfl_sync(0xffffffffu, key[j], __ffs(m) - 1);
+      }
+      if (lane == L) {
+        cnt = n < k ? n : k;
+        if (kth != 0ull) thr = key_score(kth);
+      }
+      if (!need) break;
+      L = Ln;
+      n = nn;
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) key[j] = nk[j];
+    }
+    __syncwarp();
+  }
+
   // compact the reservoirs of the lanes named in `need` (warp-uniform mask)
   __device__ __forceinline__ void compact(uint32_t need) {
+    if (C == 32u) return compact_small<1>(need);
+    if (C == 64u) return compact_small<2>(need);
     __syncwarp();
     while (need) {
       const int L = __ffs(need) - 1;
@@ -1000,5 +1065,234 @@ scan_dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   ptx2::cluster_sync();  // the peer's smem / TMEM / barriers stay alive until both CTAs are done
   if (warp == 1) ptx2::tmem_dealloc2(tmem_base, 512);
 }
+
+// ================================================================================================ 2-CTA kernel, database tile resident
+// Large shards, several query tiles (nq > 256).  scan_dense2_kernel keeps a QUERY tile resident and streams a
+// database slice past it; the query tiles that share a slice are meant to meet in L2, but over the 10.5k tiles of
+// a 100M-row slice they drift apart and the database is read from DRAM ~10 times (988 GB for 102.4 GB, ncu).
+// Here the roles are swapped: the pair keeps one DATABASE tile (256 rows x d, half per CTA, d <= 512) resident
+// and streams every query tile of the block past it (the whole query block is a few MB and lives in L2).  The
+// database is read from DRAM exactly once per query block BY CONSTRUCTION — no lockstep, nothing to drift — and
+// L2 -> SM traffic per flop is what it was.  The TMEM layout does not change (lane = query, column = database row).
+//
+// Pipeline: the resident tile is a ring of 8 chunk slots (16 KB: this CTA's 128 rows x 64 elements); chunk c of
+// the pair's next tile replaces chunk c of the current one as soon as the LAST query tile's MMAs have read it
+// (b_free[slot], committed by the MMA thread), i.e. while the last query tile is still being multiplied: the
+// tensor pipe never drains between database tiles.  The query chunks stream through the 4-stage ring as before.
+//
+// Top-k: a thread now serves m_tiles queries in turn (one per query tile), so the per-query state cannot stay in
+// registers / shared-memory lists.  Every (CTA, query) pair owns a small RESERVOIR in global memory (C = 32 keys
+// for k <= 16, 64 for k <= 32, max(256, 2 next_pow2(k)) beyond): a survivor is appended with one fire-and-forget
+// st.global.cg; a full reservoir is compacted to its k best by the warp (rank sort in registers for C <= 64,
+// bisection over the key bits beyond) and the k-th score becomes the query's threshold.  Only the threshold and
+// the fill count live on chip: thr_s / cnt_s [m_tiles][128] in shared memory.  A stale threshold only admits
+// extra candidates; expected appends per (pair, query) ~ (C-k) log(n/C) / log(C/k) (about 200 for 1.35M rows at
+// k = 10) — a dozen compactions per reservoir for the whole scan.
+struct DenseBParams {
+  uint64_t* partial;   // [nq][n_lists][k] keys out (list u = CTA pair u)
+  uint64_t* lists_ws;  // [grid][m_tiles][128][res_cap] reservoirs
+  uint32_t n_rows, nq, k, res_cap;
+  uint32_t m_tiles;    // query tiles of 256
+  uint32_t n_tiles;    // database tiles of 256 rows; pair u owns tiles u, u + n_pairs, ...
+  uint32_t n_lists;
+  uint32_t kc, idesc, debug;
+};
+
+constexpr int kD2bSlots = 8;   // resident database chunk slots (d <= 512)
+constexpr int kD2bStages = 4;  // query chunk ring
+
+__host__ __device__ __forceinline__ size_t dense_b_smem_bytes(uint32_t m_tiles) {
+  return 1024 + static_cast<size_t>(kD2bSlots + kD2bStages) * (kDenseBM * kDenseBK * 2) +
+         static_cast<size_t>(m_tiles) * kDenseBM * 8 + 256;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1)
+scan_dense2b_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
+                    const DenseBParams p) {
+  constexpr int BN = 256, NS = kD2bStages, NB = kD2bSlots;
+  extern __shared__ uint8_t dense_smem_raw[];
+  uint8_t* smem = dense_smem_raw + ((1024u - (ptx::smem_u32(dense_smem_raw) & 1023u)) & 1023u);
+  uint8_t* b_res = smem;                                            // NB slots of 16 KB
+  uint8_t* stages = smem + static_cast<size_t>(NB) * kD2HalfBytes;  // NS stages of 16 KB
+  float* thr_s = reinterpret_cast<float*>(stages + static_cast<size_t>(NS) * kD2HalfBytes);  // [m_tiles][128]
+  uint32_t* cnt_s = reinterpret_cast<uint32_t*>(thr_s + static_cast<size_t>(p.m_tiles) * kDenseBM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cnt_s + static_cast<size_t>(p.m_tiles) * kDenseBM);
+  uint64_t* full = bars;                         // leader's copy is the live one
+  uint64_t* empty = bars + NS;                   // each CTA its own (multicast commit)
+  uint64_t* b_full = bars + 2 * NS;              // leader's copy
+  uint64_t* b_free = bars + 2 * NS + NB;         // each CTA its own (multicast commit)
+  uint64_t* acc_full = bars + 2 * NS + 2 * NB;   // each CTA its own (multicast commit)
+  uint64_t* acc_empty = acc_full + 2;            // leader's copy: 8 arrivals (4 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = ptx2::cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_q);
+    ptx::prefetch_tmap(&tm_db);
+    for (int s = 0; s < NS; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < NB; ++s) {
+      ptx::mbar_init(&b_full[s], 1);
+      ptx::mbar_init(&b_free[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&acc_full[a], 1);
+      ptx::mbar_init(&acc_empty[a], 8);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx2::tmem_alloc2(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx2::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t KC = p.kc, MT = p.m_tiles;
+  const uint32_t n_my = pair < p.n_tiles ? (p.n_tiles - pair + n_pairs - 1) / n_pairs : 0u;  // this pair's tiles
+
+  if (warp == 0) {
+    // ================================================================ TMA producer (both CTAs)
+    if (lane == 0) {
+      const uint64_t pol_q = ptx::policy_evict_last();    // the query block is re-read by every pair, every tile
+      const uint64_t pol_db = ptx::policy_evict_first();  // the database passes through once
+      const uint32_t total_b = n_my * KC;
+      uint32_t nb = 0;  // next database chunk (sequence number: tile index * KC + chunk) to request
+      auto issue_b = [&](uint32_t b) {
+        const uint32_t slot = b % NB, gen = b / NB;
+        if (gen > 0) ptx::mbar_wait(&b_free[slot], (gen - 1) & 1);
+        if (leader) ptx::mbar_expect_tx(&b_full[slot], 2 * kD2HalfBytes);
+        const uint32_t tile = pair + (b / KC) * n_pairs, c = b % KC;
+        ptx2::tma_load_2d_2sm(b_res + static_cast<size_t>(slot) * kD2HalfBytes, &tm_db,
+                              static_cast<int32_t>(c * kDenseBK), static_cast<int32_t>(tile * BN + rank * kDenseBM),
+                              &b_full[slot], pol_db);
+      };
+      while (nb < total_b && nb < static_cast<uint32_t>(NB)) issue_b(nb++);
+      uint32_t g = 0;  // step = (tile index, query tile, chunk)
+      for (uint32_t ti = 0; ti < n_my; ++ti) {
+        for (uint32_t mi = 0; mi < MT; ++mi) {
+          const uint32_t m = (mi + pair) % MT;  // pairs start at different query tiles: no L2 hot spot
+          const int32_t q_row = static_cast<int32_t>(m * 256 + rank * kDenseBM);
+          for (uint32_t kc = 0; kc < KC; ++kc, ++g) {
+            const uint32_t s = g % NS, u = g / NS;
+            if (u > 0) ptx::mbar_wait(&empty[s], (u - 1) & 1);  // the MMAs of step g - NS are done
+            if (leader) ptx::mbar_expect_tx(&full[s], 2 * kD2HalfBytes);
+            ptx2::tma_load_2d_2sm(stages + static_cast<size_t>(s) * kD2HalfBytes, &tm_q,
+                                  static_cast<int32_t>(kc * kDenseBK), q_row, &full[s], pol_q);
+            // database chunks whose slot saw its last use at a step <= g - NS can be replaced now
+            while (nb < total_b && g >= static_cast<uint32_t>(NS)) {
+              const uint32_t prev = nb - NB;
+              const uint32_t last_use = ((prev / KC) * MT + (MT - 1)) * KC + prev % KC;
+              if (last_use + NS > g) break;
+              issue_b(nb++);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      uint32_t g = 0, tc = 0;
+      for (uint32_t ti = 0; ti < n_my; ++ti) {
+        for (uint32_t mi = 0; mi < MT; ++mi, ++tc) {
+          const uint32_t as = tc & 1, ua = tc >> 1;
+          if (ua > 0) ptx::mbar_wait(&acc_empty[as], (ua - 1) & 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * BN;
+          for (uint32_t kc = 0; kc < KC; ++kc, ++g) {
+            const uint32_t s = g % NS;
+            const uint32_t b = ti * KC + kc, slot = b % NB;
+            ptx::mbar_wait(&b_full[slot], (b / NB) & 1);  // completes once per tile; later query tiles pass at once
+            ptx::mbar_wait(&full[s], (g / NS) & 1);
+            ptx::tc_fence_after();
+            const uint64_t a_desc = ptx::umma_desc_k_sw128(ptx::smem_u32(stages + static_cast<size_t>(s) * kD2HalfBytes));
+            const uint64_t b_desc = ptx::umma_desc_k_sw128(ptx::smem_u32(b_res + static_cast<size_t>(slot) * kD2HalfBytes));
+#pragma unroll
+            for (uint32_t kk = 0; kk < kDenseBK / 16; ++kk)
+              ptx2::tc_mma2_f16(d_tmem, a_desc + kk * 2, b_desc + kk * 2, p.idesc, (kc | kk) != 0 ? 1u : 0u);
+            ptx2::tc_commit2(&empty[s], 3);
+            if (mi + 1 == MT) ptx2::tc_commit2(&b_free[slot], 3);  // last query tile: the chunk slot may be refilled
+          }
+          ptx2::tc_commit2(&acc_full[as], 3);
+        }
+      }
+    }
+  } else {
+    // ================================================================ epilogue (both CTAs): fused top-k
+    const uint32_t acc_empty_leader0 = ptx2::mapa(ptx::smem_u32(&acc_empty[0]), 0);
+    const int row0w = (warp & 3) * 32;  // TMEM lane quadrant this warp may read = warp_id % 4
+    const int t = row0w + lane;
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(row0w) << 16);
+    for (uint32_t m = 0; m < MT; ++m) {  // a thread only ever touches its own entries: no barrier needed
+      thr_s[m * kDenseBM + t] = -INFINITY;
+      cnt_s[m * kDenseBM + t] = 0u;
+    }
+    DenseEpiRes epi;
+    epi.k = p.k;
+    epi.C = p.res_cap;
+    epi.lane = lane;
+    uint64_t* res_cta = p.lists_ws + static_cast<size_t>(blockIdx.x) * MT * kDenseBM * p.res_cap;
+    uint32_t tc = 0;
+    for (uint32_t ti = 0; ti < n_my; ++ti) {
+      const uint32_t row0 = (pair + ti * n_pairs) * BN;
+      const uint32_t n_valid = min(static_cast<uint32_t>(BN), p.n_rows - row0);
+      for (uint32_t mi = 0; mi < MT; ++mi, ++tc) {
+        const uint32_t m = (mi + pair) % MT;
+        const uint32_t q0 = m * 256 + rank * kDenseBM;
+        const bool q_valid = q0 + t < p.nq;
+        const bool warp_valid = q0 + row0w < p.nq;
+        const uint32_t as = tc & 1;
+        ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
+        ptx::tc_fence_after();
+        if (warp_valid && !(p.debug & 4u)) {
+          epi.res_warp = res_cta + (static_cast<size_t>(m) * kDenseBM + row0w) * p.res_cap;
+          epi.thr = thr_s[m * kDenseBM + t];
+          epi.cnt = cnt_s[m * kDenseBM + t];
+          epi.template scan_tile<BN>(tq + as * BN, row0, n_valid, q_valid);
+          thr_s[m * kDenseBM + t] = epi.thr;
+          cnt_s[m * kDenseBM + t] = epi.cnt;
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx2::mbar_arrive_cluster(acc_empty_leader0 + as * 8);
+      }
+    }
+    // every reservoir down to its k best -> this pair's list of the query.  Small reservoirs come out of the rank
+    // sort in order (so even a reservoir that never filled is passed through it); large ones stay unsorted.
+    const bool small = p.res_cap <= 64u;
+    for (uint32_t m = 0; m < MT; ++m) {
+      const uint32_t q0w = m * 256 + rank * kDenseBM + row0w;
+      if (q0w >= p.nq) continue;
+      epi.res_warp = res_cta + (static_cast<size_t>(m) * kDenseBM + row0w) * p.res_cap;
+      epi.thr = thr_s[m * kDenseBM + t];
+      epi.cnt = cnt_s[m * kDenseBM + t];
+      const uint32_t need = __ballot_sync(0xffffffffu, small ? epi.cnt > 0u : epi.cnt > p.k);
+      if (need) epi.compact(need);
+      __syncwarp();
+      for (int L = 0; L < 32; ++L) {
+        const uint32_t q = q0w + L;
+        if (q >= p.nq) break;
+        const uint32_t n = __shfl_sync(0xffffffffu, epi.cnt, L);
+        const uint64_t* R = epi.res_warp + static_cast<size_t>(L) * p.res_cap;
+        uint64_t* dst = p.partial + (static_cast<size_t>(q) * p.n_lists + pair) * p.k;
+        for (uint32_t i = lane; i < p.k; i += 32) __stcg(dst + i, i < n ? __ldcg(R + i) : 0ull);
+      }
+      __syncwarp();
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx2::cluster_sync();
+  if (warp == 1) ptx2::tmem_dealloc2(tmem_base, 512);
+}
+
 
 }  // namespace sgic

@@ -118,7 +118,7 @@ struct sgic_index {
   int64_t shard_row_start = 0, shard_total_rows = -1;
   int shard_id = 0, shard_count = 1;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000;
   int64_t stat_ingest_h2d_ns = 0, stat_ingest_k0_ns = 0, stat_ingest_k1_ns = 0;
   int64_t stat_ingest_parse_ns = 0, stat_ingest_pack_ns = 0, stat_ingest_gpu_ns = 0;
   int64_t stat_zl_device_frames = 0, stat_zl_host_rows = 0, stat_zl_fallback_slabs = 0;
@@ -469,6 +469,67 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
         SGIC_CUDA(cudaStreamSynchronize(st));
         rc = ensure_buf(&h->lists_ws, &h->lists_ws_bytes, need, false);
         if (rc) return rc;
+      }
+    }
+    // Several query tiles over a large shard: the pair kernel that keeps a DATABASE tile resident and streams the
+    // query block past it — the database leaves DRAM exactly once per block (scan_dense.cuh).  Below
+    // "dense_b_min_mb" MB of database the query-resident kernel's slices still meet in L2 and its in-register /
+    // shared-memory lists are cheaper than reservoirs.  "dense_mode" = 4 forces it wherever it is eligible.
+    {
+      const uint32_t cap_b = k <= 16 ? 32u : k <= 32 ? 64u : res_cap;
+      const uint32_t units_b = std::min<uint32_t>(n_units, n_tiles);
+      const size_t ws_b = static_cast<size_t>(units_b) * 2 * m_tiles * kDenseBM * cap_b * 8;
+      const size_t db_mb = (static_cast<size_t>(n_rows) * h->d * 2) >> 20;
+      const bool eligible = pairs && h->d <= kD2MaxKc * kDenseBK && m_tiles >= 2 &&
+                            dense_b_smem_bytes(m_tiles) <= kSmemBudget && ws_b <= (size_t(1) << 30);
+      if (eligible && (h->opt_dense_mode == 4 ||
+                       (h->opt_dense_mode == 0 && db_mb >= static_cast<size_t>(h->opt_dense_b_min_mb)))) {
+        const size_t pbytes = static_cast<size_t>(nqb) * units_b * static_cast<size_t>(k) * 8;
+        if (pbytes + 16 > h->ws_bytes) {
+          SGIC_CUDA(cudaStreamSynchronize(st));
+          rc = ensure_buf(&h->ws, &h->ws_bytes, pbytes + 16, false);
+          if (rc) return rc;
+        }
+        if (ws_b > h->lists_ws_bytes) {
+          SGIC_CUDA(cudaStreamSynchronize(st));
+          rc = ensure_buf(&h->lists_ws, &h->lists_ws_bytes, ws_b, false);
+          if (rc) return rc;
+        }
+        h->ws_counter = nullptr;  // the workspace is overwritten: K3 must re-zero its counter
+        CUtensorMap tm_qb;
+        rc = make_tmap_rows(&tm_qb, static_cast<const uint8_t*>(h->qh) + static_cast<size_t>(q0) * h->d * 2, nqb,
+                            static_cast<uint32_t>(h->d), static_cast<uint32_t>(kDenseBM), h->dtype);
+        if (rc) return rc;
+        DenseBParams bp;
+        bp.partial = static_cast<uint64_t*>(h->ws);
+        bp.lists_ws = static_cast<uint64_t*>(h->lists_ws);
+        bp.n_rows = n_rows;
+        bp.nq = nqb;
+        bp.k = static_cast<uint32_t>(k);
+        bp.res_cap = cap_b;
+        bp.m_tiles = m_tiles;
+        bp.n_tiles = n_tiles;
+        bp.n_lists = units_b;
+        bp.kc = (static_cast<uint32_t>(h->d) + kDenseBK - 1) / kDenseBK;
+        bp.idesc = ptx::umma_idesc_f16(256, kDenseBN, h->dtype == SGIC_BF16 ? 1u : 0u);
+        bp.debug = static_cast<uint32_t>(h->opt_debug);
+        static bool b_configured[64] = {false};
+        if (!b_configured[h->device & 63]) {
+          SGIC_CUDA(cudaFuncSetAttribute(scan_dense2b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kSmemBudget)));
+          b_configured[h->device & 63] = true;
+        }
+        scan_dense2b_kernel<<<units_b * 2, kDenseThreads, dense_b_smem_bytes(m_tiles), st>>>(tm_qb, tm_db, bp);
+        h->stat_launches++;
+        SGIC_CUDA(cudaGetLastError());
+        h->stat_last_grid = units_b * 2;
+        h->stat_last_stages = kD2bStages;
+        if (h->opt_timing && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));
+        rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nqb, units_b, static_cast<uint32_t>(k),
+                               dev_D + static_cast<size_t>(q0) * k, dev_I + static_cast<size_t>(q0) * k, id_base, st,
+                               /*sorted_lists=*/cap_b <= 64u);
+        if (rc) return rc;
+        continue;
       }
     }
     CUtensorMap tm_q;
@@ -1495,6 +1556,7 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "dense_mode") h->opt_dense_mode = value;
   else if (n == "device_zstd") h->opt_device_zstd = value;
   else if (n == "dense_l2_mb") h->opt_dense_l2_mb = std::max<int64_t>(0, value);
+  else if (n == "dense_b_min_mb") h->opt_dense_b_min_mb = std::max<int64_t>(0, value);
   else if (n == "drop_retained") {
     std::lock_guard<std::mutex> lk(h->mu);
     h->retain_ok = false;

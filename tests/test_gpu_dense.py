@@ -29,7 +29,7 @@ def make_index(xb, dtype="fp16", **kw):
 
 # dense_mode: 0 = automatic (up to 128 queries: the transposed kernel when k <= 32 and shared memory allows, else
 # the queries-on-M single-CTA kernel; CTA pairs beyond), 1 = queries-on-M single-CTA kernel, 2 = pairs with the
-# query tile streamed, 3 = pairs forced
+# query tile streamed, 3 = pairs forced (query tile resident), 4 = pairs with the database tile resident (below)
 CASES = [
     (256, 64, 5, 4),          # smallest: one tile, d = one K chunk
     (1000, 512, 8, 10),
@@ -70,6 +70,61 @@ def test_dense_matches_oracle(n, d, nq, k, mode):
     check_topk(D[sel], I[sel], f16(xb), f16(xq[sel]), k, score_tol=3e-5, tie_tol=1e-6)
     check_topk(D[sel], I[sel], xb, xq[sel], k, score_tol=1e-3)
     idx.close()
+
+
+# dense_mode 4: the pair kernel that keeps a DATABASE tile resident and streams the query block past it
+# (scan_dense2b_kernel; picked automatically for several query tiles over a large shard).  Needs > 256 queries
+# and d <= 512; per-(CTA, query) reservoirs of 32 keys (k <= 16), 64 keys (k <= 32) or 2*next_pow2(k) beyond.
+CASES_B = [
+    (70000, 512, 300, 10),
+    (100000, 128, 4096, 5),    # a full query block (16 query tiles), two K chunks
+    (40000, 512, 600, 32),     # largest k with 64-key reservoirs
+    (40000, 512, 257, 16),     # largest k with 32-key reservoirs; one query in the second tile
+    (40000, 320, 513, 17),     # five K chunks: the resident ring rotates through its eight slots
+    (3001, 512, 300, 10),      # fewer database tiles than CTA pairs, ragged last tile
+    (300, 512, 300, 100),      # k close to n: large reservoirs that never fill
+    (30000, 256, 1000, 100),   # four K chunks (two tiles resident at once), bisection compaction
+    (50, 512, 300, 64),        # k > n: -1 / -FLT_MAX padding
+    (150000, 448, 1025, 1),    # seven K chunks, k = 1, five query tiles
+    (20000, 512, 300, 1024),   # k at the supported maximum
+    (200000, 512, 2048, 10),   # every pair owns several tiles: the slots are refilled under the last query tile
+]
+
+
+@pytest.mark.parametrize("n,d,nq,k", CASES_B)
+def test_dense_database_resident_matches_oracle(n, d, nq, k):
+    rng = np.random.default_rng(n + d + nq + k + 4)
+    xb, xq = unit(rng, n, d), unit(rng, nq, d)
+    idx = make_index(xb)
+    idx.set_option("dense_mode", 4)
+    D, I = idx.search(xq, k)
+    assert D.shape == (nq, k) and I.shape == (nq, k)
+    # first / last queries of every CTA's 128-query half and a random sample
+    edge = [q for q in (0, 127, 128, 255, 256, 383, 384, nq - 1) if q < nq]
+    sel = np.unique(np.concatenate([edge, rng.choice(nq, 40, replace=False)])).astype(np.int64)
+    check_topk(D[sel], I[sel], f16(xb), f16(xq[sel]), k, score_tol=3e-5, tie_tol=1e-6)
+    check_topk(D[sel], I[sel], xb, xq[sel], k, score_tol=1e-3)
+    # size-independent property: the query-resident pair kernel must give the same answer
+    idx.set_option("dense_mode", 3)
+    D3, I3 = idx.search(xq, k)
+    np.testing.assert_allclose(D, D3, atol=2e-5, rtol=0)
+    assert (I == I3).mean() > 0.999
+    idx.close()
+
+
+def test_dense_database_resident_duplicates_and_bf16():
+    rng = np.random.default_rng(43)
+    base = unit(rng, 9000, 512)
+    xb = np.concatenate([base, base, base])
+    xq = base[:400].copy()
+    for dtype in ("fp16", "bf16"):
+        idx = make_index(xb, dtype)
+        idx.set_option("dense_mode", 4)
+        D, I = idx.search(xq, 6)
+        for r in range(400):
+            assert list(I[r, :3]) == [r, r + 9000, r + 18000]
+            assert D[r, 0] == D[r, 1] == D[r, 2]
+        idx.close()
 
 
 def test_dense_bf16():
