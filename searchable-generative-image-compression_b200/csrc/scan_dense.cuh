@@ -49,7 +49,9 @@ struct DenseParams {
   uint32_t n_rows, nq, k, res_cap;
   uint32_t m_tiles;        // query tiles: of 128 (1-CTA kernel) or 256 (2-CTA kernel)
   uint32_t n_slices, tiles_per_slice, n_tiles;
-  uint32_t n_lists;        // = number of CTAs (CTA pairs) launched
+  uint32_t n_lists;        // lists per query in `partial`: the slices (by_slice) or the CTAs (CTA pairs) launched
+  uint32_t by_slice;       // 1: every (query tile, slice) item is visited once and writes list `slice` (nothing to
+                           //    resume, no zeroing needed); 0: a CTA parks / resumes its lists in its own slot
   uint32_t kc;             // K chunks of 64 elements (ceil(d/64); TMA zero-fills the tail)
   uint32_t tp;             // k <= 32: thread-private lists [k][128] in shared memory; else reservoirs
   uint32_t a_rows;         // rows of the query box (1-CTA kernel; < 128 for small batches)
@@ -84,6 +86,14 @@ __device__ __forceinline__ float select32(const float (&v)[32], uint32_t j) {
   for (int i = 0; i < 4; ++i) c[i] = (j & 4u) ? b[2 * i + 1] : b[2 * i];
   const float d0 = (j & 8u) ? c[1] : c[0], d1 = (j & 8u) ? c[3] : c[2];
   return (j & 16u) ? d1 : d0;
+}
+
+// one of eight registers for a run-time j in [0,8): 4+2+1 SEL
+__device__ __forceinline__ float select8(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7,
+                                         uint32_t j) {
+  const float b0 = (j & 1u) ? a1 : a0, b1 = (j & 1u) ? a3 : a2, b2 = (j & 1u) ? a5 : a4, b3 = (j & 1u) ? a7 : a6;
+  const float c0 = (j & 2u) ? b1 : b0, c1 = (j & 2u) ? b3 : b2;
+  return (j & 4u) ? c1 : c0;
 }
 
 // k <= 32: thread t keeps the sorted list of ITS query at lst[rank * 128] (shared memory; the rank stride of
@@ -400,22 +410,31 @@ struct DenseEpiRes {
       const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       const bool hit = q_valid && m > thr;
       if (__any_sync(0xffffffffu, hit)) {
+        // Large k keeps this path busy (k = 100: ~1000 appends per list), so it is cut to the bone: the four
+        // group maxima are already there — one vote per group of 8 columns, a survivor mask only for a group
+        // that has one, and the score comes out of 8 registers (7 SEL) because the group is a compile-time index.
         const uint32_t col0 = c * 32;
-        uint32_t mask = 0;
+        const uint32_t lim = n_valid - col0;  // valid columns in this chunk (>= 1)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mask |= (v[j] > thr) ? (1u << j) : 0u;
-        if (!q_valid) mask = 0;
-        if (n_valid - col0 < 32u) mask &= (1u << (n_valid - col0)) - 1u;
-        // warp-uniform loop: every lane appends its next survivor, full reservoirs are compacted at once
-        while (__any_sync(0xffffffffu, mask != 0u)) {
-          if (mask) {
-            const uint32_t j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float sc = select32(v, j);
-            if (sc > thr) append(make_key(sc, row0 + col0 + j));
+        for (int g = 0; g < 4; ++g) {
+          if (!__any_sync(0xffffffffu, q_valid && m4[g] > thr)) continue;
+          uint32_t mask = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mask |= (v[8 * g + j] > thr) ? (1u << j) : 0u;
+          if (!q_valid) mask = 0;
+          if (lim < 8u * g + 8u) mask &= (lim > 8u * g) ? ((1u << (lim - 8u * g)) - 1u) : 0u;
+          // warp-uniform loop: every lane appends its next survivor, full reservoirs are compacted at once
+          while (__any_sync(0xffffffffu, mask != 0u)) {
+            if (mask) {
+              const uint32_t j = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const float sc = select8(v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3], v[8 * g + 4], v[8 * g + 5],
+                                       v[8 * g + 6], v[8 * g + 7], j);
+              if (sc > thr) append(make_key(sc, row0 + col0 + 8u * g + j));
+            }
+            const uint32_t full = __ballot_sync(0xffffffffu, cnt == C);
+            if (full) compact(full);
           }
-          const uint32_t full = __ballot_sync(0xffffffffu, cnt == C);
-          if (full) compact(full);
         }
       }
       __syncwarp();
@@ -495,7 +514,9 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
       const uint32_t q0 = m_tile * q_tile + q_off;
       const bool q_valid = q0 + t < p.nq;
       const bool warp_valid = q0 + row0w < p.nq;
-      epi.load(p.partial, q0 + t, p.nq, p.n_lists, unit);
+      const uint32_t slot = p.by_slice ? slice : unit;
+      if (p.by_slice) epi.reset();
+      else epi.load(p.partial, q0 + t, p.nq, p.n_lists, slot);
       for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
         const uint32_t as = tc & 1;
         ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
@@ -507,7 +528,7 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
         __syncwarp();
         if (lane == 0) arrive(as);
       }
-      epi.store(p.partial, q0 + t, p.nq, p.n_lists, unit);
+      epi.store(p.partial, q0 + t, p.nq, p.n_lists, slot);
     }
   } else {
     DenseEpiRes epi;
@@ -521,7 +542,8 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
       const uint32_t q0 = m_tile * q_tile + q_off;
       const bool q_valid = q0 + t < p.nq;
       const bool warp_valid = q0 + row0w < p.nq;
-      if (warp_valid) epi.load(p.partial, q0 + row0w, p.nq, p.n_lists, unit);
+      const uint32_t slot = p.by_slice ? slice : unit;
+      if (warp_valid && !p.by_slice) epi.load(p.partial, q0 + row0w, p.nq, p.n_lists, slot);
       else epi.reset();
       for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
         const uint32_t as = tc & 1;
@@ -534,7 +556,7 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
         __syncwarp();
         if (lane == 0) arrive(as);
       }
-      if (warp_valid) epi.store(p.partial, q0 + row0w, p.nq, p.n_lists, unit);
+      if (warp_valid) epi.store(p.partial, q0 + row0w, p.nq, p.n_lists, slot);
     }
   }
 }
@@ -826,20 +848,47 @@ scan_dense_t_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
               for (int j = 0; j < 16; ++j) hit |= v[j] > t[j];
               if (__any_sync(0xffffffffu, hit && rvalid)) {
+                // which of the chunk's 16 queries have a survivor in some lane
+                uint32_t qm = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) qm |= (rvalid && v[j] > t[j]) ? (1u << j) : 0u;
+                qm = __reduce_or_sync(0xffffffffu, qm);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
+                  if (!((qm >> j) & 1u)) continue;  // warp-uniform
+                  const uint32_t q = c + j;
+                  uint64_t* Lq = lists + (static_cast<size_t>(q) * 4 + w) * k;
                   uint32_t b = __ballot_sync(0xffffffffu, rvalid && v[j] > t[j]);
-                  while (b) {
-                    const int L = __ffs(b) - 1;
-                    b &= b - 1;
-                    const float sc = __shfl_sync(0xffffffffu, v[j], L);
-                    const uint32_t q = c + j;
-                    if (sc > thr_w[q]) {  // the threshold may have moved since the chunk's copy was read
-                      const uint64_t kth =
-                          warp_list_insert(lists + (static_cast<size_t>(q) * 4 + w) * k, static_cast<int>(k),
-                                           make_key(sc, row0w + L), lane);
-                      if (lane == 0) thr_w[q] = (kth == 0ull) ? -INFINITY : key_score(kth);
-                      __syncwarp();
+                  if (k <= 32u) {
+                    // the (warp, query) list lives in the lanes while this query's survivors are inserted: lane i
+                    // holds rank i; an insert is one ballot (position) and one shuffle-up (shift), no shared memory
+                    uint64_t Li = static_cast<uint32_t>(lane) < k ? Lq[lane] : 0ull;
+                    while (b) {
+                      const int L = __ffs(b) - 1;
+                      b &= b - 1;
+                      const float sc = __shfl_sync(0xffffffffu, v[j], L);
+                      const uint64_t key = make_key(sc, row0w + L);
+                      const uint32_t pos = __popc(__ballot_sync(0xffffffffu, Li > key));
+                      if (pos < k) {
+                        const uint64_t up = __shfl_up_sync(0xffffffffu, Li, 1);
+                        Li = static_cast<uint32_t>(lane) < pos ? Li : (static_cast<uint32_t>(lane) == pos ? key : up);
+                        if (static_cast<uint32_t>(lane) >= k) Li = 0ull;
+                      }
+                    }
+                    if (static_cast<uint32_t>(lane) < k) Lq[lane] = Li;
+                    const uint64_t kth = __shfl_sync(0xffffffffu, Li, static_cast<int>(k) - 1);
+                    if (lane == 0) thr_w[q] = (kth == 0ull) ? -INFINITY : key_score(kth);
+                    __syncwarp();
+                  } else {
+                    while (b) {
+                      const int L = __ffs(b) - 1;
+                      b &= b - 1;
+                      const float sc = __shfl_sync(0xffffffffu, v[j], L);
+                      if (sc > thr_w[q]) {  // the threshold may have moved since the chunk's copy was read
+                        const uint64_t kth = warp_list_insert(Lq, static_cast<int>(k), make_key(sc, row0w + L), lane);
+                        if (lane == 0) thr_w[q] = (kth == 0ull) ? -INFINITY : key_score(kth);
+                        __syncwarp();
+                      }
                     }
                   }
                 }
