@@ -308,6 +308,10 @@ def run_ours(args):
         local.set_option("timing", 0)
         scan_ms = statistics.mean(scan_ns) / 1e6
         dense = nq >= local.stat("dense_min_nq")
+        kernel = {0: "scan_small_kernel", 1: "scan_dense_kernel", 2: "scan_dense_t_kernel", 3: "scan_dense2_kernel",
+                  4: "scan_dense2_kernel", 5: "scan_dense2b_kernel"}[local.stat("last_kernel")]
+        traffic_file = ROOT / "profiles" / "traffic.json"
+        tj = json.loads(traffic_file.read_text()) if traffic_file.exists() else {}
         if dense and nq > 128:
             # tensor-core regime: 2*nq*N_local*d flop per launch (top-k work is not counted)
             flops = 2.0 * nq * n_local * d
@@ -315,21 +319,24 @@ def run_ours(args):
             roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"],
                         "peak_kind": "cuBLAS bf16 sustained (kernel timed inside a long step)",
-                        "kernel": "scan_dense2_kernel", "algorithmic_flops_per_launch": flops, "kernel_ms": scan_ms,
+                        "kernel": kernel, "algorithmic_flops_per_launch": flops, "kernel_ms": scan_ms,
                         "frac_of_burst": achieved / pk["bf16_tflops"], "frac_of_nominal_2250": achieved / 2250.0}
+            # DRAM bytes per launch from the committed ncu capture: the database-resident pair kernel reads every
+            # row once per block of <= 4096 queries by construction
+            if kernel == "scan_dense2b_kernel" and d == 512 and "dense2b_dram_bytes_per_row_d512" in tj:
+                roofline["traffic"] = tj["dense2b_dram_bytes_per_row_d512"] * n_local * ((nq + 4095) // 4096)
         else:
             alg_bytes = n_local * d * 2
             achieved = alg_bytes / (scan_ms / 1e3) / 1e9
             roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                        "kernel": "scan_dense_t_kernel" if dense else "scan_small_kernel",
+                        "kernel": kernel,
                         "algorithmic_bytes_per_launch": alg_bytes,
                         "kernel_ms": scan_ms, "frac_of_nominal_8TBs": achieved / 8000.0}
-            traffic_file = ROOT / "profiles" / "traffic.json"
-            if traffic_file.exists() and not dense:   # dram bytes per row from the committed ncu capture
-                tj = json.loads(traffic_file.read_text())
-                if "dram_bytes_per_row_d512" in tj and d == 512:
-                    roofline["traffic"] = tj["dram_bytes_per_row_d512"] * n_local
+            if not dense and "dram_bytes_per_row_d512" in tj and d == 512:   # from the committed ncu capture
+                roofline["traffic"] = tj["dram_bytes_per_row_d512"] * n_local
+            elif kernel == "scan_dense_t_kernel" and "dense_t_dram_bytes_per_row_d512" in tj and d == 512:
+                roofline["traffic"] = tj["dense_t_dram_bytes_per_row_d512"] * n_local
         return {"batch": nq, "value": value, "ms_per_step": ms_total / steps, "steps": steps, "warmup": warmup,
                 "gpu_launches": int(launches),
                 "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(nq * d * 4),

@@ -26,7 +26,11 @@ if min_nq is not None:
 if len(sys.argv) > 9:
     idx.set_option("stages", int(sys.argv[9]))
 
-print(f"n={n} d={d} k={k} dense_min_nq={min_nq}", flush=True)
+import os
+for kv in filter(None, os.environ.get("SGIC_PROBE_OPTS", "").split(",")):   # e.g. SGIC_PROBE_OPTS=dense_gthr=0
+    name, val = kv.split("=")
+    idx.set_option(name, int(val))
+print(f"n={n} d={d} k={k} dense_min_nq={min_nq} opts={os.environ.get('SGIC_PROBE_OPTS', '')}", flush=True)
 for nq in nqs:
     q = torch.from_numpy(random_unit_queries(nq, d)).cuda()
     D = torch.empty((nq, k), device="cuda")

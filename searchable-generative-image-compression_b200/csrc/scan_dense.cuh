@@ -46,6 +46,11 @@ constexpr int kDenseBK = 64;        // K chunk: 64 x 16-bit = one 128-byte swizz
 struct DenseParams {
   uint64_t* partial;   // [nq][n_lists][k] keys: list `u` of a query belongs to CTA (pair) u, zeroed before the launch
   uint64_t* lists_ws;  // k > 32: [grid][128][res_cap] reservoirs (L2-resident workspace)
+  uint32_t* gthr;      // [nq] by_slice only, zeroed before the launch: per query, the largest "k rows score above
+                       // this" bound any finished item has published (order-preserving uint of the score just
+                       // below its k-th).  A later item of the same query starts from it instead of -inf — pure
+                       // pruning: every published bound is valid, so whichever a racing reader sees, the merged
+                       // answer is the same.
   uint32_t n_rows, nq, k, res_cap;
   uint32_t m_tiles;        // query tiles: of 128 (1-CTA kernel) or 256 (2-CTA kernel)
   uint32_t n_slices, tiles_per_slice, n_tiles;
@@ -103,10 +108,12 @@ struct DenseEpiTP {
   uint64_t* lst;
   uint32_t k;
   float thr;
+  float thr0;  // bound inherited from finished items of the same query (gthr); -inf if none
 
-  __device__ __forceinline__ void reset() {
+  __device__ __forceinline__ void reset(float inherited = -INFINITY) {
     for (uint32_t i = 0; i < k; ++i) lst[i * kDenseBM] = 0ull;
-    thr = -INFINITY;
+    thr0 = inherited;
+    thr = inherited;
   }
   // requires key > current k-th key (the caller compared the score with thr).  Shift loop from the tail,
   // four predecessors loaded per round trip to shared memory (the loop is a latency chain: one warp per
@@ -135,7 +142,7 @@ struct DenseEpiTP {
       --i;
     }
     lst[i * kDenseBM] = key;
-    thr = (kth == 0ull) ? -INFINITY : key_score(kth);
+    thr = (kth == 0ull) ? thr0 : key_score(kth);  // every key in the list is above thr0
   }
 
   template <int BN>
@@ -190,6 +197,7 @@ struct DenseEpiTP {
       kth = __ldcg(src + i);
       lst[i * kDenseBM] = kth;
     }
+    thr0 = -INFINITY;
     thr = (kth == 0ull) ? -INFINITY : key_score(kth);
   }
   __device__ __forceinline__ void store(uint64_t* partial, uint32_t q, uint32_t nq, uint32_t n_lists, uint32_t slot) {
@@ -212,6 +220,16 @@ struct DenseEpiRes {
   int lane;
   uint32_t cnt;
   float thr;
+  uint32_t* gthr_q = nullptr;  // this lane's query in DenseParams::gthr (nullptr: no sharing)
+
+  // after a compaction: publish the score just below the new k-th and pick up a better bound if another list of
+  // the same query (a concurrent slice, or an item of the previous round) has one
+  __device__ __forceinline__ void exchange_bound() {
+    if (gthr_q == nullptr || !(thr > -INFINITY)) return;
+    const uint32_t mine = score_to_ord(thr) - 1u;
+    const uint32_t old = atomicMax(gthr_q, mine);
+    if (old > mine) thr = ord_to_score(old);
+  }
 
   __device__ __forceinline__ void reset() {
     cnt = 0;
@@ -364,7 +382,10 @@ struct DenseEpiRes {
       }
       if (lane == L) {
         cnt = n < k ? n : k;
-        if (kth != 0ull) thr = key_score(kth);
+        if (kth != 0ull) {
+          thr = key_score(kth);
+          exchange_bound();
+        }
       }
       if (!need) break;
       L = Ln;
@@ -389,6 +410,7 @@ struct DenseEpiRes {
       if (lane == L) {
         cnt = k;
         thr = key_score(kth);
+        exchange_bound();
       }
     }
   }
@@ -493,6 +515,17 @@ struct DenseEpiRes {
   }
 };
 
+// gthr protocol (see DenseParams): read the bound a query inherited / publish the score just below a list's k-th
+__device__ __forceinline__ float gthr_read(const uint32_t* gthr, uint32_t q) {
+  const uint32_t g = __ldcg(gthr + q);
+  return g ? ord_to_score(g) : -INFINITY;
+}
+__device__ __forceinline__ void gthr_publish(uint32_t* gthr, uint32_t q, float thr) {
+  // ord - 1 is the next float below thr: rows that TIE with the k-th score stay admissible everywhere, so ties at
+  // the boundary are still resolved by row number in the merge
+  if (thr > -INFINITY) atomicMax(gthr + q, score_to_ord(thr) - 1u);
+}
+
 // The epilogue warps' loop over this CTA's items; `arrive(as)` hands accumulator stage `as` back to the
 // MMA issuer.  q_off: first query of this CTA inside the item's query tile (pairs: rank * 128).
 template <int BN, typename Arrive>
@@ -515,7 +548,7 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
       const bool q_valid = q0 + t < p.nq;
       const bool warp_valid = q0 + row0w < p.nq;
       const uint32_t slot = p.by_slice ? slice : unit;
-      if (p.by_slice) epi.reset();
+      if (p.by_slice) epi.reset((p.gthr && q_valid) ? gthr_read(p.gthr, q0 + t) : -INFINITY);
       else epi.load(p.partial, q0 + t, p.nq, p.n_lists, slot);
       for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
         const uint32_t as = tc & 1;
@@ -529,6 +562,7 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
         if (lane == 0) arrive(as);
       }
       epi.store(p.partial, q0 + t, p.nq, p.n_lists, slot);
+      if (p.by_slice && p.gthr && q_valid) gthr_publish(p.gthr, q0 + t, epi.thr);
     }
   } else {
     DenseEpiRes epi;
@@ -545,6 +579,8 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
       const uint32_t slot = p.by_slice ? slice : unit;
       if (warp_valid && !p.by_slice) epi.load(p.partial, q0 + row0w, p.nq, p.n_lists, slot);
       else epi.reset();
+      epi.gthr_q = (p.by_slice && p.gthr && q_valid) ? p.gthr + q0 + t : nullptr;
+      if (epi.gthr_q) epi.thr = gthr_read(p.gthr, q0 + t);
       for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
         const uint32_t as = tc & 1;
         ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
@@ -557,6 +593,7 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
         if (lane == 0) arrive(as);
       }
       if (warp_valid) epi.store(p.partial, q0 + row0w, p.nq, p.n_lists, slot);
+      if (p.by_slice && p.gthr && q_valid) gthr_publish(p.gthr, q0 + t, epi.thr);
     }
   }
 }

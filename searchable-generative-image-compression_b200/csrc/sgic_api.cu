@@ -118,11 +118,11 @@ struct sgic_index {
   int64_t shard_row_start = 0, shard_total_rows = -1;
   int shard_id = 0, shard_count = 1;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1;
   int64_t stat_ingest_h2d_ns = 0, stat_ingest_k0_ns = 0, stat_ingest_k1_ns = 0;
   int64_t stat_ingest_parse_ns = 0, stat_ingest_pack_ns = 0, stat_ingest_gpu_ns = 0;
   int64_t stat_zl_device_frames = 0, stat_zl_host_rows = 0, stat_zl_fallback_slabs = 0;
-  int64_t stat_launches = 0, stat_last_search_ns = 0, stat_last_scan_ns = 0, stat_last_grid = 0, stat_last_stages = 0;
+  int64_t stat_launches = 0, stat_last_search_ns = 0, stat_last_scan_ns = 0, stat_last_grid = 0, stat_last_stages = 0, stat_last_kernel = 0;
 };
 
 namespace sgic {
@@ -481,9 +481,10 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     const bool by_slice = n_slices <= grid_units;
     const uint32_t n_lists = by_slice ? n_slices : grid_units;
     const size_t partial_bytes = static_cast<size_t>(nqb) * std::max(n_lists, grid_units) * static_cast<size_t>(k) * 8;
-    if (partial_bytes + 16 > h->ws_bytes) {
+    const size_t gthr_off = (partial_bytes + 15) & ~size_t(15), gthr_bytes = static_cast<size_t>(nqb) * 4;
+    if (gthr_off + gthr_bytes + 16 > h->ws_bytes) {
       SGIC_CUDA(cudaStreamSynchronize(st));
-      rc = ensure_buf(&h->ws, &h->ws_bytes, partial_bytes + 16, false);
+      rc = ensure_buf(&h->ws, &h->ws_bytes, gthr_off + gthr_bytes + 16, false);
       if (rc) return rc;
       h->ws_counter = nullptr;
     }
@@ -548,6 +549,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
         SGIC_CUDA(cudaGetLastError());
         h->stat_last_grid = units_b * 2;
         h->stat_last_stages = kD2bStages;
+        h->stat_last_kernel = 5;
         if (h->opt_timing && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));
         rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nqb, units_b, static_cast<uint32_t>(k),
                                dev_D + static_cast<size_t>(q0) * k, dev_I + static_cast<size_t>(q0) * k, id_base, st,
@@ -590,6 +592,9 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.n_tiles = n_tiles;
     p.n_lists = n_lists;
     p.by_slice = by_slice ? 1u : 0u;
+    // items of one query tile that run one after the other inherit each other's bounds ("dense_gthr" = 0: off)
+    p.gthr = (by_slice && n_slices > 1 && h->opt_dense_gthr)
+                 ? reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(h->ws) + gthr_off) : nullptr;
     p.kc = (static_cast<uint32_t>(h->d) + kDenseBK - 1) / kDenseBK;
     p.tp = tp ? 1u : 0u;
     p.a_rows = pairs ? static_cast<uint32_t>(kDenseBM) : std::min<uint32_t>(kDenseBM, (nqb + 7u) & ~7u);
@@ -609,6 +614,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     h->ws_counter = nullptr;  // this launch overwrites the workspace: K3 must re-zero its "CTAs done" counter
     // empty lists where a CTA resumes its own slot; the by-slice schedule writes every list in full
     if (transposed || !by_slice) SGIC_CUDA(cudaMemsetAsync(h->ws, 0, partial_bytes, st));
+    if (!transposed && p.gthr) SGIC_CUDA(cudaMemsetAsync(p.gthr, 0, gthr_bytes, st));
     if (transposed) {
       DenseTParams tp_;
       tp_.partial = p.partial;
@@ -639,6 +645,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     SGIC_CUDA(cudaGetLastError());
     h->stat_last_grid = grid;
     h->stat_last_stages = transposed ? t_stages : pairs ? 4 : p.n_stages;
+    h->stat_last_kernel = transposed ? 2 : !pairs ? 1 : a_resident ? 3 : 4;
     if (h->opt_timing && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));
     rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nqb, transposed ? grid_units : n_lists,
                            static_cast<uint32_t>(k), dev_D + static_cast<size_t>(q0) * k,
@@ -711,6 +718,7 @@ static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
   grid = std::max<uint32_t>(1, std::min(grid, std::max<uint32_t>(n_tiles, 1)));
   h->stat_last_grid = grid;
   h->stat_last_stages = stages;
+  h->stat_last_kernel = 0;
 
   // fused grid-level merge (last CTA) when all partial lists fit in the freed stage ring
   const size_t partial_bytes = static_cast<size_t>(NQ) * grid * static_cast<size_t>(k) * 8;
@@ -1583,6 +1591,7 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "device_zstd") h->opt_device_zstd = value;
   else if (n == "dense_l2_mb") h->opt_dense_l2_mb = std::max<int64_t>(0, value);
   else if (n == "dense_b_min_mb") h->opt_dense_b_min_mb = std::max<int64_t>(0, value);
+  else if (n == "dense_gthr") h->opt_dense_gthr = value ? 1 : 0;
   else if (n == "drop_retained") {
     std::lock_guard<std::mutex> lk(h->mu);
     h->retain_ok = false;
@@ -1604,6 +1613,9 @@ int64_t sgic_index_get_stat(const sgic_index* h, const char* name) {
   if (n == "last_scan_ns") return h->stat_last_scan_ns;
   if (n == "last_grid") return h->stat_last_grid;
   if (n == "last_stages") return h->stat_last_stages;
+  // scan kernel of the last search: 0 scan_small (K3), 1 scan_dense (1 CTA), 2 scan_dense_t (K4t), 3 scan_dense2
+  // with the query tile resident, 4 scan_dense2 streamed, 5 scan_dense2b (database tile resident, K4b)
+  if (n == "last_kernel") return h->stat_last_kernel;
   if (n == "capacity") return h->capacity;
   if (n == "sm_count") return h->sm_count;
   if (n == "dense_min_nq") return h->opt_dense_min_nq ? h->opt_dense_min_nq : ((h->ntotal >= (8ll << 20)) ? 2 : 3);

@@ -154,6 +154,27 @@ def test_dense_exact_duplicates_resolve_to_lowest_ids(k):
     check_topk(D, I, f16(xb), f16(xq), k, score_tol=3e-5, tie_tol=1e-6)
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 40])
+def test_dense_ties_across_items_full_block(k):
+    """A full 4096-query block runs 8 rounds of (query tile, slice) items; later items inherit the score bound the
+    earlier ones published (gthr).  Exact copies of a row sit in different slices, so the k-th boundary is a tie
+    between lists: the answer must still be the lowest row numbers, identical with the inheritance switched off."""
+    rng = np.random.default_rng(47)
+    base = unit(rng, 9000, 512)
+    xb = np.concatenate([base, base, base])
+    xq = base[:4096].copy()
+    idx = make_index(xb)
+    D, I = idx.search(xq, k)
+    want = np.stack([np.arange(4096) + 9000 * j for j in range(3)], axis=1)[:, :min(k, 3)]
+    assert np.array_equal(I[:, :min(k, 3)], want)
+    idx.set_option("dense_gthr", 0)
+    D0, I0 = idx.search(xq, k)
+    assert np.array_equal(I, I0) and np.array_equal(D, D0)
+    sel = np.arange(0, 4096, 97)
+    check_topk(D[sel], I[sel], f16(xb), f16(xq[sel]), k, score_tol=3e-5, tie_tol=1e-6)
+    idx.close()
+
+
 def test_dense_agrees_with_streaming_kernel():
     """Size-independent property: the same queries answered one at a time by K3 (CUDA-core streaming scan) and
     as one batch by K4 (tensor cores) give the same ids; scores agree to fp32 accumulation-order noise."""

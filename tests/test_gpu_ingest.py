@@ -358,3 +358,38 @@ def test_resident_service_over_the_real_index(tmp_path):
         assert doc[0]["path"] == paths[0] and set(doc[0]) == {"path", "score"}
     finally:
         svc.close()
+
+
+def test_config_c1_10k_vectors_100_queries_one_at_a_time(tmp_path):
+    """BASELINE.json configs[0]: 10k x 512 vectors in the reference's on-disk layouts (IO/clip_vecs/*.npy + an IxFI
+    index.faiss + ids.txt), 100 text-like queries answered ONE AT A TIME through load_index -> do_search
+    (src/search.py:65-88,113-120), k = 10.  The oracle holds what FAISS would hold: the fp32 rows of the file."""
+    from sgic_b200 import retrieval
+    from oracle.flat_ip import flat_ip_search
+    rng = np.random.default_rng(101)
+    n, d, nq, k = 10_000, 512, 100, 10
+    cone = rng.standard_normal(d).astype(np.float32)
+    cone /= np.linalg.norm(cone)
+    xb = (cone + rng.standard_normal((n, d)).astype(np.float32) / np.sqrt(d)).astype(np.float32)   # CLIP-like cone
+    xb /= np.linalg.norm(xb, axis=1, keepdims=True)
+    xb[5000:5010] = xb[10:20]                                                                     # exact duplicates
+    ids = [f"../IO/bitstreams/img_{i:05d}.c2df" for i in range(n)]
+    c2df_ref.write_ixfi(tmp_path / "index.faiss", xb)
+    (tmp_path / "ids.txt").write_text("".join(s + "\n" for s in ids))                             # compress.py:112-114
+    index, paths, meta = retrieval.load_index(tmp_path)
+    assert index.ntotal == n and index.d == d and paths == ids
+    xq = (cone + 1.5 * rng.standard_normal((nq, d)).astype(np.float32) / np.sqrt(d)).astype(np.float32)
+    xq /= np.linalg.norm(xq, axis=1, keepdims=True)
+    xq[:10] = xb[10:20]                                                                           # queries with ties
+    D = np.empty((nq, k), np.float32)
+    I = np.empty((nq, k), np.int64)
+    for i in range(nq):
+        res = retrieval.do_search(xq[i:i + 1], index, paths, topk=k)
+        assert len(res) == k and all(isinstance(s, float) for _, s in res)
+        I[i] = [ids.index(p) for p, _ in res]
+        D[i] = [s for _, s in res]
+    check_topk(D, I, xb, xq, k, score_tol=1e-3)          # O-ref: fp32 rows, north_star tolerance
+    Dref, Iref = flat_ip_search(xb, xq, k)
+    for i in range(10):                                  # duplicates: both copies lead, lowest row first
+        assert list(I[i, :2]) == [10 + i, 5000 + i] and list(Iref[i, :2]) == [10 + i, 5000 + i]
+    assert (I == Iref).mean() > 0.9                       # fp16 storage may swap near-ties (<1e-3 apart) only
