@@ -276,7 +276,9 @@ def run_ours(args):
         ms_total = e0.elapsed_time(e1)
         if clk:
             windows.append(clk.end())
-        launches = local.stat("launches") - launches0 + (steps if world > 1 else 0)   # + K5 merge per step
+        # + the exchange's own kernels per step: K5x push + wait/merge, or K5 merge after the NCCL all_gather
+        xk = 0 if world == 1 else (2 if (index.exchange == "peer" and nq * k <= index._peer.max_cands) else 1)
+        launches = local.stat("launches") - launches0 + xk * steps
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -370,6 +372,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
         "config": {"workload": f"{R}x{d} {args.dtype} index row-sharded over {world} GPU(s), batch {nq}, k={k}",
                    "rows": R, "dim": d, "k": k, "batch": nq, "rows_per_gpu": n_local,
+                   "exchange": (index.exchange if world > 1 else None),
                    "l2": f"inputs larger than L2: every step streams the {n_local * d * 2 / 1e9:.1f} GB shard from HBM"},
         "clocks": main["clocks"], "gpu_launches": main["gpu_launches"],
         "e2e": main["e2e"],

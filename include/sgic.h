@@ -111,6 +111,23 @@ int sgic_merge_topk_dev(int device, int64_t nq, int n_lists, int64_t k, const fl
                         const int64_t* dev_I_lists, float* dev_D, int64_t* dev_I, int tie_by_position,
                         void* stream);
 
+/* K5x — the same exchange + merge WITHOUT a collective library call (SURVEY.md §8e "optional fusion: peer-store
+ * epilogue + flag instead of NCCL").  Every rank owns one exchange buffer; the ranks swap its 64-byte CUDA IPC
+ * handle once (any transport: the Python host uses torch.distributed.all_gather_object) and map each other's
+ * buffers.  sgic_xchg_merge_dev then (1) stores this rank's (nq,k) answer into its slot of EVERY rank's buffer
+ * over NVLink and raises a system-scope release flag per destination, (2) merges the `world` lists of its own
+ * buffer as soon as their flags carry this step's epoch — two launches on `stream`, identical result to
+ * all-gather + sgic_merge_topk_dev.  Collective: every rank calls it once per search, in the same order.
+ * nq*k <= max_cands; world <= 16.  sgic_xchg_error() != 0 after a rank waited 20 s for a peer in vain. */
+typedef struct sgic_xchg sgic_xchg;
+int sgic_xchg_create(int device, int world, int rank, int64_t max_cands, sgic_xchg** out);
+int sgic_xchg_export(sgic_xchg* x, uint8_t* handle64);
+int sgic_xchg_open(sgic_xchg* x, const uint8_t* handles /* world * 64 bytes, rank order */);
+int sgic_xchg_merge_dev(sgic_xchg* x, int64_t nq, int64_t k, const float* dev_D_local, const int64_t* dev_I_local,
+                        float* dev_D, int64_t* dev_I, int tie_by_position, void* stream);
+int sgic_xchg_error(sgic_xchg* x);
+int sgic_xchg_destroy(sgic_xchg* x);
+
 /* faiss.write_index / faiss.read_index — src/build.py:95,99,235,238; src/compress.py:95,111;
  * src/search.py:69,76.  File layout "IxFI" (SURVEY.md §8a F3): fp32 little-endian rows. */
 int sgic_index_write(sgic_index* h, const char* path);

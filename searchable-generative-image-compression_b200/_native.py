@@ -45,6 +45,13 @@ _SIGNATURES = {
                                         C.c_int64, C.c_void_p]),
     "sgic_merge_topk_dev": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "sgic_xchg_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "sgic_xchg_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sgic_xchg_open": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sgic_xchg_merge_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_void_p]),
+    "sgic_xchg_error": (C.c_int, [C.c_void_p]),
+    "sgic_xchg_destroy": (C.c_int, [C.c_void_p]),
     "sgic_index_write": (C.c_int, [C.c_void_p, C.c_char_p]),
     "sgic_index_read": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "sgic_index_write_v2": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int]),

@@ -1296,6 +1296,165 @@ int sgic_merge_topk_dev(int device, int64_t nq, int n_lists, int64_t k, const fl
   return 0;
 }
 
+// ---- K5x: exchange of the per-shard answers by peer stores over NVLink (SURVEY.md §8e "optional fusion") --------
+// Each rank owns one buffer (cudaMalloc, exported with cudaIpcGetMemHandle and mapped by every other rank):
+//   flags [2 parities][world] one 128-byte line each | error word | D_lists [2][world][max_cands] f32 |
+//   I_lists [2][world][max_cands] i64
+// A search step pushes this rank's (nq,k) answer into slot `rank` of every rank's buffer (xchg_push_kernel: plain
+// stores into the peers' HBM + one system-scope release flag per destination) and merges the `world` lists of its
+// own buffer as soon as their flags carry the step's epoch (merge_lists_kernel with wait_flags).  Two launches, no
+// NCCL call, no packing.  Parity double-buffering is enough: a rank can only start step s+1's push after its merge
+// of step s, which waited for every peer's push of step s, which follows that peer's merge of step s-1.
+struct sgic_xchg {
+  int device = 0, world = 0, rank = 0;
+  int64_t max_cands = 0;
+  uint8_t* base = nullptr;
+  size_t bytes = 0, d_off = 0, i_off = 0, err_off = 0;
+  uint8_t* peer[16] = {nullptr};
+  uint32_t epoch = 0;
+  bool opened = false;
+};
+
+int sgic_xchg_create(int device, int world, int rank, int64_t max_cands, sgic_xchg** out) {
+  SGIC_REQUIRE(out != nullptr, "out is NULL");
+  SGIC_REQUIRE(world >= 2 && world <= 16 && rank >= 0 && rank < world, "world must be 2..16 and 0 <= rank < world");
+  SGIC_REQUIRE(max_cands >= 1 && max_cands <= (1ll << 24), "max_cands out of range");
+  DeviceGuard g(device);
+  auto* x = new sgic_xchg();
+  x->device = device;
+  x->world = world;
+  x->rank = rank;
+  x->max_cands = max_cands;
+  x->err_off = static_cast<size_t>(2) * world * 128;
+  x->d_off = x->err_off + 128;
+  x->i_off = x->d_off + static_cast<size_t>(2) * world * max_cands * 4;
+  x->i_off = (x->i_off + 127) & ~size_t(127);
+  x->bytes = x->i_off + static_cast<size_t>(2) * world * max_cands * 8;
+  cudaError_t e = cudaMalloc(&x->base, x->bytes);
+  if (e != cudaSuccess) {
+    delete x;
+    set_error(std::string("exchange buffer: cudaMalloc failed: ") + cudaGetErrorString(e));
+    return 3;
+  }
+  e = cudaMemset(x->base, 0, x->bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(x->base);
+    delete x;
+    set_error(std::string("exchange buffer: memset failed: ") + cudaGetErrorString(e));
+    return 2;
+  }
+  *out = x;
+  return 0;
+}
+
+int sgic_xchg_export(sgic_xchg* x, uint8_t* handle64) {
+  SGIC_REQUIRE(x != nullptr && handle64 != nullptr, "NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  DeviceGuard g(x->device);
+  cudaIpcMemHandle_t h;
+  SGIC_CUDA(cudaIpcGetMemHandle(&h, x->base));
+  std::memcpy(handle64, &h, 64);
+  return 0;
+}
+
+int sgic_xchg_open(sgic_xchg* x, const uint8_t* handles) {
+  SGIC_REQUIRE(x != nullptr && handles != nullptr, "NULL argument");
+  SGIC_REQUIRE(!x->opened, "exchange already opened");
+  DeviceGuard g(x->device);
+  for (int r = 0; r < x->world; ++r) {
+    if (r == x->rank) {
+      x->peer[r] = x->base;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + static_cast<size_t>(r) * 64, 64);
+    void* ptr = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int r2 = 0; r2 < r; ++r2)
+        if (r2 != x->rank && x->peer[r2]) cudaIpcCloseMemHandle(x->peer[r2]);
+      for (auto& pp : x->peer) pp = nullptr;
+      (void)cudaGetLastError();
+      set_error(std::string("cudaIpcOpenMemHandle failed for rank ") + std::to_string(r) + ": " + cudaGetErrorString(e));
+      return 2;
+    }
+    x->peer[r] = static_cast<uint8_t*>(ptr);
+  }
+  x->opened = true;
+  return 0;
+}
+
+int sgic_xchg_merge_dev(sgic_xchg* x, int64_t nq, int64_t k, const float* dev_D_local, const int64_t* dev_I_local,
+                        float* dev_D, int64_t* dev_I, int tie_by_position, void* stream) {
+  SGIC_REQUIRE(x != nullptr && x->opened, "exchange is not open");
+  SGIC_REQUIRE(nq >= 1 && k >= 1 && nq * k <= x->max_cands, "nq * k exceeds the exchange buffer");
+  SGIC_REQUIRE(static_cast<int64_t>(x->world) * k < (1ll << 31), "too many candidates");
+  DeviceGuard g(x->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t epoch = ++x->epoch;
+  const size_t par = epoch & 1u, W = static_cast<size_t>(x->world), MC = static_cast<size_t>(x->max_cands);
+  XchgPushParams pp;
+  pp.D = dev_D_local;
+  pp.I = reinterpret_cast<const long long*>(dev_I_local);
+  pp.n = static_cast<uint32_t>(nq * k);
+  pp.epoch = epoch;
+  for (int r = 0; r < x->world; ++r) {
+    const size_t slot = par * W + static_cast<size_t>(x->rank);
+    pp.dstD[r] = reinterpret_cast<float*>(x->peer[r] + x->d_off) + slot * MC;
+    pp.dstI[r] = reinterpret_cast<long long*>(x->peer[r] + x->i_off) + slot * MC;
+    pp.dstFlag[r] = reinterpret_cast<uint32_t*>(x->peer[r] + slot * 128);
+  }
+  xchg_push_kernel<<<static_cast<unsigned>(x->world), 256, 0, st>>>(pp);
+  SGIC_CUDA(cudaGetLastError());
+  MergeListsParams mp;
+  mp.D_lists = reinterpret_cast<const float*>(x->base + x->d_off) + par * W * MC;
+  mp.I_lists = reinterpret_cast<const long long*>(x->base + x->i_off) + par * W * MC;
+  mp.n_lists = static_cast<uint32_t>(x->world);
+  mp.nq = static_cast<uint32_t>(nq);
+  mp.k = static_cast<uint32_t>(k);
+  const uint32_t kp = next_pow2_u32(mp.k);
+  uint32_t chunk = std::max<uint32_t>(2 * kp, std::min<uint32_t>(16384, next_pow2_u32(mp.n_lists * mp.k)));
+  chunk = std::max<uint32_t>(chunk, 64);
+  SGIC_REQUIRE(static_cast<size_t>(chunk) * 8 <= kSmemBudget, "k too large for the merge kernel");
+  mp.chunk = chunk;
+  mp.tie_by_position = tie_by_position ? 1u : 0u;
+  mp.D = dev_D;
+  mp.I = reinterpret_cast<long long*>(dev_I);
+  mp.list_stride = MC;
+  mp.wait_flags = reinterpret_cast<const uint32_t*>(x->base + par * W * 128);
+  mp.wait_epoch = epoch;
+  mp.err = reinterpret_cast<uint32_t*>(x->base + x->err_off);
+  const size_t smem = static_cast<size_t>(chunk) * 8;
+  if (smem > 48 * 1024)
+    SGIC_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+  const int threads = static_cast<int>(std::min<uint32_t>(1024, std::max<uint32_t>(32, chunk / 2)));
+  merge_lists_kernel<<<static_cast<unsigned>(nq), threads, smem, st>>>(mp);
+  SGIC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sgic_xchg_error(sgic_xchg* x) {
+  SGIC_REQUIRE(x != nullptr, "exchange is NULL");
+  DeviceGuard g(x->device);
+  uint32_t v = 0;
+  SGIC_CUDA(cudaMemcpy(&v, x->base + x->err_off, 4, cudaMemcpyDeviceToHost));
+  if (v) set_error("peer exchange: a rank's candidates did not arrive within the time-out");
+  return v ? 2 : 0;
+}
+
+int sgic_xchg_destroy(sgic_xchg* x) {
+  if (x == nullptr) return 0;
+  DeviceGuard g(x->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < x->world; ++r)
+    if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
+  if (x->base) cudaFree(x->base);
+  delete x;
+  return 0;
+}
+
 int sgic_index_reconstruct(sgic_index* h, int64_t i0, int64_t n, float* host_out) {
   SGIC_REQUIRE(h != nullptr, "index is NULL");
   SGIC_REQUIRE(i0 >= 0 && n >= 0 && i0 + n <= h->ntotal, "row range out of bounds");

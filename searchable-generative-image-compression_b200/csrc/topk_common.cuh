@@ -201,19 +201,82 @@ struct MergeListsParams {
   uint32_t tie_by_position;
   float* D;
   long long* I;
+  size_t list_stride = 0;            // elements between two lists (0: nq * k, the all-gather layout)
+  // peer exchange (K5x): list g is complete once wait_flags[g * kXchgFlagStride] >= wait_epoch (written by rank g
+  // over NVLink with a system-scope release after its candidates); nullptr: the lists are already there
+  const uint32_t* wait_flags = nullptr;
+  uint32_t wait_epoch = 0;
+  uint32_t* err = nullptr;           // set to 1 if a flag did not arrive within kXchgTimeoutNs
 };
+
+constexpr uint32_t kXchgFlagStride = 32;                     // one flag per 128-byte line
+constexpr unsigned long long kXchgTimeoutNs = 20000000000ull;  // a peer that is 20 s late is gone: do not hang the GPU
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// K5x push: this rank's (nq, k) answer -> slot `rank` of EVERY rank's gather buffer (its own included), written
+// straight into the peers' HBM over NVLink, then one release-flag per destination.  One CTA per destination.
+struct XchgPushParams {
+  const float* D;          // [n] this rank's scores (n = nq * k)
+  const long long* I;      // [n] global row numbers
+  uint32_t n;
+  uint32_t epoch;
+  float* dstD[16];         // per destination rank: slot `rank` of its D_lists / I_lists / flags (peer mappings)
+  long long* dstI[16];
+  uint32_t* dstFlag[16];
+};
+
+__global__ void __launch_bounds__(256, 1) xchg_push_kernel(const XchgPushParams p) {
+  const uint32_t dst = blockIdx.x;
+  float* D = p.dstD[dst];
+  long long* I = p.dstI[dst];
+  for (uint32_t i = threadIdx.x; i < p.n; i += blockDim.x) {
+    D[i] = p.D[i];
+    I[i] = p.I[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_sys(p.dstFlag[dst], p.epoch);
+}
 
 __global__ void __launch_bounds__(1024, 1) merge_lists_kernel(MergeListsParams p) {
   extern __shared__ __align__(16) uint64_t ml_smem[];
   const uint32_t q = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const uint32_t n_total = p.n_lists * p.k;
+  const size_t stride = p.list_stride ? p.list_stride : static_cast<size_t>(p.nq) * p.k;
+  if (p.wait_flags != nullptr) {
+    if (tid < p.n_lists) {
+      const uint32_t* f = p.wait_flags + static_cast<size_t>(tid) * kXchgFlagStride;
+      const unsigned long long t0 = global_timer_ns();
+      while (static_cast<int32_t>(ld_acquire_sys(f) - p.wait_epoch) < 0) {
+        if (global_timer_ns() - t0 > kXchgTimeoutNs) {
+          if (p.err) *p.err = 1u;
+          break;
+        }
+        __nanosleep(100);
+      }
+    }
+    __syncthreads();
+  }
   if (n_total <= p.chunk && p.n_lists <= 32u * kMergeMaxLpl) {
     // fast path: all candidates fit in shared memory -> stage the keys, one warp merges the heads
     for (uint32_t e = tid; e < n_total; e += nt) {
       const uint32_t g = e / p.k, j = e - g * p.k;
-      const size_t o = (static_cast<size_t>(g) * p.nq + q) * p.k + j;
-      const long long id = p.I_lists[o];
-      ml_smem[e] = (id >= 0) ? make_key(p.D_lists[o], p.tie_by_position ? e : static_cast<uint32_t>(id)) : 0ull;
+      const size_t o = static_cast<size_t>(g) * stride + static_cast<size_t>(q) * p.k + j;
+      const long long id = __ldcg(p.I_lists + o);
+      ml_smem[e] = (id >= 0) ? make_key(__ldcg(p.D_lists + o), p.tie_by_position ? e : static_cast<uint32_t>(id)) : 0ull;
     }
     __syncthreads();
     if (tid < 32) {
@@ -226,9 +289,9 @@ __global__ void __launch_bounds__(1024, 1) merge_lists_kernel(MergeListsParams p
                                             pp.I[out] = -1;
                                           } else if (pp.tie_by_position) {
                                             const uint32_t e = key_id(key), g = e / pp.k, j = e - g * pp.k;
-                                            const size_t o = (static_cast<size_t>(g) * pp.nq + q) * pp.k + j;
-                                            pp.D[out] = pp.D_lists[o];
-                                            pp.I[out] = pp.I_lists[o];
+                                            const size_t o = static_cast<size_t>(g) * stride + static_cast<size_t>(q) * pp.k + j;
+                                            pp.D[out] = __ldcg(pp.D_lists + o);
+                                            pp.I[out] = __ldcg(pp.I_lists + o);
                                           } else {
                                             pp.D[out] = key_score(key);
                                             pp.I[out] = static_cast<long long>(key_id(key));
@@ -245,9 +308,9 @@ __global__ void __launch_bounds__(1024, 1) merge_lists_kernel(MergeListsParams p
       uint64_t key = 0ull;
       if (i < take) {
         const uint32_t e = pos + i, g = e / p.k, j = e - g * p.k;
-        const size_t o = (static_cast<size_t>(g) * p.nq + q) * p.k + j;
-        const long long id = p.I_lists[o];
-        if (id >= 0) key = make_key(p.D_lists[o], p.tie_by_position ? e : static_cast<uint32_t>(id));
+        const size_t o = static_cast<size_t>(g) * stride + static_cast<size_t>(q) * p.k + j;
+        const long long id = __ldcg(p.I_lists + o);
+        if (id >= 0) key = make_key(__ldcg(p.D_lists + o), p.tie_by_position ? e : static_cast<uint32_t>(id));
       }
       ml_smem[carry + i] = key;
     }
@@ -264,9 +327,9 @@ __global__ void __launch_bounds__(1024, 1) merge_lists_kernel(MergeListsParams p
       p.I[out] = -1;
     } else if (p.tie_by_position) {
       const uint32_t e = key_id(key), g = e / p.k, j = e - g * p.k;
-      const size_t o = (static_cast<size_t>(g) * p.nq + q) * p.k + j;
-      p.D[out] = p.D_lists[o];
-      p.I[out] = p.I_lists[o];
+      const size_t o = static_cast<size_t>(g) * stride + static_cast<size_t>(q) * p.k + j;
+      p.D[out] = __ldcg(p.D_lists + o);
+      p.I[out] = __ldcg(p.I_lists + o);
     } else {
       p.D[out] = key_score(key);
       p.I[out] = static_cast<long long>(key_id(key));

@@ -7,6 +7,13 @@ top-k on each GPU (K3/K4) with global row numbers → ONE ``all_gather`` of the 
 ``G·k → k`` (K5, ``sgic_merge_topk_dev``) ordered by (score desc, global id asc), so the
 G-GPU answer is identical to the 1-GPU answer.  There is no other collective on the path.
 
+When the ranks can map each other's memory (CUDA IPC, one box) the exchange runs without a
+collective call at all (K5x, ``sgic_xchg_merge_dev``): every rank stores its candidates straight
+into the peers' HBM over NVLink, raises a flag, and merges its own buffer as soon as all flags
+are up — two small launches instead of pack + all_gather + unpack + merge.  NCCL stays the
+transport for anything the buffer does not hold (``nq·k`` above ``PEER_MAX_CANDS``) and when
+``SGIC_EXCHANGE=nccl`` asks for it.
+
 The reference has no multi-GPU retrieval (its only ``torch.distributed`` use shards the image
 encoder over files, src/compress.py:34-55,293-306, with rank 0 building the index serially);
 this class is the additive surface the north star asks for and keeps the faiss names.
@@ -28,6 +35,67 @@ def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
     per = -(-n // world) if n > 0 else 0
     lo = min(n, rank * per)
     return lo, min(n, lo + per)
+
+
+PEER_MAX_CANDS = 1 << 19   # nq*k the peer-exchange buffer holds per rank (12 MB per rank and parity at 8 GPUs)
+
+
+class PeerExchange:
+    """K5x: the per-rank exchange buffer, its IPC handle swap, and the push + wait + merge call."""
+
+    def __init__(self, dist, group, device_index: int, world: int, rank: int, max_cands: int = PEER_MAX_CANDS):
+        import torch
+        lib = _native.lib()
+        self._lib, self._h, self.max_cands = lib, C.c_void_p(), int(max_cands)
+        self._dist, self._group = dist, group
+        ok, handle = True, bytes(64)
+        try:
+            _native.check(lib.sgic_xchg_create(device_index, world, rank, self.max_cands, C.byref(self._h)))
+            buf = (C.c_uint8 * 64)()
+            _native.check(lib.sgic_xchg_export(self._h, buf))
+            handle = bytes(buf)
+        except RuntimeError:
+            ok = False
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (ok, handle), group=group)
+        if ok and all(g[0] for g in gathered):
+            try:
+                blob = b"".join(g[1] for g in gathered)
+                _native.check(lib.sgic_xchg_open(self._h, C.c_char_p(blob)))
+            except RuntimeError:
+                ok = False
+        else:
+            ok = False
+        verdict = [None] * world
+        dist.all_gather_object(verdict, ok, group=group)   # every rank mapped every peer, or nobody uses it
+        self.ok = all(verdict)
+        if not self.ok:
+            self.close(collective=False)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def merge(self, D_local, I_local, k: int, by_position: bool):
+        import torch
+        nq = D_local.shape[0]
+        D = torch.empty((nq, k), dtype=torch.float32, device=D_local.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=D_local.device)
+        _native.check(self._lib.sgic_xchg_merge_dev(self._h, nq, k, C.c_void_p(D_local.data_ptr()),
+                                                    C.c_void_p(I_local.data_ptr()), C.c_void_p(D.data_ptr()),
+                                                    C.c_void_p(I.data_ptr()), 1 if by_position else 0,
+                                                    _torch_stream(D_local.device)))
+        return D, I
+
+    def check(self) -> None:
+        _native.check(self._lib.sgic_xchg_error(self._h))
+
+    def close(self, collective: bool = True) -> None:
+        if self._h:
+            if collective:
+                import torch
+                torch.cuda.synchronize()
+                self._dist.barrier(group=self._group)   # nobody still writes into a buffer that is about to go
+            self._lib.sgic_xchg_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 def _merge_cuda(D_lists, I_lists, k: int, by_position: bool):
@@ -73,6 +141,12 @@ class ShardedIndexFlatIP(Index):
             self._dev = torch.device("cpu")
         self.local = local_factory(d) if local_factory else IndexFlatIP(d, dtype=dtype, device=dev, retain_fp32=False)
         self._merge = merge_fn or _merge_cuda
+        self._peer = None
+        import os
+        if (self._cuda and self.world > 1 and merge_fn is None
+                and os.environ.get("SGIC_EXCHANGE", "peer") != "nccl" and self.world <= 16):
+            px = PeerExchange(dist, group, dev, self.world, self.rank)
+            self._peer = px if px.ok else None
         # segments of this rank: (global_start, local_start, count), ascending in both
         self._segments: List[Tuple[int, int, int]] = []
         self._ntotal = 0
@@ -168,6 +242,9 @@ class ShardedIndexFlatIP(Index):
             I = self._to_global(I)
         if self.world == 1:
             return D, I
+        contiguous_shards = self._ntotal >= (1 << 32)   # ids beyond 32 bits: tie-break by shard position
+        if self._peer is not None and nq * k <= self._peer.max_cands:
+            return self._peer.merge(D.contiguous(), I.contiguous(), k, contiguous_shards)
         # pack (ids, scores) into one buffer so that the exchange is a single all_gather
         packed = torch.empty((nq, k, 3), dtype=torch.int32, device=q.device)
         packed[..., :2] = I.view(torch.int32).view(nq, k, 2)
@@ -177,8 +254,21 @@ class ShardedIndexFlatIP(Index):
         gathered = gathered.view(self.world, nq, k, 3)
         I_lists = gathered[..., :2].contiguous().view(torch.int64).view(self.world, nq, k)
         D_lists = gathered[..., 2].contiguous().view(torch.float32)
-        contiguous_shards = self._ntotal >= (1 << 32)   # ids beyond 32 bits: tie-break by shard position
         return self._merge(D_lists, I_lists, k, contiguous_shards)
+
+    @property
+    def exchange(self) -> str:
+        """"peer" (K5x: stores into the peers' HBM + flags) or "nccl" (all_gather + K5)."""
+        return "peer" if self._peer is not None else "nccl"
+
+    def close(self) -> None:
+        """Collective.  Releases the peer-exchange buffer (after a barrier) and the local shard."""
+        if self._peer is not None:
+            self._peer.check()
+            self._peer.close()
+            self._peer = None
+        if hasattr(self.local, "close"):
+            self.local.close()
 
     def search(self, x, k: int):
         """faiss signature: host fp32 (nq, d) in, host (D, I) out — on every rank."""

@@ -67,12 +67,33 @@ def _worker(rank, world, port, out_dir):
         idx.add(xb[:30_000])
         idx.add(xb[30_000:])                               # two segments per rank
         assert idx.ntotal == xb.shape[0]
-        for nq, k in ((1, 10), (6, 10), (2, 100)):
+        # the exchange is K5x (stores into the peer's HBM over NVLink + flags) wherever the ranks can map each
+        # other's memory; the NCCL all_gather + K5 route must give bit-identical answers
+        os.environ["SGIC_EXCHANGE"] = "nccl"
+        idx_nccl = ShardedIndexFlatIP(d)
+        del os.environ["SGIC_EXCHANGE"]
+        idx_nccl.add(xb[:30_000])
+        idx_nccl.add(xb[30_000:])
+        assert idx_nccl.exchange == "nccl"
+        (Path(out_dir) / f"exchange{rank}").write_text(idx.exchange)
+        for nq, k in ((1, 10), (6, 10), (2, 100), (300, 10), (1, 1), (3, 1024)):
             xq = np.concatenate([xb[:1], unit(rng, nq - 1, d)]) if nq > 1 else xb[:1].copy()
-            D, I = idx.search(xq, k)
+            for rep in range(3):                               # both parities of the exchange buffer, and a reuse
+                D, I = idx.search(xq, k)
+            Dn, In = idx_nccl.search(xq, k)
+            assert np.array_equal(I, In) and np.array_equal(D, Dn)
             xb16 = xb.astype(np.float16).astype(np.float64)
-            check_topk(D, I, xb16, xq.astype(np.float16).astype(np.float64), k, score_tol=2e-5, tie_tol=1e-6)
-            assert I[0, 0] == 0 and I[0, 1] == 40_000      # exact tie -> lower global id first
+            sel = slice(0, min(nq, 8))
+            check_topk(D[sel], I[sel], xb16, xq[sel].astype(np.float16).astype(np.float64), k, score_tol=2e-5, tie_tol=1e-6)
+            if k >= 2:
+                assert I[0, 0] == 0 and I[0, 1] == 40_000      # exact tie -> lower global id first
+        # candidates beyond the exchange buffer (nq * k > PEER_MAX_CANDS) travel by all_gather
+        xq = unit(rng, 600, d)
+        D, I = idx.search(xq, 1000)
+        Dn, In = idx_nccl.search(xq, 1000)
+        assert np.array_equal(I, In) and np.array_equal(D, Dn)
+        if idx._peer is not None:
+            idx._peer.check()
         # collective .c2df ingest (config C5's loader) + SGI2 shard files: save, reload, same answers
         from oracle import c2df_ref
         paths = sorted(str(p) for p in Path(out_dir).glob("corpus/*.c2df"))
@@ -123,3 +144,5 @@ def test_two_gpu_nccl_sharded_search(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+    # one box, NVLink between the GPUs: the peer exchange must have come up (a silent NCCL-only run would hide it)
+    assert (tmp_path / "exchange0").read_text() == "peer" and (tmp_path / "exchange1").read_text() == "peer"
