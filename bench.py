@@ -392,7 +392,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def ingest_extra(faiss, dev, n_distinct=20_000, tile=10, d=512):
+def ingest_extra(faiss, dev, n_distinct=20_000, tile=40, d=512):
     """North-star item (a): batched .c2df ingest (TLV walk on the host cores, clip_stream decode, K1 on the
     device) in files/s — device-side zstd decode (K0) against the libzstd-on-host route, same corpus: `n_distinct`
     reference-style files (~2.3 KB: codec streams + clip_stream + clip_meta) repeated `tile` times."""

@@ -88,22 +88,24 @@ struct sgic_index {
   void* lists_ws = nullptr;  // dense path, k > 32: per-query reservoirs
   size_t lists_ws_bytes = 0;
   // device-side clip_stream decode (K0): u8 row matrix, packed frames, descriptors, per-frame status
-  void* zl_rows = nullptr;
-  size_t zl_rows_bytes = 0;
-  void* zl_frames = nullptr;
-  size_t zl_frames_bytes = 0;
-  void* zl_desc = nullptr;
-  size_t zl_desc_bytes = 0;
-  void* zl_status = nullptr;
-  size_t zl_status_bytes = 0;
-  void* zl_status_host = nullptr;
-  size_t zl_status_host_bytes = 0;
-  void* zl_pin_rows = nullptr;  // pinned staging of a slab: u8 matrix, packed frames, descriptors
-  size_t zl_pin_rows_bytes = 0;
-  void* zl_pin_frames = nullptr;
-  size_t zl_pin_frames_bytes = 0;
-  void* zl_pin_desc = nullptr;
-  size_t zl_pin_desc_bytes = 0;
+  // ingest pipeline (device-side clip_stream decode): kZlDepth slabs in flight — the host walks / packs slab i
+  // while slab i-1 crosses PCIe on the copy stream and K0 decodes slab i-2 on the index's stream
+  struct ZlSlab {
+    void *pin_rows = nullptr, *pin_frames = nullptr, *pin_desc = nullptr, *status_host = nullptr;  // pinned
+    size_t pin_rows_bytes = 0, pin_frames_bytes = 0, pin_desc_bytes = 0, status_host_bytes = 0;
+    void *rows = nullptr, *frames = nullptr, *desc = nullptr, *status = nullptr;                    // device
+    size_t rows_bytes = 0, frames_bytes = 0, desc_bytes = 0, status_bytes = 0;
+    cudaEvent_t copied = nullptr, decoded = nullptr, freed = nullptr;
+    cudaEvent_t t_c0 = nullptr, t_c1 = nullptr, t_k0 = nullptr, t_k1 = nullptr, t_q0 = nullptr, t_q1 = nullptr;  // "timing" option
+    bool used = false, timed = false;
+    // the slab currently in the set
+    int64_t s0 = 0, cnt = 0, w = 0, nf = 0, nh = 0, full = 0;  // full: files of a full slab (buffer sizing)
+    size_t fbytes = 0;
+    int mode = 0;  // 0 nothing to append, 1 device decode, 2 host route (nothing in the device profile)
+  };
+  static constexpr int kZlDepth = 3;
+  ZlSlab zl[kZlDepth];
+  cudaStream_t copy_stream = nullptr;
   void* qdev = nullptr;  // queries / outputs for the host-buffer search
   size_t qdev_bytes = 0;
   void* odev = nullptr;
@@ -872,14 +874,19 @@ int sgic_index_destroy(sgic_index* h) {
   if (h->qdev) cudaFree(h->qdev);
   if (h->qh) cudaFree(h->qh);
   if (h->lists_ws) cudaFree(h->lists_ws);
-  if (h->zl_rows) cudaFree(h->zl_rows);
-  if (h->zl_frames) cudaFree(h->zl_frames);
-  if (h->zl_desc) cudaFree(h->zl_desc);
-  if (h->zl_status) cudaFree(h->zl_status);
-  if (h->zl_status_host) cudaFreeHost(h->zl_status_host);
-  if (h->zl_pin_rows) cudaFreeHost(h->zl_pin_rows);
-  if (h->zl_pin_frames) cudaFreeHost(h->zl_pin_frames);
-  if (h->zl_pin_desc) cudaFreeHost(h->zl_pin_desc);
+  for (auto& z : h->zl) {
+    if (z.rows) cudaFree(z.rows);
+    if (z.frames) cudaFree(z.frames);
+    if (z.desc) cudaFree(z.desc);
+    if (z.status) cudaFree(z.status);
+    if (z.status_host) cudaFreeHost(z.status_host);
+    if (z.pin_rows) cudaFreeHost(z.pin_rows);
+    if (z.pin_frames) cudaFreeHost(z.pin_frames);
+    if (z.pin_desc) cudaFreeHost(z.pin_desc);
+    for (cudaEvent_t e : {z.copied, z.decoded, z.freed, z.t_c0, z.t_c1, z.t_k0, z.t_k1, z.t_q0, z.t_q1})
+      if (e) cudaEventDestroy(e);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->odev) cudaFree(h->odev);
   if (h->opin) cudaFreeHost(h->opin);
   if (h->db) cudaFree(h->db);
@@ -1035,34 +1042,76 @@ int sgic_c2df_parse(const uint8_t* blob, const int64_t* offsets, int64_t n, int 
   return c2df_parse_batch(blob, offsets, n, dim, out_u8, status_out, dim_out, n_threads);
 }
 
-// Appends `w` rows staged in the index's pinned slab buffers: rows named by the `nf` descriptors are clip_stream
-// frames decoded on the device (K0) into the u8 matrix, the others were decoded by libzstd on the host and sit
-// in the matrix already; then K1 expands the matrix into the database.  *bad = true (and nothing appended) if
-// the device rejects a frame: the caller redoes the slab with libzstd, which stays the judge of malformed input.
-static int add_u8_with_frames(sgic_index* h, int64_t w, int64_t n_host_rows, size_t frames_bytes, int64_t nf64,
-                              bool* bad) {
+// ---- ingest pipeline stages (device-side clip_stream decode) ---------------------------------
+// A slab goes through: host (TLV walk + classification + pinned packing, n_threads) -> copy (H2D on the copy
+// stream) -> decode (K0 on the index's stream, status back) -> finalize (host checks the statuses, K1 expands the
+// u8 rows into the database, or libzstd redoes the slab).  Slabs are finalized in order, so rows keep file order.
+static int zl_slab_prepare(sgic_index* h, sgic_index::ZlSlab& z) {
   using namespace sgic;
-  *bad = false;
+  if (!h->copy_stream) SGIC_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&z.copied, &z.decoded, &z.freed})
+    if (!*e) SGIC_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  for (cudaEvent_t* e : {&z.t_c0, &z.t_c1, &z.t_k0, &z.t_k1, &z.t_q0, &z.t_q1})
+    if (!*e) SGIC_CUDA(cudaEventCreate(e));
+  return 0;
+}
+
+// "timing" option: per-phase device times of the slab that last used this set (events long complete by now)
+static int zl_slab_harvest(sgic_index* h, sgic_index::ZlSlab& z) {
+  if (!z.timed) return 0;
+  z.timed = false;
+  float ms = 0.f;
+  SGIC_CUDA(cudaEventSynchronize(z.t_q1));
+  SGIC_CUDA(cudaEventElapsedTime(&ms, z.t_c0, z.t_c1));
+  h->stat_ingest_h2d_ns += static_cast<int64_t>(ms * 1e6);
+  SGIC_CUDA(cudaEventElapsedTime(&ms, z.t_k0, z.t_k1));
+  h->stat_ingest_k0_ns += static_cast<int64_t>(ms * 1e6);
+  SGIC_CUDA(cudaEventElapsedTime(&ms, z.t_q0, z.t_q1));
+  h->stat_ingest_k1_ns += static_cast<int64_t>(ms * 1e6);
+  return 0;
+}
+
+// H2D of a packed slab on the copy stream; the set's device buffers are free once K1 of their previous slab ran
+static int zl_slab_copy(sgic_index* h, sgic_index::ZlSlab& z) {
+  using namespace sgic;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  int rc;
+  const size_t d = static_cast<size_t>(h->d);
+  const uint32_t nf = static_cast<uint32_t>(z.nf);
+  cudaStream_t cs = h->copy_stream;
+  if (z.used) SGIC_CUDA(cudaStreamWaitEvent(cs, z.freed, 0));
+  // device buffers sized for a FULL slab of typical frames the first time (a short first slab must not cost a
+  // reallocation — cudaFree / cudaFreeHost synchronise — when the next one is full)
+  const size_t n_full = static_cast<size_t>(std::max<int64_t>(z.full, z.w));
+  const size_t need_rows = n_full * d, need_frames = std::max(z.fbytes + 16, n_full * 640 + (1u << 20));
+  const size_t need_desc = std::max<size_t>(nf, n_full) * sizeof(ZlDesc), need_status = std::max<size_t>(nf, n_full) * 4;
+  const bool grow = need_rows > z.rows_bytes || need_frames > z.frames_bytes || need_desc > z.desc_bytes ||
+                    need_status > z.status_bytes;
+  if (grow) SGIC_CUDA(cudaDeviceSynchronize());  // (re)allocation: nothing may still use the old buffers
+  if ((rc = ensure_buf(&z.rows, &z.rows_bytes, need_rows, false))) return rc;
+  if ((rc = ensure_buf(&z.frames, &z.frames_bytes, need_frames, false))) return rc;
+  if ((rc = ensure_buf(&z.desc, &z.desc_bytes, need_desc, false))) return rc;
+  if ((rc = ensure_buf(&z.status, &z.status_bytes, need_status, false))) return rc;
+  if ((rc = ensure_buf(&z.status_host, &z.status_host_bytes, need_status, true))) return rc;
+  if (h->opt_timing) SGIC_CUDA(cudaEventRecord(z.t_c0, cs));
+  if (z.nh > 0) SGIC_CUDA(cudaMemcpyAsync(z.rows, z.pin_rows, static_cast<size_t>(z.w) * d, cudaMemcpyHostToDevice, cs));
+  SGIC_CUDA(cudaMemcpyAsync(z.frames, z.pin_frames, z.fbytes, cudaMemcpyHostToDevice, cs));
+  SGIC_CUDA(cudaMemcpyAsync(z.desc, z.pin_desc, static_cast<size_t>(nf) * sizeof(ZlDesc), cudaMemcpyHostToDevice, cs));
+  if (h->opt_timing) SGIC_CUDA(cudaEventRecord(z.t_c1, cs));
+  SGIC_CUDA(cudaEventRecord(z.copied, cs));
+  z.used = true;
+  return 0;
+}
+
+// K0 on the index's stream once the slab has landed; statuses come back to pinned memory
+static int zl_slab_decode(sgic_index* h, sgic_index::ZlSlab& z) {
+  using namespace sgic;
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   cudaStream_t st = h->stream;
-  int rc = ensure_capacity(h, h->ntotal + w, st);
-  if (rc) return rc;
-  const size_t d = static_cast<size_t>(h->d);
-  const uint32_t nf = static_cast<uint32_t>(nf64);
-  if ((rc = ensure_buf(&h->zl_rows, &h->zl_rows_bytes, static_cast<size_t>(w) * d, false))) return rc;
-  if ((rc = ensure_buf(&h->zl_frames, &h->zl_frames_bytes, frames_bytes + 16, false))) return rc;
-  if ((rc = ensure_buf(&h->zl_desc, &h->zl_desc_bytes, static_cast<size_t>(nf) * sizeof(ZlDesc), false))) return rc;
-  if ((rc = ensure_buf(&h->zl_status, &h->zl_status_bytes, static_cast<size_t>(nf) * 4, false))) return rc;
-  if ((rc = ensure_buf(&h->zl_status_host, &h->zl_status_host_bytes, static_cast<size_t>(nf) * 4, true))) return rc;
-  const bool tm = h->opt_timing != 0;  // per-phase device times (bench / probes only)
-  if (tm) SGIC_CUDA(cudaEventRecord(h->t0, st));
-  if (n_host_rows > 0)
-    SGIC_CUDA(cudaMemcpyAsync(h->zl_rows, h->zl_pin_rows, static_cast<size_t>(w) * d, cudaMemcpyHostToDevice, st));
-  SGIC_CUDA(cudaMemcpyAsync(h->zl_frames, h->zl_pin_frames, frames_bytes, cudaMemcpyHostToDevice, st));
-  SGIC_CUDA(cudaMemcpyAsync(h->zl_desc, h->zl_pin_desc, static_cast<size_t>(nf) * sizeof(ZlDesc),
-                            cudaMemcpyHostToDevice, st));
-  if (tm) SGIC_CUDA(cudaEventRecord(h->tm, st));
+  const uint32_t nf = static_cast<uint32_t>(z.nf);
+  SGIC_CUDA(cudaStreamWaitEvent(st, z.copied, 0));
   const size_t smem = static_cast<size_t>(kZlWarpsPerBlock) * sizeof(ZlWarpSmem);  // ~71 KB: 3 CTAs per SM
   static bool zl_configured[64] = {false};
   if (!zl_configured[h->device & 63]) {
@@ -1072,42 +1121,50 @@ static int add_u8_with_frames(sgic_index* h, int64_t w, int64_t n_host_rows, siz
   }
   const unsigned grid = std::min<unsigned>((nf + kZlWarpsPerBlock - 1) / kZlWarpsPerBlock,
                                            static_cast<unsigned>(h->sm_count) * 3u);
+  if (h->opt_timing) SGIC_CUDA(cudaEventRecord(z.t_k0, st));
   zstd_lit_decode_kernel<<<grid, kZlWarpsPerBlock * 32, smem, st>>>(
-      static_cast<const uint8_t*>(h->zl_frames), static_cast<const ZlDesc*>(h->zl_desc), nf, static_cast<uint32_t>(d),
-      static_cast<uint8_t*>(h->zl_rows), static_cast<int32_t*>(h->zl_status));
+      static_cast<const uint8_t*>(z.frames), static_cast<const ZlDesc*>(z.desc), nf, static_cast<uint32_t>(h->d),
+      static_cast<uint8_t*>(z.rows), static_cast<int32_t*>(z.status));
   h->stat_launches++;
   SGIC_CUDA(cudaGetLastError());
-  if (tm) SGIC_CUDA(cudaEventRecord(h->t1, st));
-  SGIC_CUDA(cudaMemcpyAsync(h->zl_status_host, h->zl_status, static_cast<size_t>(nf) * 4, cudaMemcpyDeviceToHost, st));
-  SGIC_CUDA(cudaStreamSynchronize(st));
-  if (tm) {
-    float ms = 0.f;
-    SGIC_CUDA(cudaEventElapsedTime(&ms, h->t0, h->tm));
-    h->stat_ingest_h2d_ns += static_cast<int64_t>(ms * 1e6);
-    SGIC_CUDA(cudaEventElapsedTime(&ms, h->tm, h->t1));
-    h->stat_ingest_k0_ns += static_cast<int64_t>(ms * 1e6);
-  }
-  const int32_t* stt = static_cast<const int32_t*>(h->zl_status_host);
-  for (uint32_t i = 0; i < nf; ++i)
+  if (h->opt_timing) SGIC_CUDA(cudaEventRecord(z.t_k1, st));
+  SGIC_CUDA(cudaMemcpyAsync(z.status_host, z.status, static_cast<size_t>(nf) * 4, cudaMemcpyDeviceToHost, st));
+  SGIC_CUDA(cudaEventRecord(z.decoded, st));
+  return 0;
+}
+
+// Waits for the slab's statuses; all good: K1 appends its rows (asynchronously, stream-ordered before whatever
+// touches the database next).  *bad = true (nothing appended) if the device rejected a frame: the caller redoes
+// the slab with libzstd, which stays the judge of malformed input.
+static int zl_slab_finalize(sgic_index* h, sgic_index::ZlSlab& z, bool* bad) {
+  using namespace sgic;
+  *bad = false;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->stream;
+  SGIC_CUDA(cudaEventSynchronize(z.decoded));
+  const int32_t* stt = static_cast<const int32_t*>(z.status_host);
+  for (int64_t i = 0; i < z.nf; ++i)
     if (stt[i] != zl::ZL_OK) {
       *bad = true;
+      SGIC_CUDA(cudaEventRecord(z.freed, st));
       return 0;
     }
-  if (tm) SGIC_CUDA(cudaEventRecord(h->t0, st));
-  rc = launch_dequant_u8(h, static_cast<const uint8_t*>(h->zl_rows), h->ntotal, w, st);
+  int rc = ensure_capacity(h, h->ntotal + z.w, st);
   if (rc) return rc;
-  if (tm) SGIC_CUDA(cudaEventRecord(h->t1, st));
-  SGIC_CUDA(cudaStreamSynchronize(st));
-  if (tm) {
-    float ms = 0.f;
-    SGIC_CUDA(cudaEventElapsedTime(&ms, h->t0, h->t1));
-    h->stat_ingest_k1_ns += static_cast<int64_t>(ms * 1e6);
+  if (h->opt_timing) SGIC_CUDA(cudaEventRecord(z.t_q0, st));
+  rc = launch_dequant_u8(h, static_cast<const uint8_t*>(z.rows), h->ntotal, z.w, st);
+  if (rc) return rc;
+  if (h->opt_timing) {
+    SGIC_CUDA(cudaEventRecord(z.t_q1, st));
+    z.timed = true;
   }
+  SGIC_CUDA(cudaEventRecord(z.freed, st));
   h->retain_ok = false;
   h->retained.clear();
-  h->ntotal += w;
-  h->stat_zl_device_frames += nf;
-  h->stat_zl_host_rows += n_host_rows;
+  h->ntotal += z.w;
+  h->stat_zl_device_frames += z.nf;
+  h->stat_zl_host_rows += z.nh;
   return 0;
 }
 
@@ -1123,7 +1180,7 @@ int sgic_index_add_c2df(sgic_index* h, const uint8_t* blob, const int64_t* offse
   // previous chunk inside add_u8).  Device decode: the host walks the TLV container, lets libzstd decode only the
   // frames outside the device profile, and packs ~300-byte frames into pinned memory (all on n_threads threads);
   // one H2D + K0 + K1 per slab.
-  const int64_t slab = dev_dec ? 131072 : std::max<int64_t>(1, static_cast<int64_t>((256u << 20) / d));
+  const int64_t slab = dev_dec ? 65536 : std::max<int64_t>(1, static_cast<int64_t>((256u << 20) / d));
   struct RawBuf {  // uninitialised host rows (a std::vector would memset 64 MB per slab)
     uint8_t* p = nullptr;
     size_t cap = 0;
@@ -1160,66 +1217,105 @@ int sgic_index_add_c2df(sgic_index* h, const uint8_t* blob, const int64_t* offse
     }
     return 0;
   };
-  for (int64_t s0 = 0; s0 < n; s0 += slab) {
-    const int64_t cnt = std::min(slab, n - s0);
-    SGIC_REQUIRE(rows.resize(static_cast<size_t>(cnt) * d), "out of host memory for the row slab");
-    if (!dev_dec) {
+  auto now_ns = [] {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch())
+        .count();
+  };
+  if (!dev_dec) {
+    for (int64_t s0 = 0; s0 < n; s0 += slab) {
+      const int64_t cnt = std::min(slab, n - s0);
+      SGIC_REQUIRE(rows.resize(static_cast<size_t>(cnt) * d), "out of host memory for the row slab");
       int rc = host_route(s0, cnt, true);
       if (rc) return rc;
-      continue;
     }
-    foff.resize(static_cast<size_t>(cnt));
-    flen.resize(static_cast<size_t>(cnt));
-    auto now_ns = [] {
-      return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch())
-          .count();
-    };
-    const int64_t t_a = now_ns();
-    int rc = sgic::c2df_parse_batch(blob, offsets + s0, cnt, h->d, rows.data(), status_out + s0, nullptr, n_threads,
-                                    foff.data(), flen.data());
-    if (rc) return rc;
-    const int64_t t_b = now_ns();
-    h->stat_ingest_parse_ns += t_b - t_a;
-    int64_t w = 0, nf = 0, nh = 0;
-    size_t fbytes = 0;
-    {
-      std::lock_guard<std::mutex> lk(h->mu);
-      sgic::DeviceGuard g(h->device);
-      // pinned slab buffers: sized once for a full slab of typical frames (grown only if a slab needs more)
-      const size_t frames_need = static_cast<size_t>(slab) * 640 + (1u << 20);
-      if ((rc = sgic::ensure_buf(&h->zl_pin_rows, &h->zl_pin_rows_bytes, static_cast<size_t>(slab) * d, true))) return rc;
-      if ((rc = sgic::ensure_buf(&h->zl_pin_desc, &h->zl_pin_desc_bytes, static_cast<size_t>(slab) * sizeof(sgic::ZlDesc), true)))
-        return rc;
-      size_t need = 0;
-      for (int64_t i = 0; i < cnt; ++i)
-        if (status_out[s0 + i] == SGIC_C2DF_OK && foff[static_cast<size_t>(i)] >= 0)
-          need += (static_cast<size_t>(flen[static_cast<size_t>(i)]) + 15u) & ~static_cast<size_t>(15);
-      if ((rc = sgic::ensure_buf(&h->zl_pin_frames, &h->zl_pin_frames_bytes, std::max(need + 16, frames_need), true)))
-        return rc;
-    }
-    rc = sgic::c2df_pack_batch(blob, cnt, h->d, status_out + s0, foff.data(), flen.data(), rows.data(),
-                               static_cast<uint8_t*>(h->zl_pin_rows), static_cast<uint8_t*>(h->zl_pin_frames),
-                               h->zl_pin_frames_bytes, static_cast<sgic::ZlDesc*>(h->zl_pin_desc), &w, &nf, &nh, &fbytes,
-                               n_threads);
-    if (rc) return rc;
-    const int64_t t_c = now_ns();
-    h->stat_ingest_pack_ns += t_c - t_b;
-    if (w == 0) continue;
-    if (nf == 0) {  // nothing for the device in this slab
-      rc = host_route(s0, cnt, false);
+    if (n_added) *n_added = added;
+    return 0;
+  }
+  // Device decode, pipelined: step i = host work of slab i, then finalize slab i-2 (its K0 ran under the host work of
+  // slabs i-1 and i), then enqueue copy + K0 of slab i (the copy overlaps K0 of slab i-1).
+  constexpr int kDepth = sgic_index::kZlDepth;
+  const int64_t n_slabs = (n + slab - 1) / slab;
+  auto finalize = [&](sgic_index::ZlSlab& z) -> int {
+    int rc = 0;
+    if (z.mode == 1) {
+      const int64_t t0 = now_ns();
+      bool bad = false;
+      rc = zl_slab_finalize(h, z, &bad);
+      h->stat_ingest_gpu_ns += now_ns() - t0;   // host time spent waiting for the device
       if (rc) return rc;
-      continue;
+      if (bad) {  // a frame the device could not decode: libzstd decides for the whole slab
+        h->stat_zl_fallback_slabs++;
+        SGIC_REQUIRE(rows.resize(static_cast<size_t>(z.cnt) * d), "out of host memory for the row slab");
+        rc = host_route(z.s0, z.cnt, true);
+      } else {
+        added += z.w;
+      }
+    } else if (z.mode == 2) {  // nothing for the device in this slab
+      SGIC_REQUIRE(rows.resize(static_cast<size_t>(z.cnt) * d), "out of host memory for the row slab");
+      rc = host_route(z.s0, z.cnt, true);
     }
-    bool bad = false;
-    rc = add_u8_with_frames(h, w, nh, fbytes, nf, &bad);
-    if (rc) return rc;
-    h->stat_ingest_gpu_ns += now_ns() - t_c;
-    if (bad) {  // a frame the device could not decode: libzstd decides for the whole slab
-      h->stat_zl_fallback_slabs++;
-      rc = host_route(s0, cnt, true);
+    z.mode = 0;
+    return rc;
+  };
+  for (int64_t i = 0; i < n_slabs + (kDepth - 1); ++i) {
+    if (i < n_slabs) {
+      sgic_index::ZlSlab& z = h->zl[i % kDepth];
+      const int64_t s0 = i * slab, cnt = std::min(slab, n - s0);
+      z.s0 = s0;
+      z.cnt = cnt;
+      z.full = slab;
+      z.mode = 0;
+      SGIC_REQUIRE(rows.resize(static_cast<size_t>(cnt) * d), "out of host memory for the row slab");
+      foff.resize(static_cast<size_t>(cnt));
+      flen.resize(static_cast<size_t>(cnt));
+      const int64_t t_a = now_ns();
+      int rc = sgic::c2df_parse_batch(blob, offsets + s0, cnt, h->d, rows.data(), status_out + s0, nullptr, n_threads,
+                                      foff.data(), flen.data());
       if (rc) return rc;
-    } else {
-      added += w;
+      const int64_t t_b = now_ns();
+      h->stat_ingest_parse_ns += t_b - t_a;
+      {
+        std::lock_guard<std::mutex> lk(h->mu);
+        sgic::DeviceGuard g(h->device);
+        if ((rc = zl_slab_prepare(h, z))) return rc;
+        if ((rc = zl_slab_harvest(h, z))) return rc;
+        // pinned slab buffers: sized once for a full slab of typical frames (grown only if a slab needs more);
+        // the previous slab of this set was finalized two steps ago, so nothing reads them any more
+        const size_t frames_need = static_cast<size_t>(slab) * 640 + (1u << 20);
+        if ((rc = sgic::ensure_buf(&z.pin_rows, &z.pin_rows_bytes, static_cast<size_t>(slab) * d, true))) return rc;
+        if ((rc = sgic::ensure_buf(&z.pin_desc, &z.pin_desc_bytes, static_cast<size_t>(slab) * sizeof(sgic::ZlDesc), true)))
+          return rc;
+        size_t need = 0;
+        for (int64_t j = 0; j < cnt; ++j)
+          if (status_out[s0 + j] == SGIC_C2DF_OK && foff[static_cast<size_t>(j)] >= 0)
+            need += (static_cast<size_t>(flen[static_cast<size_t>(j)]) + 15u) & ~static_cast<size_t>(15);
+        if ((rc = sgic::ensure_buf(&z.pin_frames, &z.pin_frames_bytes, std::max(need + 16, frames_need), true))) return rc;
+      }
+      rc = sgic::c2df_pack_batch(blob, cnt, h->d, status_out + s0, foff.data(), flen.data(), rows.data(),
+                                 static_cast<uint8_t*>(z.pin_rows), static_cast<uint8_t*>(z.pin_frames),
+                                 z.pin_frames_bytes, static_cast<sgic::ZlDesc*>(z.pin_desc), &z.w, &z.nf, &z.nh, &z.fbytes,
+                                 n_threads);
+      if (rc) return rc;
+      h->stat_ingest_pack_ns += now_ns() - t_b;
+      z.mode = z.w == 0 ? 0 : (z.nf == 0 ? 2 : 1);
+    }
+    if (i >= kDepth - 1) {
+      int rc = finalize(h->zl[(i - (kDepth - 1)) % kDepth]);
+      if (rc) return rc;
+    }
+    if (i < n_slabs && h->zl[i % kDepth].mode == 1) {
+      int rc = zl_slab_copy(h, h->zl[i % kDepth]);
+      if (rc) return rc;
+      if ((rc = zl_slab_decode(h, h->zl[i % kDepth]))) return rc;
+    }
+  }
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    sgic::DeviceGuard g(h->device);
+    SGIC_CUDA(cudaStreamSynchronize(h->stream));  // the last K1s: the rows are in the database when the call returns
+    for (auto& z : h->zl) {
+      int rc = zl_slab_harvest(h, z);
+      if (rc) return rc;
     }
   }
   if (n_added) *n_added = added;
