@@ -39,7 +39,24 @@ struct ScanSmallParams {
   float* D;              // [nq][k]
   long long* I;          // [nq][k]
   long long id_base;
+  // k > 1024 runs as several passes of <= 1024: a pass only admits candidates whose key lies strictly below
+  // *bound (the last key the previous pass returned; device memory, nullptr / 0 = no bound).  Keys order
+  // candidates by (score desc, id asc), so the passes enumerate the answer in order without gaps or repeats.
+  const uint64_t* bound;
 };
+
+// next pass's bound = key of the last answer slot of this pass (1 = "nothing left" if that slot is padding)
+__global__ void next_bound_kernel(const float* D, const long long* I, uint32_t last, long long id_base, uint64_t* bound) {
+  const long long id = I[last];
+  *bound = id < 0 ? 1ull : make_key(D[last], static_cast<uint32_t>(id - id_base));
+}
+__global__ void fill_padding_kernel(float* D, long long* I, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    D[i] = kNegFltMax;
+    I[i] = -1;
+  }
+}
 
 template <typename T>
 __device__ __forceinline__ uint32_t pack2(float a, float b);
@@ -123,6 +140,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanS
     float thr[NQ];
 #pragma unroll
     for (int qi = 0; qi < NQ; ++qi) thr[qi] = -INFINITY;
+    const uint64_t bound = p.bound ? *p.bound : 0ull;
 
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -203,8 +221,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanS
         const int se = src >> (5 - L);
         const int sq = se / RB, sj = se % RB;
         const uint32_t id = row0 + warp * RB + sj;
+        const uint64_t key = make_key(sv, id);
+        if (bound != 0ull && key >= bound) continue;  // returned by an earlier pass (warp-uniform)
         uint64_t* Lq = lists + (static_cast<size_t>(sq) * W + warp) * p.kp;
-        const uint64_t kth = warp_list_insert(Lq, static_cast<int>(p.k), make_key(sv, id), lane);
+        const uint64_t kth = warp_list_insert(Lq, static_cast<int>(p.k), key, lane);
         const float nt = (kth == 0ull) ? -INFINITY : key_score(kth);
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi)

@@ -81,6 +81,8 @@ struct sgic_index {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   // search workspaces
   void* ws = nullptr;  // partial keys (+ the fused merge's CTA counter)
+  void* ws2 = nullptr;  // k > 1024: the bound handed from one pass to the next
+  size_t ws2_bytes = 0;
   uint32_t* ws_counter = nullptr;
   size_t ws_bytes = 0;
   void* qh = nullptr;  // queries rounded to the storage dtype (dense path operand A)
@@ -667,28 +669,71 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
 }
 
 static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
-                             int64_t id_base, cudaStream_t st);
+                             int64_t id_base, cudaStream_t st, const uint64_t* bound = nullptr);
+
+// Smallest batch that goes to the tensor-core kernels ("dense_min_nq" overrides).  K3 owns lanes by 256-element
+// slabs of a row (8 elements per lane and chunk): at d = 512 / 768 / 1024 / 2048 every lane works and one query
+// streams at 7.4 TB/s, but narrow rows (d <= 128: 5.4 TB/s, d = 64: 2.7 TB/s) and widths that fill the last
+// template instance badly (d = 1280: 6.1 TB/s) leave lanes idle — there even a single query is better off on the
+// transposed kernel (7.1-7.3 TB/s at every width, profiles/r01_dims.log) once the shard is large enough to hide
+// its extra launches.
+static int64_t auto_dense_min_nq(const sgic_index* h) {
+  if (h->opt_dense_min_nq != 0) return h->opt_dense_min_nq;
+  const ScanCfg cfg = scan_cfg_for_d(h->d);
+  const double lane_util = static_cast<double>(h->d) / (cfg.cpl * 256.0);
+  if (h->ntotal >= (2ll << 20) && lane_util < 0.7) return 1;
+  return (h->ntotal >= (8ll << 20)) ? 2 : 3;
+}
 
 // Searches `nq` device-resident fp32 queries; results to device buffers.  Regime choice: a few
 // queries -> K3 (CUDA-core streaming scan, HBM-bound); batches -> K4 (tcgen05 dense contraction).
 static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
                            int64_t id_base, cudaStream_t st) {
   SGIC_REQUIRE(k >= 1, "k must be >= 1");
-  SGIC_REQUIRE(k <= kMaxK, "k > 1024 is not supported by this build");
   SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
   if (nq == 0) return 0;
   SGIC_REQUIRE(h->ntotal < (1ll << 32) - 1, "more than 2^32-2 rows in one shard");
+  if (k > kMaxK) {
+    // FAISS takes any k (do_search asks for min(topk, ntotal), src/search.py:114).  Beyond 1024 the answer is
+    // enumerated in passes of <= 1024 by K3, one query at a time: pass p only admits keys strictly below the last
+    // key of pass p-1 (the bound stays on the device), so the concatenation is the exact ordered top-k.
+    SGIC_REQUIRE(k <= (1ll << 24), "k too large");
+    const int64_t valid = std::min<int64_t>(k, h->ntotal);
+    if (32 > h->ws2_bytes) {
+      SGIC_CUDA(cudaStreamSynchronize(st));
+      int rc = ensure_buf(&h->ws2, &h->ws2_bytes, 32, false);
+      if (rc) return rc;
+    }
+    uint64_t* bound = static_cast<uint64_t*>(h->ws2);
+    for (int64_t q = 0; q < nq; ++q) {
+      float* Dq = dev_D + q * k;
+      int64_t* Iq = dev_I + q * k;
+      for (int64_t got = 0; got < valid; got += kMaxK) {
+        const int64_t kk = std::min<int64_t>(kMaxK, valid - got);
+        int rc = search_small_impl(h, 1, dev_q + q * h->d, kk, Dq + got, Iq + got, id_base, st, got ? bound : nullptr);
+        if (rc) return rc;
+        if (got + kk < valid)
+          next_bound_kernel<<<1, 1, 0, st>>>(Dq + got, reinterpret_cast<const long long*>(Iq + got),
+                                             static_cast<uint32_t>(kk - 1), id_base, bound);
+      }
+      if (valid < k) {
+        const uint32_t pad = static_cast<uint32_t>(k - valid);
+        fill_padding_kernel<<<(pad + 255) / 256, 256, 0, st>>>(Dq + valid, reinterpret_cast<long long*>(Iq + valid), pad);
+      }
+      SGIC_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
   // Regime choice (measured, 512-d fp16): one query -> K3.  Two queries -> K3 on small shards (one launch), the
   // transposed tensor-core kernel from ~8M rows (100M rows: 14.2 ms against K3's 15.8 ms).  Three or more ->
   // tensor cores always (K3 with 4 queries is FMA-bound: 18.5 ms at 100M rows against 15.4 ms).
-  int64_t min_nq = h->opt_dense_min_nq;
-  if (min_nq == 0) min_nq = (h->ntotal >= (8ll << 20)) ? 2 : 3;
+  const int64_t min_nq = auto_dense_min_nq(h);
   if (h->ntotal > 0 && nq >= min_nq) return search_dense_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st);
   return search_small_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st);
 }
 
 static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
-                             int64_t id_base, cudaStream_t st) {
+                             int64_t id_base, cudaStream_t st, const uint64_t* bound) {
   SGIC_REQUIRE(k >= 1, "k must be >= 1");
   SGIC_REQUIRE(k <= kMaxK, "k > 1024 is not supported by this build");
   SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
@@ -760,6 +805,7 @@ static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.D = dev_D + static_cast<size_t>(q0) * k;
     p.I = reinterpret_cast<long long*>(dev_I + static_cast<size_t>(q0) * k);
     p.id_base = id_base;
+    p.bound = bound;
     cudaError_t e;
     if (n_rows > 0) {
       if (h->dtype == SGIC_F16) e = launch_scan_t<__half>(p, NQ, cfg.cpl, cfg.rb, grid, smem, st);
@@ -874,6 +920,7 @@ int sgic_index_destroy(sgic_index* h) {
   if (h->qdev) cudaFree(h->qdev);
   if (h->qh) cudaFree(h->qh);
   if (h->lists_ws) cudaFree(h->lists_ws);
+  if (h->ws2) cudaFree(h->ws2);
   for (auto& z : h->zl) {
     if (z.rows) cudaFree(z.rows);
     if (z.frames) cudaFree(z.frames);
@@ -1873,7 +1920,7 @@ int64_t sgic_index_get_stat(const sgic_index* h, const char* name) {
   if (n == "last_kernel") return h->stat_last_kernel;
   if (n == "capacity") return h->capacity;
   if (n == "sm_count") return h->sm_count;
-  if (n == "dense_min_nq") return h->opt_dense_min_nq ? h->opt_dense_min_nq : ((h->ntotal >= (8ll << 20)) ? 2 : 3);
+  if (n == "dense_min_nq") return auto_dense_min_nq(h);
   if (n == "ingest_h2d_ns") return h->stat_ingest_h2d_ns;
   if (n == "ingest_k0_ns") return h->stat_ingest_k0_ns;
   if (n == "ingest_k1_ns") return h->stat_ingest_k1_ns;

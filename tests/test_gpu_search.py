@@ -115,3 +115,33 @@ def test_argument_errors():
         faiss.IndexFlatIP(513, device=0)
     with pytest.raises(RuntimeError):
         faiss.read_index("/nonexistent/index.faiss")
+
+
+@pytest.mark.parametrize("n,nq,k", [(5000, 3, 2500), (5000, 2, 5000), (3000, 1, 7000), (40000, 2, 1025), (2049, 1, 2048)])
+def test_k_beyond_1024_runs_in_passes(n, nq, k):
+    """FAISS takes any k (do_search asks for min(topk, ntotal), src/search.py:114).  Beyond 1024 the answer is
+    enumerated in passes of <= 1024, each bounded by the last key of the previous one: the concatenation must be
+    the exact ordered top-k — including runs of exact ties that straddle a pass boundary — padded when k > n."""
+    from sgic_b200 import faiss_compat as faiss
+    rng = np.random.default_rng(n + k)
+    base = unit(rng, n // 2, 512)
+    xb = np.concatenate([base, base, unit(rng, n - 2 * (n // 2), 512)])        # every score appears twice: ties everywhere
+    xq = unit(rng, nq, 512)
+    idx = faiss.IndexFlatIP(512, device=0)
+    idx.add(xb)
+    D, I = idx.search(xq, k)
+    assert D.shape == (nq, k) and I.shape == (nq, k)
+    kk = min(k, n)
+    assert np.all(I[:, kk:] == -1) and np.all(D[:, kk:] == np.float32(-3.4028234663852886e38))
+    for r in range(nq):
+        ids = I[r, :kk]
+        assert len(set(ids.tolist())) == kk and ids.min() >= 0 and ids.max() < n     # no repeats, no gaps
+        assert np.all(np.diff(D[r, :kk]) <= 0)
+        pairs = list(zip((-D[r, :kk]).tolist(), ids.tolist()))
+        assert pairs == sorted(pairs)                                              # (score desc, id asc) throughout
+    check_topk(D, I, rounded(xb, "fp16"), rounded(xq, "fp16"), k, score_tol=3e-5, tie_tol=1e-6)
+    # the first 1024 are what a k = 1024 search returns (a batch may take the tensor-core kernel there: same ids,
+    # scores equal up to the accumulation order)
+    D1, I1 = idx.search(xq, 1024)
+    assert np.array_equal(I[:, :1024], I1)
+    np.testing.assert_allclose(D[:, :1024], D1, atol=2e-5, rtol=0)
