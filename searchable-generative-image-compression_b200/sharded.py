@@ -141,6 +141,7 @@ class ShardedIndexFlatIP(Index):
             self._dev = torch.device("cpu")
         self.local = local_factory(d) if local_factory else IndexFlatIP(d, dtype=dtype, device=dev, retain_fp32=False)
         self._merge = merge_fn or _merge_cuda
+        self._pin_q = self._pin_D = self._pin_I = None
         self._peer = None
         import os
         if (self._cuda and self.world > 1 and merge_fn is None
@@ -276,9 +277,26 @@ class ShardedIndexFlatIP(Index):
         x = np.ascontiguousarray(x, dtype="float32")
         assert x.ndim == 2 and x.shape[1] == self._d, "search expects (n, d)"
         assert k > 0, "k must be positive"
-        q = torch.from_numpy(x).to(self._dev, non_blocking=False)
+        if not self._cuda:
+            D, I = self.search_torch(torch.from_numpy(x).to(self._dev), k)
+            return D.cpu().numpy(), I.cpu().numpy()
+        # pinned staging both ways, one synchronisation per call (what sgic_index_search does on one GPU)
+        nq = x.shape[0]
+        need_in, need_out = nq * self._d, nq * k
+        if self._pin_q is None or self._pin_q.numel() < need_in:
+            self._pin_q = torch.empty(max(need_in, 1 << 16), dtype=torch.float32).pin_memory()
+        if self._pin_D is None or self._pin_D.numel() < need_out:
+            self._pin_D = torch.empty(max(need_out, 1 << 14), dtype=torch.float32).pin_memory()
+            self._pin_I = torch.empty(max(need_out, 1 << 14), dtype=torch.int64).pin_memory()
+        pq = self._pin_q[:need_in].view(nq, self._d)
+        pq.copy_(torch.from_numpy(x))
+        q = pq.to(self._dev, non_blocking=True)
         D, I = self.search_torch(q, k)
-        return D.cpu().numpy(), I.cpu().numpy()
+        pD, pI = self._pin_D[:need_out].view(nq, k), self._pin_I[:need_out].view(nq, k)
+        pD.copy_(D, non_blocking=True)
+        pI.copy_(I, non_blocking=True)
+        torch.cuda.current_stream(self._dev).synchronize()
+        return pD.numpy().copy(), pI.numpy().copy()
 
     # ---------------------------------------------------------------- persistence (SGI2 shard files)
     @staticmethod
