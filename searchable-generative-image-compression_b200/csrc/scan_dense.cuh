@@ -18,14 +18,16 @@
 // Work split: items = (query tile m, database slice s), m fastest, dealt round-robin to the CTAs (pairs), so the
 // CTAs that run concurrently share a few slices and re-use each other's database tiles from L2 while they stay
 // close (10M rows: 12.7 GB read from DRAM for a 10.2 GB database; 100M rows: the query tiles drift apart over
-// 10.5k tiles and DRAM reads grow to 988 GB — 34 % of DRAM peak, not the bound.  Two attempts to restore the
-// sharing were measured and dropped: shorter slices (host's slice comment) and a bounded soft lockstep of the
-// producers through progress counters in global memory (nq = 4096: 358-373 ms against 370 ms, nq = 1024: 17 %
-// slower) — the batch regime is limited by the power cap on the tensor pipe, not by DRAM).  A CTA parks
-// a query tile's top-k list in its own slot of `partial` at the end of an item and resumes it — threshold
-// included — if it visits that tile again; merge_keys_*_kernel merges the CTAs' lists at the end.
+// 10.5k tiles and DRAM reads grow to 988 GB).  Shorter slices and a soft lockstep of the producers were measured
+// and dropped; what removes the re-reads by construction is scan_dense2b_kernel at the end of this file (the
+// database tile stays, the queries stream) — and the measurement that both run at the same speed shows the batch
+// regime is limited by the power cap on the tensor pipe, not by DRAM.
+// Lists: every (query tile, slice) item is visited once and writes list `slice` of its queries in `partial`
+// ([nq][n_slices][k]); merge_keys_*_kernel merges the slices' lists.  Items of one query that run later inherit the
+// score bound earlier ones published (gthr).  (The optional short-slice schedule revisits query tiles instead: a
+// CTA then parks a tile's list in its own slot and resumes it, threshold included.)
 //
-// Two kernels:
+// Kernels (plus scan_dense_t_kernel for small batches and scan_dense2b_kernel for very large shards, below):
 //   scan_dense_kernel   cta_group::1 — 128 queries x 256 rows per CTA; A and B both streamed per K chunk.
 //   scan_dense2_kernel  cta_group::2 — a CTA PAIR (cluster of 2 on one TPC) computes 256 queries x 256 rows:
 //                       each CTA holds 128 queries (its TMEM lanes) and loads HALF of the database tile; the
@@ -44,7 +46,7 @@ constexpr int kDenseBM = 128;       // queries per CTA (TMEM lanes)
 constexpr int kDenseBK = 64;        // K chunk: 64 x 16-bit = one 128-byte swizzle row
 
 struct DenseParams {
-  uint64_t* partial;   // [nq][n_lists][k] keys: list `u` of a query belongs to CTA (pair) u, zeroed before the launch
+  uint64_t* partial;   // [nq][n_lists][k] keys (list = slice, or CTA (pair) when lists are parked and resumed)
   uint64_t* lists_ws;  // k > 32: [grid][128][res_cap] reservoirs (L2-resident workspace)
   uint32_t* gthr;      // [nq] by_slice only, zeroed before the launch: per query, the largest "k rows score above
                        // this" bound any finished item has published (order-preserving uint of the score just
