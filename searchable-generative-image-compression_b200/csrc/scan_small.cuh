@@ -36,6 +36,12 @@ struct ScanSmallParams {
   // fused final merge: the last CTA to finish merges every CTA's list and writes the answer
   uint32_t fused;        // 0: partial lists only (merge_keys_kernel follows)
   uint32_t* counter;     // zero on entry, reset to zero by the last CTA
+  // Tiles [0, n_static) are dealt round-robin (tile = cta + i * grid: equal shares); the rest is claimed two at a
+  // time from *steal (zero on entry; reset by the last CTA when fused, by the host otherwise).  CTAs do not stream
+  // at the same pace (per-CTA %globaltimer stamps, 1M rows: first done at 140.6 us, last at 147.6 us; 12.5M rows:
+  // 1687 / 1732 us) — with equal shares the slowest sets the time, with a shared tail they finish together.
+  uint32_t n_static;
+  uint32_t* steal;
   float* D;              // [nq][k]
   long long* I;          // [nq][k]
   long long id_base;
@@ -43,6 +49,9 @@ struct ScanSmallParams {
   // *bound (the last key the previous pass returned; device memory, nullptr / 0 = no bound).  Keys order
   // candidates by (score desc, id asc), so the passes enumerate the answer in order without gaps or repeats.
   const uint64_t* bound;
+  // "trace" option: per CTA, %globaltimer at kernel entry / end of the scan / lists written / kernel exit
+  // ([gridDim.x][4] u64, nullptr = off); scripts/probe_k3_trace.py turns it into the launch / ramp / tail picture
+  unsigned long long* trace;
 };
 
 // next pass's bound = key of the last answer slot of this pass (1 = "nothing left" if that slot is padding)
@@ -84,10 +93,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanS
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.n_stages) * p.stage_bytes);
   uint64_t* full_bar = lists + static_cast<size_t>(NQ) * W * p.kp;
   uint64_t* empty_bar = full_bar + kScanMaxStages;
+  uint32_t* stage_tile = reinterpret_cast<uint32_t*>(empty_bar + kScanMaxStages);  // tile in each stage (producer -> consumers)
+  constexpr uint32_t kEndOfStream = 0xffffffffu;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t row_bytes = p.d * 2u;
   const uint32_t n_chunks = p.d >> 3;  // 16-byte chunks per row
+  if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 0] = global_timer_ns();
 
   for (uint32_t i = tid; i < static_cast<uint32_t>(NQ) * W * p.kp; i += kScanThreads) lists[i] = 0ull;
   if (tid == 0) {
@@ -105,16 +117,30 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanS
       const uint64_t pol = p.evict_first ? ptx::policy_evict_first() : ptx::policy_evict_last();
       const uint8_t* db = static_cast<const uint8_t*>(p.db);
       uint32_t it = 0;
-      for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      auto issue = [&](uint32_t tile) {
         const uint32_t s = it % p.n_stages, use = it / p.n_stages;
         if (use > 0) ptx::mbar_wait(&empty_bar[s], (use - 1) & 1);
-        const uint32_t row0 = tile * R;
-        const uint32_t rows = min(static_cast<uint32_t>(R), p.n_rows - row0);
-        const uint32_t bytes = rows * row_bytes;
-        ptx::mbar_expect_tx(&full_bar[s], bytes);
-        ptx::bulk_g2s(stage_base + static_cast<size_t>(s) * p.stage_bytes,
-                      db + static_cast<size_t>(row0) * row_bytes, bytes, &full_bar[s], pol);
+        stage_tile[s] = tile;  // ordered before the consumers' wait by the arrive (release) below
+        if (tile == kEndOfStream) {
+          ptx::mbar_arrive(&full_bar[s]);
+        } else {
+          const uint32_t row0 = tile * R;
+          const uint32_t rows = min(static_cast<uint32_t>(R), p.n_rows - row0);
+          const uint32_t bytes = rows * row_bytes;
+          ptx::mbar_expect_tx(&full_bar[s], bytes);
+          ptx::bulk_g2s(stage_base + static_cast<size_t>(s) * p.stage_bytes,
+                        db + static_cast<size_t>(row0) * row_bytes, bytes, &full_bar[s], pol);
+        }
+        ++it;
+      };
+      for (uint32_t tile = blockIdx.x; tile < p.n_static; tile += gridDim.x) issue(tile);
+      while (true) {  // the shared tail: two tiles per claim (one atomic round trip per 64 KB streamed)
+        const uint32_t t0 = p.n_static + atomicAdd(p.steal, 2u);
+        if (t0 >= p.n_tiles) break;
+        issue(t0);
+        if (t0 + 1 < p.n_tiles) issue(t0 + 1);
       }
+      issue(kEndOfStream);
     }
   } else {
     // ------------------------------------------------------------ consumers
@@ -142,10 +168,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanS
     for (int qi = 0; qi < NQ; ++qi) thr[qi] = -INFINITY;
     const uint64_t bound = p.bound ? *p.bound : 0ull;
 
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    for (uint32_t it = 0;; ++it) {
       const uint32_t s = it % p.n_stages, use = it / p.n_stages;
       ptx::mbar_wait(&full_bar[s], use & 1);
+      const uint32_t tile = stage_tile[s];
+      if (tile == kEndOfStream) break;
       const uint32_t row0 = tile * R;
       const uint32_t rows = min(static_cast<uint32_t>(R), p.n_rows - row0);
       const uint8_t* sb = stage_base + static_cast<size_t>(s) * p.stage_bytes;
@@ -235,12 +262,27 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanS
 
   // ---------------------------------------------------------------- CTA merge of the W warp lists
   __syncthreads();
+  if (p.trace && tid == 0) p.trace[blockIdx.x * 4 + 1] = global_timer_ns();
   const uint32_t m = W * p.kp;  // power of two
-  for (uint32_t qi = 0; qi < p.nq; ++qi) {
-    uint64_t* Lq = lists + static_cast<size_t>(qi) * m;
-    block_bitonic_sort_desc(Lq, m);
-    uint64_t* dst = p.partial + (static_cast<size_t>(qi) * gridDim.x + blockIdx.x) * p.k;
-    for (uint32_t i = tid; i < p.k; i += kScanThreads) dst[i] = Lq[i];
+  if (p.k <= 64u) {
+    // short lists: warp qi merges the eight sorted warp lists of query qi head by head (k rounds of a 3-step
+    // warp max) — ~1 us instead of the 28 barrier-separated stages of the block-wide sort below
+    if (warp < static_cast<int>(p.nq)) {
+      uint64_t* dst = p.partial + (static_cast<size_t>(warp) * gridDim.x + blockIdx.x) * p.k;
+      warp_multiway_merge<1>(lists + static_cast<size_t>(warp) * m, W, p.kp, p.k, lane,
+                             [=](uint32_t r, uint64_t key) { dst[r] = key; });
+    }
+  } else {
+    for (uint32_t qi = 0; qi < p.nq; ++qi) {
+      uint64_t* Lq = lists + static_cast<size_t>(qi) * m;
+      block_bitonic_sort_desc(Lq, m);
+      uint64_t* dst = p.partial + (static_cast<size_t>(qi) * gridDim.x + blockIdx.x) * p.k;
+      for (uint32_t i = tid; i < p.k; i += kScanThreads) dst[i] = Lq[i];
+    }
+  }
+  if (p.trace) {
+    __syncthreads();
+    if (tid == 0) p.trace[blockIdx.x * 4 + 2] = p.trace[blockIdx.x * 4 + 3] = global_timer_ns();
   }
   if (!p.fused) return;
 
@@ -267,7 +309,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanS
     warp_multiway_merge<kMergeMaxLpl>(all + static_cast<size_t>(warp) * per_q, gridDim.x, p.k, p.k, lane,
                                       [=](uint32_t r, uint64_t key) { store_answer(D, I, o0 + r, key, base); });
   }
-  if (tid == 0) *p.counter = 0u;
+  if (tid == 0) {
+    *p.counter = 0u;
+    *p.steal = 0u;
+  }
+  if (p.trace) {
+    __syncthreads();
+    if (tid == 0) p.trace[blockIdx.x * 4 + 3] = global_timer_ns();
+  }
 }
 
 }  // namespace sgic

@@ -122,7 +122,7 @@ struct sgic_index {
   int64_t shard_row_start = 0, shard_total_rows = -1;
   int shard_id = 0, shard_count = 1;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1, opt_trace = 0, opt_steal = 1;
   int64_t stat_ingest_h2d_ns = 0, stat_ingest_k0_ns = 0, stat_ingest_k1_ns = 0;
   int64_t stat_ingest_parse_ns = 0, stat_ingest_pack_ns = 0, stat_ingest_gpu_ns = 0;
   int64_t stat_zl_device_frames = 0, stat_zl_host_rows = 0, stat_zl_fallback_slabs = 0;
@@ -748,7 +748,7 @@ static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
   const uint32_t R = kScanConsumerWarps * cfg.rb;
   const uint32_t stage_bytes = ((R * h->d * 2u) + 127u) & ~127u;
   const size_t list_bytes = static_cast<size_t>(NQ) * kScanConsumerWarps * kp * 8;
-  const size_t bar_bytes = 2 * kScanMaxStages * 8;
+  const size_t bar_bytes = 2 * kScanMaxStages * 8 + kScanMaxStages * 4;  // full / empty barriers + the stages' tile numbers
   SGIC_REQUIRE(list_bytes + bar_bytes + 2 * stage_bytes <= kSmemBudget, "k too large for shared memory");
   // Measured on B200 (profiles/r01_k3_stage_sweep.md): ~128 KB of bulk copies in flight per SM is
   // the sweet spot (7.4-7.5 TB/s); 160 KB and more drops to ~6.8 TB/s, 64 KB to ~6.4 TB/s.
@@ -802,10 +802,15 @@ static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.evict_first = h->opt_evict_first ? 1u : 0u;
     p.fused = fused ? 1u : 0u;
     p.counter = counter;
+    // equal round-robin shares for the first 7/8 of the tiles, the rest is claimed dynamically ("steal" = 0: all static)
+    p.n_static = h->opt_steal ? static_cast<uint32_t>((static_cast<uint64_t>(n_tiles) * 7 / 8) / grid) * grid : n_tiles;
+    p.steal = counter + 1;
+    if (!fused && n_rows > 0) SGIC_CUDA(cudaMemsetAsync(p.steal, 0, 4, st));  // nobody resets it in the kernel then
     p.D = dev_D + static_cast<size_t>(q0) * k;
     p.I = reinterpret_cast<long long*>(dev_I + static_cast<size_t>(q0) * k);
     p.id_base = id_base;
     p.bound = bound;
+    p.trace = reinterpret_cast<unsigned long long*>(static_cast<uintptr_t>(h->opt_trace));
     cudaError_t e;
     if (n_rows > 0) {
       if (h->dtype == SGIC_F16) e = launch_scan_t<__half>(p, NQ, cfg.cpl, cfg.rb, grid, smem, st);
@@ -1894,6 +1899,8 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "dense_l2_mb") h->opt_dense_l2_mb = std::max<int64_t>(0, value);
   else if (n == "dense_b_min_mb") h->opt_dense_b_min_mb = std::max<int64_t>(0, value);
   else if (n == "dense_gthr") h->opt_dense_gthr = value ? 1 : 0;
+  else if (n == "steal") h->opt_steal = value ? 1 : 0;
+  else if (n == "trace") h->opt_trace = value;  // device address of a [grid][4] u64 buffer (0 = off), see scan_small.cuh
   else if (n == "drop_retained") {
     std::lock_guard<std::mutex> lk(h->mu);
     h->retain_ok = false;

@@ -99,12 +99,13 @@ __device__ __forceinline__ void warp_multiway_merge(const uint64_t* lists, uint3
         best = head[j];
         bj = j;
       }
-    uint64_t w = best;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const uint64_t o = __shfl_xor_sync(0xffffffffu, w, off);
-      w = (o > w) ? o : w;
-    }
+    // warp max of a 64-bit key with two REDUX.MAX (score word, then the id word among the lanes that hold the
+    // best score) instead of a 5-step shuffle butterfly: the rounds are a latency chain, this halves it.
+    // A real key never has a zero id word (ids stop at 2^32-2), so 0 stands for "not a contender".
+    const uint32_t bh = static_cast<uint32_t>(best >> 32);
+    const uint32_t mh = __reduce_max_sync(0xffffffffu, bh);
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, bh == mh ? static_cast<uint32_t>(best) : 0u);
+    const uint64_t w = (static_cast<uint64_t>(mh) << 32) | ml;
     if (lane == 0) emit(r, w);
     if (w == 0ull) {  // every list exhausted: the rest is padding
       for (uint32_t r2 = r + 1 + lane; r2 < k_out; r2 += 32) emit(r2, 0ull);
