@@ -261,7 +261,20 @@ def run_ours(args):
         search_host = lambda qq: index.search(qq, k)
         windows = []
         # ---- device-resident throughput ------------------------------------------------------
+        # W warm-up steps, and then keep warming until the GPU has been busy for ~1 s: this part sits at its
+        # 1000 W power cap in every regime, and the cap bites only after a few hundred ms — a timed region that
+        # starts earlier measures boost clocks the end-to-end loop right after it never sees.
+        t_w = time.perf_counter()
         for _ in range(warmup):
+            search_dev(q)
+        torch.cuda.synchronize(dev)
+        el = time.perf_counter() - t_w
+        t = torch.tensor([el, el / max(warmup, 1)], dtype=torch.float64, device=dev)
+        if world > 1:   # the searches are collective: every rank must run the same number of extra steps
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el, per = (float(x) for x in t.tolist())
+        extra = 0 if el >= 1.0 else min(2000, int((1.0 - el) / max(per, 1e-6)) + 1)
+        for _ in range(extra):
             search_dev(q)
         barrier()
         launches0 = local.stat("launches")
@@ -340,6 +353,7 @@ def run_ours(args):
             elif kernel == "scan_dense_t_kernel" and "dense_t_dram_bytes_per_row_d512" in tj and d == 512:
                 roofline["traffic"] = tj["dense_t_dram_bytes_per_row_d512"] * n_local
         return {"batch": nq, "value": value, "ms_per_step": ms_total / steps, "steps": steps, "warmup": warmup,
+                "extra_warmup_steps": extra,
                 "gpu_launches": int(launches),
                 "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(nq * d * 4),
                         "d2h_bytes_per_step": int(nq * k * 12)},
@@ -374,7 +388,7 @@ def run_ours(args):
                    "rows": R, "dim": d, "k": k, "batch": nq, "rows_per_gpu": n_local,
                    "exchange": (index.exchange if world > 1 else None),
                    "l2": f"inputs larger than L2: every step streams the {n_local * d * 2 / 1e9:.1f} GB shard from HBM"},
-        "clocks": main["clocks"], "gpu_launches": main["gpu_launches"],
+        "clocks": main["clocks"], "gpu_launches": main["gpu_launches"], "extra_warmup_steps": main["extra_warmup_steps"],
         "e2e": main["e2e"],
         "roofline": main["roofline"],
     }
