@@ -243,9 +243,11 @@ struct DenseEpiRes {
   }
 
   // Warp-cooperative: keep the k largest of R[0..n) (n > k) in R[0..k); returns the k-th largest key.
-  template <bool REG>
+  // KPLR > 0: the reservoir (n <= 32 * KPLR keys) is held in registers, KPLR keys per lane; 0: re-read from L2.
+  template <int KPLR>
   __device__ __forceinline__ uint64_t select_topk(uint64_t* R, uint32_t n) {
-    constexpr int KPL = 8;  // REG: n <= 256
+    constexpr bool REG = KPLR > 0;
+    constexpr int KPL = REG ? KPLR : 1;
     uint64_t key[KPL];
     if (REG) {
 #pragma unroll
@@ -408,7 +410,7 @@ struct DenseEpiRes {
       need &= need - 1;
       const uint32_t n = __shfl_sync(0xffffffffu, cnt, L);
       uint64_t* R = res_warp + static_cast<size_t>(L) * C;
-      const uint64_t kth = (C == 256u) ? select_topk<true>(R, n) : select_topk<false>(R, n);
+      const uint64_t kth = (C == 256u) ? select_topk<8>(R, n) : (C == 512u) ? select_topk<16>(R, n) : select_topk<0>(R, n);
       if (lane == L) {
         cnt = k;
         thr = key_score(kth);

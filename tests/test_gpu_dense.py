@@ -47,6 +47,8 @@ CASES = [
     (100000, 128, 4096, 5),   # a full query block
     (20000, 512, 64, 1024),   # k at the supported maximum (reservoirs of 2048 keys)
     (60000, 256, 129, 500),
+    (40000, 512, 300, 200),   # reservoirs of 512 keys: the second register-resident select
+    (40000, 768, 40, 256),    # same, single-CTA kernel, k at the top of that range
     (33000, 512, 2, 10),      # transposed kernel: smallest batch, ragged last tile
     (33000, 768, 33, 32),     # transposed: 48 query columns, largest thread-private k
     (33000, 1024, 64, 7),     # transposed: 64 columns, d = 1024
@@ -88,6 +90,7 @@ CASES_B = [
     (150000, 448, 1025, 1),    # seven K chunks, k = 1, five query tiles
     (20000, 512, 300, 1024),   # k at the supported maximum
     (200000, 512, 2048, 10),   # every pair owns several tiles: the slots are refilled under the last query tile
+    (30000, 512, 600, 130),    # 512-key reservoirs per (CTA, query)
 ]
 
 
