@@ -334,6 +334,82 @@ struct DenseEpiRes {
     return kth;
   }
 
+  // Large reservoirs (C = 1024 / 2048, 256 < k <= 1024): 64-bit keys do not fit in registers, but their SCORE words
+  // do (KH per lane).  The k-th largest score word T is found by bisection in registers; only the entries that tie
+  // with T — normally one — are looked at again in memory to settle the id word.  Three passes over the reservoir
+  // (load, tie, compaction) instead of one per bisection step.
+  template <int KH>
+  __device__ __forceinline__ uint64_t select_topk_hi(uint64_t* R, uint32_t n) {
+    uint32_t hi[KH];
+#pragma unroll
+    for (int i = 0; i < KH; ++i) {
+      const uint32_t idx = i * 32 + lane;
+      hi[i] = idx < n ? static_cast<uint32_t>(__ldcg(R + idx) >> 32) : 0u;  // 0: empty (no real score maps to 0)
+    }
+    const uint32_t h0 = __shfl_sync(0xffffffffu, hi[0], 0);
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < KH; ++i) x |= hi[i] ? hi[i] ^ h0 : 0u;
+    x = __reduce_or_sync(0xffffffffu, x);
+    uint32_t T = h0;  // all score words equal: T is that word
+    if (x) {
+      int b = 31 - __clz(x);
+      T = (b == 31) ? 0u : (h0 >> (b + 1)) << (b + 1);
+      for (; b >= 0; --b) {  // T = largest value with count(hi >= T) >= k = the k-th largest score word
+        const uint32_t cand = T | (1u << b);
+        uint32_t c = 0;
+#pragma unroll
+        for (int i = 0; i < KH; ++i) c += hi[i] >= cand ? 1u : 0u;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= k) T = cand;
+      }
+    }
+    uint32_t c_gt = 0, c_eq = 0;
+#pragma unroll
+    for (int i = 0; i < KH; ++i) {
+      c_gt += hi[i] > T ? 1u : 0u;
+      c_eq += hi[i] == T ? 1u : 0u;
+    }
+    c_gt = __reduce_add_sync(0xffffffffu, c_gt);
+    c_eq = __reduce_add_sync(0xffffffffu, c_eq);
+    const uint32_t r = k - c_gt;  // how many of the entries that tie with T belong to the top-k (1 <= r <= c_eq)
+    // id word of the k-th key = the r-th largest id word among the ties
+    uint32_t lo_kth = 0;
+    if (r == c_eq) {  // all ties are in: the smallest id word among them
+      uint32_t mn = 0xffffffffu;
+#pragma unroll
+      for (int i = 0; i < KH; ++i)
+        if (hi[i] == T) mn = min(mn, static_cast<uint32_t>(__ldcg(R + i * 32 + lane)));
+      lo_kth = __reduce_min_sync(0xffffffffu, mn);
+    } else {  // exact score ties straddle the k-th place (duplicate rows): bisection over the ties' id words
+      for (int b = 31; b >= 0; --b) {
+        const uint32_t cand = lo_kth | (1u << b);
+        uint32_t c = 0;
+#pragma unroll
+        for (int i = 0; i < KH; ++i)
+          if (hi[i] == T) c += static_cast<uint32_t>(__ldcg(R + i * 32 + lane)) >= cand ? 1u : 0u;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= r) lo_kth = cand;
+      }
+    }
+    const uint64_t kth = (static_cast<uint64_t>(T) << 32) | lo_kth;
+    // survivors to the front (stable, in place: the write position never passes the read position)
+    uint32_t out = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t base = 0; base < n; base += 32) {
+      const uint32_t idx = base + lane;
+      const uint64_t v = idx < n ? __ldcg(R + idx) : 0ull;
+      const bool keep = v >= kth;
+      const uint32_t m = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();
+      if (keep) __stcg(R + out + __popc(m & lt), v);
+      out += __popc(m);
+      __syncwarp();
+    }
+    __syncwarp();
+    return kth;
+  }
+
   // Small reservoirs (C = 32 * KPL keys, KPL keys per lane): rank sort in registers.  Every lane counts the keys
   // larger than its own (32 * KPL shuffles of 64 bits); a key of rank r < k goes to slot r, so the k survivors come
   // out SORTED and the k-th key is the one of rank k-1.  The next reservoir's keys are fetched from L2 while this
@@ -410,7 +486,11 @@ struct DenseEpiRes {
       need &= need - 1;
       const uint32_t n = __shfl_sync(0xffffffffu, cnt, L);
       uint64_t* R = res_warp + static_cast<size_t>(L) * C;
-      const uint64_t kth = (C == 256u) ? select_topk<8>(R, n) : (C == 512u) ? select_topk<16>(R, n) : select_topk<0>(R, n);
+      const uint64_t kth = (C == 256u)    ? select_topk<8>(R, n)
+                           : (C == 512u)  ? select_topk<16>(R, n)
+                           : (C == 1024u) ? select_topk_hi<32>(R, n)
+                           : (C == 2048u) ? select_topk_hi<64>(R, n)
+                                          : select_topk<0>(R, n);
       if (lane == L) {
         cnt = k;
         thr = key_score(kth);

@@ -178,6 +178,33 @@ def test_dense_ties_across_items_full_block(k):
     idx.close()
 
 
+@pytest.mark.parametrize("nq,k,mode", [(150, 300, 0), (150, 600, 0), (300, 1000, 0), (40, 700, 1), (300, 300, 4), (300, 200, 0)])
+def test_large_k_with_triplicated_rows(nq, k, mode):
+    """Every row exists three times, so every score in a reservoir ties with two others and the k-th place falls
+    inside a tie group for most k: the select that works on score words only (1024 / 2048-key reservoirs) must
+    settle those ties by row number exactly like the sorted-list paths do."""
+    rng = np.random.default_rng(nq + k)
+    base = unit(rng, 700, 512)
+    xb = np.concatenate([base, base, base])
+    xq = unit(rng, nq, 512)
+    idx = make_index(xb)
+    idx.set_option("dense_mode", mode)
+    D, I = idx.search(xq, k)
+    idx.close()
+    for r in range(0, nq, 7):
+        ids = I[r]
+        assert len(set(ids.tolist())) == k and ids.min() >= 0
+        pairs = list(zip((-D[r]).tolist(), ids.tolist()))
+        assert pairs == sorted(pairs)                                   # (score desc, id asc)
+        groups = {}
+        for i in ids.tolist():
+            groups.setdefault(i % 700, []).append(i)
+        for g, members in groups.items():                                # copies enter lowest row number first
+            assert sorted(members) == [g + 700 * j for j in range(len(members))]
+    sel = np.arange(0, nq, 11)
+    check_topk(D[sel], I[sel], f16(xb), f16(xq[sel]), k, score_tol=3e-5, tie_tol=1e-6)
+
+
 def test_dense_agrees_with_streaming_kernel():
     """Size-independent property: the same queries answered one at a time by K3 (CUDA-core streaming scan) and
     as one batch by K4 (tensor cores) give the same ids; scores agree to fp32 accumulation-order noise."""
