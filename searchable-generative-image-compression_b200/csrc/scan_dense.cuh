@@ -815,7 +815,9 @@ scan_dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 struct DenseTParams {
   uint64_t* partial;  // [nq][n_lists][k] keys
   uint32_t n_rows, nq, k;
-  uint32_t n_pad;     // ceil16(nq): MMA N, query box rows
+  uint32_t n_pad;     // ceil16(nq): query columns the epilogue walks (lists, thresholds, accumulator stride)
+  uint32_t n_mma;     // MMA N = rows of the query box: n_pad, or 8 for batches of up to 8 queries (the columns
+                      // 8..15 of an accumulator are then never written; their thresholds are +inf)
   uint32_t n_slices, tiles_per_slice, n_tiles, n_lists;
   uint32_t kc, n_stages, idesc, db_evict_first, debug;
 };
@@ -832,7 +834,7 @@ scan_dense_t_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const DenseTParams p) {
   extern __shared__ uint8_t dense_smem_raw[];
   uint8_t* smem = dense_smem_raw + ((1024u - (ptx::smem_u32(dense_smem_raw) & 1023u)) & 1023u);
-  const uint32_t ns = p.n_stages, q_chunk = p.n_pad * (kDenseBK * 2u);
+  const uint32_t ns = p.n_stages, q_chunk = p.n_mma * (kDenseBK * 2u);
   uint8_t* stages = smem;
   uint8_t* q_res = smem + static_cast<size_t>(ns) * kDtStageBytes;  // kc chunks of [n_pad][128 B], SWIZZLE_128B
   uint64_t* lists = reinterpret_cast<uint64_t*>(q_res + static_cast<size_t>(p.kc) * q_chunk);  // [n_pad][4][k]

@@ -122,7 +122,7 @@ struct sgic_index {
   int64_t shard_row_start = 0, shard_total_rows = -1;
   int shard_id = 0, shard_count = 1;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1, opt_trace = 0, opt_steal = 1;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1, opt_trace = 0, opt_steal = 1, opt_t_n8 = 1;
   int64_t stat_ingest_h2d_ns = 0, stat_ingest_k0_ns = 0, stat_ingest_k1_ns = 0;
   int64_t stat_ingest_parse_ns = 0, stat_ingest_pack_ns = 0, stat_ingest_gpu_ns = 0;
   int64_t stat_zl_device_frames = 0, stat_zl_host_rows = 0, stat_zl_fallback_slabs = 0;
@@ -568,6 +568,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     // "dense_mode" = 1 keeps the queries-on-M single-CTA kernel (A/B comparisons).
     const uint32_t kc_chunks = (static_cast<uint32_t>(h->d) + kDenseBK - 1) / kDenseBK;
     const uint32_t n_pad = (nqb + 15u) & ~15u;
+    const uint32_t n_mma = (nqb <= 8u && h->opt_t_n8) ? 8u : n_pad;  // tensor work proportional to the batch down to N = 8
     uint32_t t_stages = 0;
     if (!pairs && h->opt_dense_mode != 1) {  // any k whose (warp, query) lists fit next to the ring
       const size_t fixed = dense_t_fixed_bytes(n_pad, kc_chunks, static_cast<uint32_t>(k)) + 1024 + 256;
@@ -579,7 +580,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     const bool transposed = t_stages > 0;
     rc = make_tmap_rows(&tm_q, static_cast<const uint8_t*>(h->qh) + static_cast<size_t>(q0) * h->d * 2, nqb,
                         static_cast<uint32_t>(h->d),
-                        transposed ? n_pad
+                        transposed ? n_mma
                                    : pairs ? static_cast<uint32_t>(kDenseBM) : std::min<uint32_t>(kDenseBM, (nqb + 7u) & ~7u),
                         h->dtype);
     if (rc) return rc;
@@ -626,13 +627,14 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
       tp_.nq = nqb;
       tp_.k = static_cast<uint32_t>(k);
       tp_.n_pad = n_pad;
+      tp_.n_mma = n_mma;
       tp_.n_slices = n_slices;  // m_tiles == 1: one slice per CTA
       tp_.tiles_per_slice = tiles_per_slice;
       tp_.n_tiles = n_tiles;
       tp_.n_lists = grid_units;
       tp_.kc = kc_chunks;
       tp_.n_stages = t_stages;
-      tp_.idesc = ptx::umma_idesc_f16(128, n_pad, h->dtype == SGIC_BF16 ? 1u : 0u);
+      tp_.idesc = ptx::umma_idesc_f16(128, n_mma, h->dtype == SGIC_BF16 ? 1u : 0u);
       tp_.db_evict_first = p.db_evict_first;
       tp_.debug = p.debug;
       static bool t_configured[64] = {false};
@@ -1900,6 +1902,7 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "dense_b_min_mb") h->opt_dense_b_min_mb = std::max<int64_t>(0, value);
   else if (n == "dense_gthr") h->opt_dense_gthr = value ? 1 : 0;
   else if (n == "steal") h->opt_steal = value ? 1 : 0;
+  else if (n == "t_n8") h->opt_t_n8 = value ? 1 : 0;
   else if (n == "trace") h->opt_trace = value;  // device address of a [grid][4] u64 buffer (0 = off), see scan_small.cuh
   else if (n == "drop_retained") {
     std::lock_guard<std::mutex> lk(h->mu);
