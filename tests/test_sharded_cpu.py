@@ -97,6 +97,7 @@ def _worker(rank, world, port, seed, out_dir):
         for b in blocks:
             idx.add(b)
         assert idx.ntotal == full.shape[0] and idx.d == d
+        assert idx.exchange == "nccl"      # the peer exchange (K5x) needs CUDA IPC: never on a CPU / gloo group
         totals = [None] * world
         dist.all_gather_object(totals, idx.local_ntotal)
         assert sum(totals) == full.shape[0]
@@ -119,6 +120,8 @@ def _worker(rank, world, port, seed, out_dir):
         D3, I3 = idx2.search(rows[[0, len(good) - 1]], 5)
         Dr, Ir = flat_ip_search(rows, rows[[0, len(good) - 1]], 5)
         assert np.array_equal(I3, Ir) and I3[0, 0] == 0 and I3[1, 0] == len(good) - 1
+        idx.close()                        # collective; with stand-ins there is nothing to release
+        idx2.close()
         (Path(out_dir) / f"ok{rank}").write_text("ok")
     finally:
         dist.destroy_process_group()
