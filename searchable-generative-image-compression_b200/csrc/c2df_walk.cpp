@@ -193,8 +193,36 @@ bool clip_meta_dim(const char* s, size_t n, long long* dim) {
     if (!j.skip_value()) return false;
     const size_t ve = j.i;
     if (ke - kb == 3 && std::memcmp(s + kb, "dim", 3) == 0) {
+      // what the reference writes is a short run of digits ("dim": 512): no allocation, no strtod for that
+      bool digits = ve > vb && ve - vb <= 9 && !(s[vb] == '0' && ve - vb > 1);
+      long long iv = 0;
+      for (size_t t = vb; digits && t < ve; ++t) {
+        digits = s[t] >= '0' && s[t] <= '9';
+        iv = iv * 10 + (s[t] - '0');
+      }
+      if (digits) {
+        *dim = iv;
+        goto next_member;
+      }
       std::string v(s + vb, ve - vb);
-      if (!v.empty() && v.front() == '"' && v.back() == '"') v = v.substr(1, v.size() - 2);  // int("512")
+      if (v.size() >= 2 && v.front() == '"' && v.back() == '"') {
+        // int("512"): Python strips surrounding whitespace and takes an optional sign and decimal digits — no
+        // point, no exponent (int("512.0") raises)
+        size_t a = 1, b = v.size() - 1;
+        auto is_ws = [](char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; };
+        while (a < b && is_ws(v[a])) ++a;
+        while (b > a && is_ws(v[b - 1])) --b;
+        bool neg = false;
+        if (a < b && (v[a] == '+' || v[a] == '-')) neg = v[a++] == '-';
+        if (a >= b || b - a > 15) return false;
+        long long sv = 0;
+        for (size_t t = a; t < b; ++t) {
+          if (v[t] < '0' || v[t] > '9') return false;
+          sv = sv * 10 + (v[t] - '0');
+        }
+        *dim = neg ? -sv : sv;
+        goto next_member;
+      }
       if (v == "true") {
         *dim = 1;
       } else if (v == "false") {
@@ -206,6 +234,7 @@ bool clip_meta_dim(const char* s, size_t n, long long* dim) {
         *dim = static_cast<long long>(dv);  // int() truncates toward zero
       }
     }
+  next_member:
     j.ws();
     if (j.i >= n) return false;
     if (s[j.i] == ',') {
@@ -362,6 +391,19 @@ int c2df_parse_batch(const uint8_t* blob, const int64_t* offsets, int64_t n, int
       const int64_t e = (b + kGrain < n) ? b + kGrain : n;
       for (int64_t i = b; i < e; ++i) {
         const int64_t o0 = offsets[i], o1 = offsets[i + 1];
+        // The walk touches a handful of cache lines per 2 KB file and the blob is far larger than the caches:
+        // it is bound by memory latency, not by instructions.  Pull in the lines that are certain to be read of
+        // the file two ahead: the container header and the tail, where pack_c2df (insertion order) puts
+        // clip_stream and clip_meta.
+        if (i + 2 < n) {
+          const int64_t p0 = offsets[i + 2], p1 = offsets[i + 3];
+          if (p0 >= 0 && p1 > p0) {
+            const uint8_t* pb = blob + p0;
+            const int64_t len = p1 - p0;
+            for (int64_t o = 0; o < 256 && o < len; o += 64) __builtin_prefetch(pb + o, 0, 1);
+            for (int64_t o = (len > 640 ? len - 640 : 0) & ~int64_t(63); o < len; o += 64) __builtin_prefetch(pb + o, 0, 1);
+          }
+        }
         int32_t dd = 0;
         int st;
         const uint8_t* dfr = nullptr;
@@ -440,6 +482,10 @@ int c2df_pack_batch(const uint8_t* blob, int64_t cnt, int dim, const int32_t* st
       if (b >= cnt) break;
       const int64_t e = (b + kGrain < cnt) ? b + kGrain : cnt;
       for (int64_t i = b; i < e; ++i) {
+        if (i + 3 < e && frame_off[i + 3] >= 0) {  // the frames were last touched a whole slab ago: fetch ahead
+          const uint8_t* pf = blob + frame_off[i + 3];
+          for (uint32_t o = 0; o < frame_len[i + 3]; o += 64) __builtin_prefetch(pf + o, 0, 0);
+        }
         const int64_t r = wi[static_cast<size_t>(i)];
         if (r < 0) continue;
         if (frame_off[i] >= 0) {

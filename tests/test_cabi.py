@@ -95,6 +95,39 @@ def test_batch_parser_status_codes_mirror_reference_exceptions(golden):
         assert (st == 0) == (cls == "OK")           # skipped by us iff skipped by the reference
 
 
+def test_clip_meta_dim_spellings_follow_the_reference():
+    """int(meta.get('dim', 0)) of the reference (src/search.py:30-33) for every spelling json.dumps can produce:
+    the batch parser has a digits-only fast path and a general path; both must skip exactly what the reference's
+    decode_clip_from_c2df skips (restated in oracle/c2df_ref.py)."""
+    from oracle import c2df_ref
+    from sgic_b200 import c2df
+    from sgic_b200.index_build import quantize_u8_and_compress
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal(512).astype(np.float32)
+    v /= np.linalg.norm(v)
+    payload, meta = quantize_u8_and_compress(v)
+    spellings = [512, "512", 512.0, 512.9, True, False, 0, -3, None, "abc", [512], {"dim": 512}, 5120, " 512", "512 ", "512.0", "+512", "-512", "5e2", "", "0512", 512.0000001, 1e400]
+    blobs = []
+    for sp in spellings:
+        m = dict(meta)
+        m["dim"] = sp
+        m["nested"] = {"dim": 7, "list": [1, {"dim": 9}]}       # only the top-level key counts
+        blobs.append(c2df.pack_c2df({"clip_stream": payload, "clip_meta": m}, {"version": 2}))
+    m = dict(meta)
+    del m["dim"]
+    blobs.append(c2df.pack_c2df({"clip_stream": payload, "clip_meta": m}, {"version": 2}))
+    offs = np.zeros(len(blobs) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in blobs], out=offs[1:])
+    out, status, dims = _parse(np.frombuffer(b"".join(blobs), dtype=np.uint8), offs, 512, threads=1)
+    for i, b in enumerate(blobs):
+        try:
+            _, z = c2df_ref.decode_clip(b)
+            ok = z.shape[0] == 512
+        except Exception:
+            ok = False
+        assert (status[i] == 0) == ok, (i, spellings[i] if i < len(spellings) else "missing", int(status[i]))
+
+
 def test_batch_parser_ragged_and_empty_inputs():
     out, status, dims = _parse(np.zeros(0, np.uint8), [0], 512)
     assert out.shape == (0, 512)
