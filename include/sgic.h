@@ -13,6 +13,16 @@
  * Buffers named host_* are ordinary host memory (pageable or pinned).  Buffers named dev_*
  * are device pointers on the index's device; `stream` is a cudaStream_t passed as void*
  * (NULL = the index's own stream).  *_dev calls enqueue work and do not synchronise.
+ *
+ * Streams.  An index owns one non-blocking stream; host-buffer calls (add_f32, add_u8, add_c2df, search,
+ * reconstruct, write, write_v2) run on it and return when their work is done.  The *_dev calls run on the
+ * stream the caller passes.  The library orders consecutive calls on one index across streams by itself: a
+ * call first makes its stream wait (cudaStreamWaitEvent) for whatever the previous call on a DIFFERENT stream
+ * enqueued, so add_f32_dev(stream A) followed by search() / write() / search_dev(stream B) sees the new rows
+ * without a synchronise in between, and the shared search workspaces are never used by two streams at once.
+ * The caller's part: buffers passed to a *_dev call must stay valid until that stream has run the work, and
+ * calls on one index are serialised by its mutex (concurrent searches from several host threads take turns; the
+ * resident service batches them into one search instead, see service.py).
  */
 #ifndef SGIC_H_
 #define SGIC_H_
@@ -30,6 +40,10 @@ enum { SGIC_F16 = 0, SGIC_BF16 = 1 };  /* storage type of the HBM-resident datab
 enum {
   SGIC_RETAIN_F32 = 1, /* keep the fp32 rows given to add_f32 on the host so that
                           sgic_index_write is bit-identical to faiss.write_index */
+  SGIC_RETAIN_U8 = 2,  /* keep the u8 clip_stream codes of rows added through add_u8 / add_c2df on the
+                          host (1 byte per element) so that sgic_index_write regenerates the fp32
+                          rows of dequantize_clip_u8 + l2n (src/build.py:18-24) and the file is
+                          byte-identical to the one src/build.py:95,99 writes */
 };
 
 /* per-file status codes of the batched .c2df ingest; they mirror the exceptions of
@@ -142,6 +156,13 @@ int sgic_index_write_v2(sgic_index* h, const char* path, int64_t row_start, int6
                         int n_shards);
 /* out4 = {row_start, total_rows, shard, n_shards} of an index loaded from an SGI2 file. */
 int sgic_index_shard_info(const sgic_index* h, int64_t* out4);
+
+/* The retained u8 codes of rows [i0, i0+n) (SGIC_RETAIN_U8; fails unless every row came in as codes). */
+int sgic_index_codes(sgic_index* h, int64_t i0, int64_t n, uint8_t* host_out);
+/* dequantize_clip_u8 + l2n (src/search.py:16-22 == src/build.py:18-24) on the host for n rows of d codes, with
+ * numpy's operation order (fp32 division by 255, *2, -1; pairwise sum of squares; division by max(norm, 1e-9)):
+ * bit-identical to the reference's fp32 rows.  What sgic_index_write uses for an index that retains its codes. */
+int sgic_codes_to_f32(const uint8_t* host_q, int64_t n, int d, float* host_out);
 
 /* rows [i0, i0+n) up-cast to fp32 (faiss reconstruct_n); host buffer. */
 int sgic_index_reconstruct(sgic_index* h, int64_t i0, int64_t n, float* host_out);

@@ -57,6 +57,8 @@ _SIGNATURES = {
     "sgic_index_write_v2": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int]),
     "sgic_index_shard_info": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sgic_index_reconstruct": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "sgic_index_codes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "sgic_codes_to_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "sgic_index_data_dev": (C.c_void_p, [C.c_void_p]),
     "sgic_index_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "sgic_index_get_stat": (C.c_int64, [C.c_void_p, C.c_char_p]),
@@ -66,6 +68,7 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 SGIC_F16, SGIC_BF16 = 0, 1
 SGIC_RETAIN_F32 = 1
+SGIC_RETAIN_U8 = 2
 
 C2DF_STATUS = {
     0: "ok",

@@ -10,6 +10,7 @@
 // dlopen("libzstd.so.1") and hand-declared prototypes (stable public ABI since zstd 1.0).
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdint>
 #include <cstring>
@@ -115,51 +116,79 @@ struct Json {
     ++i;
     return true;
   }
-  bool skip_value() {
+  // Nesting json.loads accepts before it raises RecursionError (CPython 3.12, the reference's Dockerfile base:
+  // the C scanner's recursion budget; measured 9997 with this interpreter).  build.py:87-88 turns that exception
+  // into [SKIP]; deeper payloads are refused here the same way instead of being followed.
+  static constexpr size_t kMaxDepth = 9990;
+  bool key_colon() {  // "key" :
     ws();
-    if (i >= n) return false;
-    const char c = s[i];
-    if (c == '"') {
-      size_t b, e;
-      return string(&b, &e);
-    }
-    if (c == '{' || c == '[') {
-      const char close = (c == '{') ? '}' : ']';
-      ++i;
-      ws();
-      if (i < n && s[i] == close) {
-        ++i;
-        return true;
+    size_t b, e;
+    if (!string(&b, &e)) return false;
+    ws();
+    if (i >= n || s[i] != ':') return false;
+    ++i;
+    return true;
+  }
+  // Iterative (the payload is untrusted and may be 4 GB of '['): the open containers live on an explicit stack of
+  // one bit each (object / array) — 64 levels inline, deeper ones on the heap.
+  bool skip_value() {
+    uint64_t small = 0;
+    std::vector<uint8_t> big;
+    size_t depth = 0;
+    auto push = [&](bool obj) {
+      if (depth < 64) small = (small & ~(1ull << depth)) | (static_cast<uint64_t>(obj) << depth);
+      else {
+        if (big.size() <= depth - 64) big.resize(std::max<size_t>(256, 2 * (depth - 64 + 1)));
+        big[depth - 64] = obj;
       }
-      for (;;) {
-        if (c == '{') {
-          ws();
-          size_t b, e;
-          if (!string(&b, &e)) return false;
-          ws();
-          if (i >= n || s[i] != ':') return false;
+      ++depth;
+    };
+    auto top_is_obj = [&]() -> bool { return depth <= 64 ? ((small >> (depth - 1)) & 1u) != 0 : big[depth - 1 - 64] != 0; };
+    for (;;) {
+      ws();
+      if (i >= n) return false;
+      const char c = s[i];
+      if (c == '"') {
+        size_t b, e;
+        if (!string(&b, &e)) return false;
+      } else if (c == '{' || c == '[') {
+        if (depth >= kMaxDepth) return false;
+        const char close = (c == '{') ? '}' : ']';
+        ++i;
+        ws();
+        if (i < n && s[i] == close) {
           ++i;
+        } else {
+          push(c == '{');
+          if (c == '{' && !key_colon()) return false;
+          continue;  // the container's first value
         }
-        if (!skip_value()) return false;
+      } else {
+        // number / true / false / null / NaN / Infinity
+        const size_t b = i;
+        while (i < n && s[i] != ',' && s[i] != '}' && s[i] != ']' && s[i] != ' ' && s[i] != '\t' && s[i] != '\n' &&
+               s[i] != '\r')
+          ++i;
+        if (i == b) return false;
+      }
+      // a value is complete: close finished containers, or step to the next member
+      for (;;) {
+        if (depth == 0) return true;
         ws();
         if (i >= n) return false;
         if (s[i] == ',') {
           ++i;
-          continue;
+          if (top_is_obj() && !key_colon()) return false;
+          break;
         }
-        if (s[i] == close) {
+        if (s[i] == (top_is_obj() ? '}' : ']')) {
           ++i;
-          return true;
+          --depth;
+          continue;
         }
         return false;
       }
     }
-    // number / true / false / null / NaN / Infinity
-    const size_t b = i;
-    while (i < n && s[i] != ',' && s[i] != '}' && s[i] != ']' && s[i] != ' ' && s[i] != '\t' && s[i] != '\n' &&
-           s[i] != '\r')
-      ++i;
-    return i > b;
   }
 };
 

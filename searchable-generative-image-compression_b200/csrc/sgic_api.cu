@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -115,9 +116,20 @@ struct sgic_index {
   void* opin = nullptr;
   size_t opin_bytes = 0;
   cudaEvent_t t0 = nullptr, t1 = nullptr, tm = nullptr;
+  // Cross-stream ordering.  The *_dev entry points enqueue on the CALLER's stream, the host-buffer calls on the
+  // index's own stream, and all of them share the database and the search workspaces: every call first makes its
+  // stream wait for the work the previous call left on a different stream (order_begin / order_end below).
+  cudaEvent_t ev_order = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool last_stream_valid = false;
   // retained fp32 rows (SGIC_RETAIN_F32)
   std::vector<float> retained;
   bool retain_ok = false;
+  // retained u8 codes (SGIC_RETAIN_U8): rows that came in as clip_stream codes (add_u8 / add_c2df) are kept on the
+  // host, 1 byte per element, so that sgic_index_write can regenerate the fp32 rows the reference's
+  // dequantize_clip_u8 + l2n (src/build.py:18-24) would have handed to faiss — bit for bit
+  std::vector<uint8_t> codes;
+  bool codes_ok = false;
   // shard placement recorded in / restored from an SGI2 file (single index: 0, ntotal, 0, 1)
   int64_t shard_row_start = 0, shard_total_rows = -1;
   int shard_id = 0, shard_count = 1;
@@ -132,6 +144,24 @@ struct sgic_index {
 namespace sgic {
 
 static size_t elt_rows_bytes(const sgic_index* h, int64_t rows) { return static_cast<size_t>(rows) * h->d * 2; }
+
+// Stream hand-over (call with the index mutex held).  order_begin(st): if the previous call enqueued on another
+// stream, `st` waits for it — for the index's own stream the event is recorded now (everything enqueued there so
+// far), for a caller's stream it was recorded right after that call's last enqueue (the handle may be gone by
+// now).  order_end(st): remember `st`; a foreign stream gets its event immediately.  Same stream again: no cost.
+static int order_begin(sgic_index* h, cudaStream_t st) {
+  if (h->last_stream_valid && h->last_stream != st) {
+    if (h->last_stream == h->stream) SGIC_CUDA(cudaEventRecord(h->ev_order, h->stream));
+    SGIC_CUDA(cudaStreamWaitEvent(st, h->ev_order, 0));
+  }
+  return 0;
+}
+static int order_end(sgic_index* h, cudaStream_t st) {
+  h->last_stream = st;
+  h->last_stream_valid = true;
+  if (st != h->stream) SGIC_CUDA(cudaEventRecord(h->ev_order, st));
+  return 0;
+}
 
 static int ensure_capacity(sgic_index* h, int64_t rows, cudaStream_t st) {
   if (rows <= h->capacity) return 0;
@@ -843,6 +873,67 @@ static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
   return 0;
 }
 
+// ---- retained rows ---------------------------------------------------------------------------
+// a row arrived by a route that does not keep its source: the host copies no longer describe the whole index
+static void drop_codes(sgic_index* h) {
+  h->codes_ok = false;
+  h->codes.clear();
+  h->codes.shrink_to_fit();
+}
+static void keep_codes(sgic_index* h, const uint8_t* q, int64_t n) {
+  if (!h->codes_ok) return;
+  try {
+    h->codes.insert(h->codes.end(), q, q + static_cast<size_t>(n) * h->d);
+  } catch (const std::bad_alloc&) {
+    drop_codes(h);
+  }
+}
+
+// numpy's add.reduce over a contiguous float32 axis (pairwise_sum in loops_utils.h: blocks of <= 128 elements
+// summed with 8 interleaved accumulators, halves split on multiples of 8), which is what
+// np.linalg.norm(x, axis=-1) of l2n (src/search.py:16-18 == src/build.py:18-20) runs on x*x.
+// tests/test_oracle.py checks this restatement against numpy itself, bit for bit.
+static float np_pairwise_sum_f32(const float* a, int64_t n) {
+  if (n < 8) {
+    float res = 0.f;
+    for (int64_t i = 0; i < n; ++i) res += a[i];
+    return res;
+  }
+  if (n <= 128) {
+    float r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int64_t i = 8;
+    for (; i < n - (n % 8); i += 8)
+      for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+    float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+  }
+  int64_t n2 = n / 2;
+  n2 -= n2 % 8;
+  return np_pairwise_sum_f32(a, n2) + np_pairwise_sum_f32(a + n2, n - n2);
+}
+
+// u8 codes -> the fp32 unit rows of the reference, same operations in the same order:
+//   z = (q.astype(float32) / 255.0) * 2.0 - 1.0 ;  z / np.maximum(np.linalg.norm(z, axis=-1, keepdims=True), 1e-9)
+// (this translation unit is compiled with -ffp-contract=off: no fused multiply-add may merge two roundings)
+void rows_from_codes_f32(const uint8_t* q, int64_t n, int d, float* out) {
+  float lut[256];
+  for (int v = 0; v < 256; ++v) lut[v] = (static_cast<float>(v) / 255.0f) * 2.0f - 1.0f;
+  std::vector<float> sq(static_cast<size_t>(d));
+  for (int64_t r = 0; r < n; ++r) {
+    const uint8_t* qr = q + static_cast<size_t>(r) * d;
+    float* zr = out + static_cast<size_t>(r) * d;
+    for (int i = 0; i < d; ++i) {
+      zr[i] = lut[qr[i]];
+      sq[static_cast<size_t>(i)] = zr[i] * zr[i];
+    }
+    const float nrm = std::sqrt(np_pairwise_sum_f32(sq.data(), d));
+    const float den = nrm > 1e-9f ? nrm : 1e-9f;
+    for (int i = 0; i < d; ++i) zr[i] = zr[i] / den;
+  }
+}
+
 // ---- IxFI ---------------------------------------------------------------------------------
 #pragma pack(push, 1)
 struct IxfiHeader {
@@ -896,9 +987,11 @@ int sgic_index_create(int d, int dtype, int device, int64_t capacity_rows, int f
   h->flags = flags;
   h->sm_count = prop.multiProcessorCount;
   h->retain_ok = (flags & SGIC_RETAIN_F32) != 0;
+  h->codes_ok = (flags & SGIC_RETAIN_U8) != 0;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->t0) != cudaSuccess || cudaEventCreate(&h->t1) != cudaSuccess ||
-      cudaEventCreate(&h->tm) != cudaSuccess) {
+      cudaEventCreate(&h->tm) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming) != cudaSuccess) {
     set_error("stream/event creation failed");
     delete h;
     return 2;
@@ -947,6 +1040,7 @@ int sgic_index_destroy(sgic_index* h) {
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);
   if (h->tm) cudaEventDestroy(h->tm);
+  if (h->ev_order) cudaEventDestroy(h->ev_order);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -963,6 +1057,8 @@ int sgic_index_reserve(sgic_index* h, int64_t rows) {
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   if (rows <= h->capacity) return 0;
+  int orc = order_begin(h, h->stream);
+  if (orc) return orc;
   // exact reservation: no geometric slack on an explicit request
   void* nb = nullptr;
   cudaError_t e = cudaMalloc(&nb, elt_rows_bytes(h, rows));
@@ -987,6 +1083,8 @@ int sgic_index_reset(sgic_index* h) {
   h->ntotal = 0;
   h->retained.clear();
   h->retain_ok = (h->flags & SGIC_RETAIN_F32) != 0;
+  h->codes.clear();
+  h->codes_ok = (h->flags & SGIC_RETAIN_U8) != 0;
   return 0;
 }
 
@@ -997,7 +1095,9 @@ int sgic_index_add_f32(sgic_index* h, int64_t n, const float* host_x) {
   SGIC_REQUIRE(host_x != nullptr, "x is NULL");
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
-  int rc = ensure_capacity(h, h->ntotal + n, h->stream);
+  int rc = order_begin(h, h->stream);
+  if (rc) return rc;
+  rc = ensure_capacity(h, h->ntotal + n, h->stream);
   if (rc) return rc;
   const int64_t base = h->ntotal;
   rc = stream_rows_h2d(h, reinterpret_cast<const uint8_t*>(host_x), n, static_cast<size_t>(h->d) * 4,
@@ -1005,6 +1105,8 @@ int sgic_index_add_f32(sgic_index* h, int64_t n, const float* host_x) {
                          return launch_pack_f32(h, static_cast<const float*>(dev), base + first, rows, h->stream);
                        });
   if (rc) return rc;
+  if ((rc = order_end(h, h->stream))) return rc;
+  drop_codes(h);
   if (h->retain_ok) {
     try {
       h->retained.insert(h->retained.end(), host_x, host_x + static_cast<size_t>(n) * h->d);
@@ -1025,11 +1127,15 @@ int sgic_index_add_f32_dev(sgic_index* h, int64_t n, const float* dev_x, void* s
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
-  int rc = ensure_capacity(h, h->ntotal + n, st);
+  int rc = order_begin(h, st);
+  if (rc) return rc;
+  rc = ensure_capacity(h, h->ntotal + n, st);
   if (rc) return rc;
   rc = launch_pack_f32(h, dev_x, h->ntotal, n, st);
   if (rc) return rc;
+  if ((rc = order_end(h, st))) return rc;
   h->retain_ok = false;
+  drop_codes(h);
   h->retained.clear();
   h->ntotal += n;
   return 0;
@@ -1042,11 +1148,15 @@ int sgic_index_add_packed_dev(sgic_index* h, int64_t n, const void* dev_rows, vo
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
-  int rc = ensure_capacity(h, h->ntotal + n, st);
+  int rc = order_begin(h, st);
+  if (rc) return rc;
+  rc = ensure_capacity(h, h->ntotal + n, st);
   if (rc) return rc;
   SGIC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(h->db) + elt_rows_bytes(h, h->ntotal), dev_rows,
                             elt_rows_bytes(h, n), cudaMemcpyDeviceToDevice, st));
+  if ((rc = order_end(h, st))) return rc;
   h->retain_ok = false;
+  drop_codes(h);
   h->retained.clear();
   h->ntotal += n;
   return 0;
@@ -1059,14 +1169,18 @@ int sgic_index_add_u8(sgic_index* h, int64_t n, const uint8_t* host_q) {
   SGIC_REQUIRE(host_q != nullptr, "q is NULL");
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
-  int rc = ensure_capacity(h, h->ntotal + n, h->stream);
+  int rc = order_begin(h, h->stream);
+  if (rc) return rc;
+  rc = ensure_capacity(h, h->ntotal + n, h->stream);
   if (rc) return rc;
   const int64_t base = h->ntotal;
   rc = stream_rows_h2d(h, host_q, n, static_cast<size_t>(h->d), [&](void* dev, int64_t first, int64_t rows) {
     return launch_dequant_u8(h, static_cast<const uint8_t*>(dev), base + first, rows, h->stream);
   });
   if (rc) return rc;
+  if ((rc = order_end(h, h->stream))) return rc;
   h->retain_ok = false;
+  keep_codes(h, host_q, n);
   h->retained.clear();
   h->ntotal += n;
   return 0;
@@ -1079,11 +1193,15 @@ int sgic_index_add_u8_dev(sgic_index* h, int64_t n, const uint8_t* dev_q, void* 
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
-  int rc = ensure_capacity(h, h->ntotal + n, st);
+  int rc = order_begin(h, st);
+  if (rc) return rc;
+  rc = ensure_capacity(h, h->ntotal + n, st);
   if (rc) return rc;
   rc = launch_dequant_u8(h, dev_q, h->ntotal, n, st);
   if (rc) return rc;
+  if ((rc = order_end(h, st))) return rc;
   h->retain_ok = false;
+  drop_codes(h);
   h->retained.clear();
   h->ntotal += n;
   return 0;
@@ -1165,6 +1283,11 @@ static int zl_slab_decode(sgic_index* h, sgic_index::ZlSlab& z) {
   DeviceGuard g(h->device);
   cudaStream_t st = h->stream;
   const uint32_t nf = static_cast<uint32_t>(z.nf);
+  {
+    int orc = order_begin(h, st);
+    if (orc) return orc;
+    if ((orc = order_end(h, st))) return orc;
+  }
   SGIC_CUDA(cudaStreamWaitEvent(st, z.copied, 0));
   const size_t smem = static_cast<size_t>(kZlWarpsPerBlock) * sizeof(ZlWarpSmem);  // ~71 KB: 3 CTAs per SM
   static bool zl_configured[64] = {false};
@@ -1182,6 +1305,10 @@ static int zl_slab_decode(sgic_index* h, sgic_index::ZlSlab& z) {
   h->stat_launches++;
   SGIC_CUDA(cudaGetLastError());
   if (h->opt_timing) SGIC_CUDA(cudaEventRecord(z.t_k1, st));
+  // SGIC_RETAIN_U8: the slab's u8 rows come back into the pinned buffer they partly left from (the H2D of the
+  // host-decoded rows is long done: K0 waited for it), 1 byte per element; finalize appends them to h->codes
+  if (h->codes_ok)
+    SGIC_CUDA(cudaMemcpyAsync(z.pin_rows, z.rows, static_cast<size_t>(z.w) * h->d, cudaMemcpyDeviceToHost, st));
   SGIC_CUDA(cudaMemcpyAsync(z.status_host, z.status, static_cast<size_t>(nf) * 4, cudaMemcpyDeviceToHost, st));
   SGIC_CUDA(cudaEventRecord(z.decoded, st));
   return 0;
@@ -1204,7 +1331,10 @@ static int zl_slab_finalize(sgic_index* h, sgic_index::ZlSlab& z, bool* bad) {
       SGIC_CUDA(cudaEventRecord(z.freed, st));
       return 0;
     }
-  int rc = ensure_capacity(h, h->ntotal + z.w, st);
+  int rc = order_begin(h, st);
+  if (rc) return rc;
+  if ((rc = order_end(h, st))) return rc;
+  rc = ensure_capacity(h, h->ntotal + z.w, st);
   if (rc) return rc;
   if (h->opt_timing) SGIC_CUDA(cudaEventRecord(z.t_q0, st));
   rc = launch_dequant_u8(h, static_cast<const uint8_t*>(z.rows), h->ntotal, z.w, st);
@@ -1215,6 +1345,7 @@ static int zl_slab_finalize(sgic_index* h, sgic_index::ZlSlab& z, bool* bad) {
   }
   SGIC_CUDA(cudaEventRecord(z.freed, st));
   h->retain_ok = false;
+  keep_codes(h, static_cast<const uint8_t*>(z.pin_rows), z.w);  // copied back behind K0 (zl_slab_decode)
   h->retained.clear();
   h->ntotal += z.w;
   h->stat_zl_device_frames += z.nf;
@@ -1382,7 +1513,11 @@ int sgic_index_search_dev(sgic_index* h, int64_t nq, const float* dev_q, int64_t
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
-  return search_dev_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st);
+  int rc = order_begin(h, st);
+  if (rc) return rc;
+  rc = search_dev_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st);
+  if (rc) return rc;
+  return order_end(h, st);
 }
 
 int sgic_index_search(sgic_index* h, int64_t nq, const float* host_q, int64_t k, float* host_D, int64_t* host_I) {
@@ -1401,6 +1536,8 @@ int sgic_index_search(sgic_index* h, int64_t nq, const float* host_q, int64_t k,
   if (rc) return rc;
   rc = ensure_buf(&h->opin, &h->opin_bytes, std::max(qbytes, dbytes + ibytes), true);
   if (rc) return rc;
+  if ((rc = order_begin(h, h->stream))) return rc;
+  if ((rc = order_end(h, h->stream))) return rc;
   // queries: host -> pinned -> device; results: device -> pinned -> host
   std::memcpy(h->opin, host_q, qbytes);
   SGIC_CUDA(cudaMemcpyAsync(h->qdev, h->opin, qbytes, cudaMemcpyHostToDevice, h->stream));
@@ -1613,6 +1750,8 @@ int sgic_index_reconstruct(sgic_index* h, int64_t i0, int64_t n, float* host_out
   DeviceGuard g(h->device);
   int rc = ensure_staging(h);
   if (rc) return rc;
+  if ((rc = order_begin(h, h->stream))) return rc;
+  if ((rc = order_end(h, h->stream))) return rc;
   const size_t row_bytes = static_cast<size_t>(h->d) * 4;
   const int64_t rows_per_chunk = std::max<int64_t>(1, static_cast<int64_t>(kStageChunkBytes / row_bytes));
   for (int64_t done = 0; done < n; done += rows_per_chunk) {
@@ -1655,8 +1794,21 @@ int sgic_index_write(sgic_index* h, const char* path) {
   const bool from_host =
       h->retain_ok && h->retained.size() == static_cast<size_t>(h->ntotal) * static_cast<size_t>(h->d);
   if (ok && h->ntotal > 0) {
+    const bool from_codes =
+        h->codes_ok && h->codes.size() == static_cast<size_t>(h->ntotal) * static_cast<size_t>(h->d);
     if (from_host) {
       ok = std::fwrite(h->retained.data(), sizeof(float), h->retained.size(), f) == h->retained.size();
+    } else if (from_codes) {
+      // rows that came from clip_stream codes: what build.py:82-94 hands to faiss is dequantize_clip_u8(q) in
+      // fp32, regenerated here with the reference's operation order — the file equals the reference's byte for byte
+      const int64_t chunk = std::max<int64_t>(1, static_cast<int64_t>((16u << 20) / (h->d * 4)));
+      std::vector<float> buf(static_cast<size_t>(std::min(chunk, h->ntotal)) * h->d);
+      for (int64_t i0 = 0; ok && i0 < h->ntotal; i0 += chunk) {
+        const int64_t rows = std::min(chunk, h->ntotal - i0);
+        rows_from_codes_f32(h->codes.data() + static_cast<size_t>(i0) * h->d, rows, h->d, buf.data());
+        ok = std::fwrite(buf.data(), sizeof(float), static_cast<size_t>(rows) * h->d, f) ==
+             static_cast<size_t>(rows) * h->d;
+      }
     } else {
       const int64_t chunk = std::max<int64_t>(1, static_cast<int64_t>((64u << 20) / (h->d * 4)));
       std::vector<float> buf(static_cast<size_t>(std::min(chunk, h->ntotal)) * h->d);
@@ -1707,11 +1859,19 @@ int sgic_index_write_v2(sgic_index* h, const char* path, int64_t row_start, int6
   DeviceGuard g(h->device);
   int rc = ensure_staging(h);
   if (rc) return rc;
+  if ((rc = order_begin(h, h->stream))) return rc;
+  if ((rc = order_end(h, h->stream))) return rc;
   FILE* f = std::fopen(path, "wb");
   if (!f) {
     set_error(std::string("could not open ") + path + " for writing");
     return 3;
   }
+  struct Closer {  // every early return below (SGIC_CUDA) closes the file
+    FILE** f;
+    ~Closer() {
+      if (*f) std::fclose(*f);
+    }
+  } closer{&f};
   std::vector<uint8_t> page(kSgi2Payload, 0);
   Sgi2Header hd;
   std::memset(&hd, 0, sizeof(hd));
@@ -1752,7 +1912,11 @@ int sgic_index_write_v2(sgic_index* h, const char* path, int64_t row_start, int6
     written += len[b];
     b ^= 1;
   }
-  ok = (std::fclose(f) == 0) && ok;
+  {
+    FILE* ff = f;
+    f = nullptr;
+    ok = (std::fclose(ff) == 0) && ok;
+  }
   if (!ok) {
     set_error(std::string("write error on ") + path);
     return 3;
@@ -1799,6 +1963,7 @@ static int read_v2_body(FILE* f, const char* path, const Sgi2Header& hd, int dev
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail("stream synchronise failed while loading", 2);
     h->ntotal = hd.ntotal;
     h->retain_ok = false;
+    drop_codes(h);
     h->shard_row_start = hd.row_start;
     h->shard_total_rows = hd.total_rows;
     h->shard_id = static_cast<int>(hd.shard);
@@ -1885,6 +2050,22 @@ int sgic_index_read(const char* path, int dtype, int device, int flags, sgic_ind
   return 0;
 }
 
+int sgic_index_codes(sgic_index* h, int64_t i0, int64_t n, uint8_t* host_out) {
+  SGIC_REQUIRE(h != nullptr && (host_out != nullptr || n == 0), "NULL argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  SGIC_REQUIRE(h->codes_ok && h->codes.size() == static_cast<size_t>(h->ntotal) * static_cast<size_t>(h->d),
+               "this index does not hold the u8 codes of all its rows (SGIC_RETAIN_U8, rows added as codes only)");
+  SGIC_REQUIRE(i0 >= 0 && n >= 0 && i0 + n <= h->ntotal, "row range out of bounds");
+  std::memcpy(host_out, h->codes.data() + static_cast<size_t>(i0) * h->d, static_cast<size_t>(n) * h->d);
+  return 0;
+}
+
+int sgic_codes_to_f32(const uint8_t* host_q, int64_t n, int d, float* host_out) {
+  SGIC_REQUIRE(n >= 0 && d > 0 && (n == 0 || (host_q != nullptr && host_out != nullptr)), "bad arguments");
+  rows_from_codes_f32(host_q, n, d, host_out);
+  return 0;
+}
+
 int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   SGIC_REQUIRE(h != nullptr && name != nullptr, "NULL argument");
   const std::string n(name);
@@ -1941,6 +2122,7 @@ int64_t sgic_index_get_stat(const sgic_index* h, const char* name) {
   if (n == "zl_host_rows") return h->stat_zl_host_rows;
   if (n == "zl_fallback_slabs") return h->stat_zl_fallback_slabs;
   if (n == "retained_rows") return h->retain_ok ? static_cast<int64_t>(h->retained.size() / h->d) : -1;
+  if (n == "retained_code_rows") return h->codes_ok ? static_cast<int64_t>(h->codes.size() / h->d) : -1;
   return -1;
 }
 

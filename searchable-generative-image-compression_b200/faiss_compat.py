@@ -19,7 +19,7 @@ from typing import Iterable, Sequence
 import numpy as np
 
 from . import _native
-from ._native import SGIC_BF16, SGIC_F16, SGIC_RETAIN_F32, check
+from ._native import SGIC_BF16, SGIC_F16, SGIC_RETAIN_F32, SGIC_RETAIN_U8, check
 
 METRIC_INNER_PRODUCT = 0
 
@@ -78,17 +78,20 @@ class IndexFlatIP(Index):
     ``IndexFlatIP(d)`` is the faiss signature (src/build.py:93).  The keyword
     arguments are additive: ``dtype`` of the stored rows ("fp16" default, "bf16"),
     ``device`` ordinal, ``capacity`` rows to reserve, ``retain_fp32`` to keep the
-    fp32 rows on the host for a bit-exact ``write_index``.
+    fp32 rows on the host for a bit-exact ``write_index``, ``retain_codes`` to keep the
+    u8 ``clip_stream`` codes of rows added through ``add_u8`` / ``add_c2df`` (1 byte per
+    element on the host) so that ``write_index`` emits exactly the fp32 rows the
+    reference's ``dequantize_clip_u8`` would have given faiss (src/build.py:82-99).
     """
 
     def __init__(self, d: int, *, dtype="fp16", device: int | None = None, capacity: int = 0,
-                 retain_fp32: bool = True, _handle=None):
+                 retain_fp32: bool = True, retain_codes: bool = False, _handle=None):
         self._lib = _native.lib()
         self._h = C.c_void_p()
         if _handle is not None:
             self._h = _handle
             return
-        flags = SGIC_RETAIN_F32 if retain_fp32 else 0
+        flags = (SGIC_RETAIN_F32 if retain_fp32 else 0) | (SGIC_RETAIN_U8 if retain_codes else 0)
         dev = _default_device() if device is None else int(device)
         check(self._lib.sgic_index_create(int(d), _dtype_code(dtype), dev, int(capacity), flags, C.byref(self._h)))
 
@@ -155,6 +158,13 @@ class IndexFlatIP(Index):
 
     def reconstruct(self, i: int) -> np.ndarray:
         return self.reconstruct_n(int(i), 1)[0]
+
+    def codes(self, i0: int = 0, n: int | None = None) -> np.ndarray:
+        """The retained u8 ``clip_stream`` codes of rows [i0, i0+n) (``retain_codes=True``)."""
+        n = self.ntotal - i0 if n is None else n
+        out = np.empty((n, self.d), dtype=np.uint8)
+        check(self._lib.sgic_index_codes(self._h, int(i0), int(n), _ptr(out)))
+        return out
 
     # -- additive surface (north-star items a / c) -----------------------------------------
     def reserve(self, rows: int) -> None:
@@ -270,6 +280,16 @@ def shard_info(index: IndexFlatIP) -> dict:
     out = (C.c_int64 * 4)()
     check(index._lib.sgic_index_shard_info(index._h, out))
     return {"row_start": int(out[0]), "total_rows": int(out[1]), "shard": int(out[2]), "n_shards": int(out[3])}
+
+
+def codes_to_f32(q) -> np.ndarray:
+    """``dequantize_clip_u8`` + ``l2n`` (src/search.py:16-22) for a block of u8 rows on the host, with numpy's
+    operation order — bit-identical to what the reference computes row by row."""
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    assert q.ndim == 2
+    out = np.empty(q.shape, dtype=np.float32)
+    check(_native.lib().sgic_codes_to_f32(_ptr(q), q.shape[0], q.shape[1], _ptr(out)))
+    return out
 
 
 def write_index(index: IndexFlatIP, path: str) -> None:

@@ -46,6 +46,22 @@ def _skip_reason(path: Path, code: int) -> str:
     return _native.C2DF_STATUS.get(code, f"status {code}")
 
 
+def _header_model_id(path):
+    """``header.get("model_id")`` of one ``.c2df`` reading only its JSON header (filemaker.py:146-150), not the
+    entries: the sniff stays cheap when no file of a large corpus names a model."""
+    import struct
+    try:
+        with open(path, "rb") as f:
+            head = f.read(10)
+            if len(head) < 10 or head[:4] != b"C2DF":
+                return None
+            (hlen,) = struct.unpack_from("<I", head, 6)
+            header = json.loads(f.read(hlen).decode("utf-8"))
+        return header.get("model_id") if isinstance(header, dict) else None
+    except Exception:
+        return None
+
+
 def build_index_from_c2df_dir(c2df_dir, index_dir, *, dtype="fp16", device=None, n_threads: int = 0) -> None:
     c2df_dir, index_dir = Path(c2df_dir), Path(index_dir)
     index_dir.mkdir(parents=True, exist_ok=True)
@@ -66,20 +82,23 @@ def build_index_from_c2df_dir(c2df_dir, index_dir, *, dtype="fp16", device=None,
         for p in paths:
             print(f"[SKIP] {p.name}: not a usable .c2df")
         raise RuntimeError("No available .c2df")
-    model_id = None
-    index = faiss.IndexFlatIP(d, dtype=dtype, device=device, retain_fp32=False)
+    # retain_codes: the u8 codes stay on the host (1 byte per element) so that the two IxFI files below hold the
+    # fp32 rows of dequantize_clip_u8 exactly as build.py:82-99 writes them, not fp16-rounded values
+    index = faiss.IndexFlatIP(d, dtype=dtype, device=device, retain_fp32=False, retain_codes=True)
     statuses = index.add_c2df_paths(paths, n_threads=n_threads)
+    if any(int(st) == 7 for st in statuses):
+        # a decodable file of another dimension: the reference collects it and then fails as a whole in
+        # np.concatenate (build.py:91) — same here, nothing is written
+        bad = next(p for p, st in zip(paths, statuses) if int(st) == 7)
+        raise ValueError("all the input array dimensions except for the concatenation axis must match exactly, "
+                         f"but along dimension 1, the first array has size {d} and {bad.name} has another size")
     keep: List[str] = []
+    model_id = None
     for p, st in zip(paths, statuses):
         if st == 0:
             keep.append(str(p))
-            if model_id is None:
-                try:
-                    _, header = unpack_c2df(p)
-                    if isinstance(header, dict):
-                        model_id = header.get("model_id")
-                except Exception:
-                    pass
+            if model_id is None:      # build.py:85-86: the first kept header that names a model
+                model_id = _header_model_id(p)
         else:
             print(f"[SKIP] {p.name}: {_skip_reason(p, int(st))}")
     if not keep:

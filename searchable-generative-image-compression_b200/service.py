@@ -50,13 +50,19 @@ class SearchService:
 
     def __init__(self, index_dir=None, *, index=None, paths: Optional[Sequence[str]] = None, meta: Optional[Dict] = None,
                  max_batch: int = 256, max_wait_ms: float = 1.0,
-                 preview_url: Optional[Callable[[str], Optional[str]]] = None):
+                 preview_url: Optional[Callable[[str], Optional[str]]] = None,
+                 max_topk: int = 1024, allowed_roots: Optional[Sequence] = None):
         if index is None:
             from .retrieval import load_index
             index, paths, meta = load_index(index_dir)
         self.index, self.paths, self.meta = index, list(paths), dict(meta or {})
         self.max_batch, self.max_wait = int(max_batch), float(max_wait_ms) / 1e3
         self.preview_url = preview_url or (lambda p: None)
+        # Untrusted callers (the TCP front end): topk is clamped to `max_topk`, and server-side paths are only
+        # opened below one of `allowed_roots` (none configured: no path requests over the socket, inline vectors
+        # only).  In-process callers are trusted like the reference's CLI is.
+        self.max_topk = max(1, int(max_topk))
+        self.allowed_roots = [Path(r).resolve() for r in (allowed_roots or [])]
         self._q: "queue.Queue[Optional[_Pending]]" = queue.Queue()
         self.stats = {"requests": 0, "batches": 0, "max_batch_seen": 0}
         self._worker = threading.Thread(target=self._run, name="sgic-search-batcher", daemon=True)
@@ -70,7 +76,10 @@ class SearchService:
                 return
             batch = [first]
             deadline = time.perf_counter() + self.max_wait
-            while len(batch) < self.max_batch:
+            # a request for more than `max_topk` results runs alone: k > 1024 is answered by repeated full scans,
+            # one query at a time, and must not drag the ordinary requests of its micro-batch onto that path
+            held: Optional[_Pending] = None
+            while len(batch) < self.max_batch and first.topk <= self.max_topk:
                 left = deadline - time.perf_counter()
                 try:
                     nxt = self._q.get(timeout=max(left, 0.0)) if left > 0 else self._q.get_nowait()
@@ -78,6 +87,9 @@ class SearchService:
                     break
                 if nxt is None:
                     self._q.put(None)
+                    break
+                if nxt.topk > self.max_topk:
+                    held = nxt
                     break
                 batch.append(nxt)
             try:
@@ -96,6 +108,8 @@ class SearchService:
             self.stats["max_batch_seen"] = max(self.stats["max_batch_seen"], len(batch))
             for p in batch:
                 p.done.set()
+            if held is not None:
+                self._q.put(held)       # next round, on its own
 
     def close(self) -> None:
         self._q.put(None)
@@ -129,11 +143,43 @@ class SearchService:
         """stdout of ``search.py`` (src/search.py:163-166), what webapp.py:249 feeds to ``json.loads``."""
         return json.dumps([{"path": p, "score": s} for p, s in results], ensure_ascii=False, indent=2)
 
-    def ndjson_events(self, request: Dict) -> Iterator[Dict]:
-        """Event dictionaries of one streamed search, in the order webapp.py:243-261 yields them."""
+    def _checked_path(self, p, trusted: bool) -> Path:
+        """Server-side path of a request.  Untrusted requests may only name files below an allowed root."""
+        path = Path(str(p))
+        if trusted:
+            return path
+        real = path.resolve()
+        for root in self.allowed_roots:
+            if real == root or root in real.parents:
+                return real
+        raise PermissionError("path outside the served roots")
+
+    @staticmethod
+    def _public_error(e: BaseException) -> str:
+        """What an untrusted client is told: the kind of failure, never the exception text (which can carry
+        server-side paths and library internals)."""
+        if isinstance(e, PermissionError):
+            return "path not allowed"
+        if isinstance(e, FileNotFoundError):
+            return "file not found"
+        if isinstance(e, NotImplementedError):
+            return "query type needs an embedding (send \"vec\")"
+        if isinstance(e, (ValueError, AssertionError, KeyError, TypeError)):
+            return "bad request"
+        return "search failed"
+
+    def ndjson_events(self, request: Dict, trusted: bool = True) -> Iterator[Dict]:
+        """Event dictionaries of one streamed search, in the order webapp.py:243-261 yields them.
+        ``trusted=False`` (the TCP front end): topk clamped to ``max_topk``, paths checked against
+        ``allowed_roots``, error details reduced to a category."""
         t0 = time.perf_counter()
         kind = request.get("type") or request.get("query_type") or "c2df"
-        topk = int(request.get("topk") or 10)
+        try:
+            topk = int(request.get("topk") or 10)
+        except (TypeError, ValueError):
+            topk = 10
+        if not trusted:
+            topk = max(1, min(topk, self.max_topk))
         start = {"type": "meta", "stage": "start", "query_type": kind, "topk": topk}
         if kind == "text":
             start["query"] = request.get("text", "")
@@ -144,9 +190,9 @@ class SearchService:
             if "vec" in request:
                 items = self.search_vec(np.asarray(request["vec"], dtype="float32"), topk)
             elif "vec_path" in request:
-                items = self.search_vec_file(request["vec_path"], topk)
+                items = self.search_vec_file(self._checked_path(request["vec_path"], trusted), topk)
             elif kind == "c2df":
-                items = self.search_c2df(request["path"], topk)
+                items = self.search_c2df(self._checked_path(request["path"], trusted), topk)
             else:
                 raise NotImplementedError(f"{kind} query without an embedding: the CLIP encoder is outside this path "
                                           "(send \"vec\" or \"vec_path\")")
@@ -156,7 +202,7 @@ class SearchService:
                 yield {"type": "item", "path": p, "score": float(s), "preview_url": self.preview_url(p)}
             yield {"type": "done", "elapsed_ms": ms()}
         except Exception as e:
-            yield {"type": "error", "detail": str(e)}
+            yield {"type": "error", "detail": str(e) if trusted else self._public_error(e)}
 
 
 class _Handler(socketserver.StreamRequestHandler):
@@ -169,9 +215,12 @@ class _Handler(socketserver.StreamRequestHandler):
             try:
                 req = json.loads(line)
             except ValueError as e:
-                self.wfile.write((json.dumps({"type": "error", "detail": f"bad request: {e}"}) + "\n").encode())
+                self.wfile.write((json.dumps({"type": "error", "detail": "bad request"}) + "\n").encode())
                 continue
-            for ev in svc.ndjson_events(req):
+            if not isinstance(req, dict):
+                self.wfile.write((json.dumps({"type": "error", "detail": "bad request"}) + "\n").encode())
+                continue
+            for ev in svc.ndjson_events(req, trusted=False):
                 self.wfile.write((json.dumps(ev, ensure_ascii=False) + "\n").encode("utf-8"))   # webapp._yield_ndjson
             self.wfile.flush()
 
@@ -198,8 +247,12 @@ def main(argv=None) -> None:
     ap.add_argument("--port", type=int, default=8765)
     ap.add_argument("--max_batch", type=int, default=256)
     ap.add_argument("--max_wait_ms", type=float, default=1.0)
+    ap.add_argument("--max_topk", type=int, default=1024, help="largest topk a socket client may ask for")
+    ap.add_argument("--allow_root", type=Path, action="append", default=[],
+                    help="directory whose files socket clients may name in \"path\" / \"vec_path\" (repeatable)")
     a = ap.parse_args(argv)
-    svc = SearchService(a.index_dir, max_batch=a.max_batch, max_wait_ms=a.max_wait_ms)
+    svc = SearchService(a.index_dir, max_batch=a.max_batch, max_wait_ms=a.max_wait_ms, max_topk=a.max_topk,
+                        allowed_roots=a.allow_root)
     srv = serve(svc, a.host, a.port)
     print(json.dumps({"listening": list(srv.server_address), "ntotal": svc.index.ntotal, "d": svc.index.d}), flush=True)
     try:

@@ -151,9 +151,15 @@ def test_build_index_from_c2df_dir_and_cli(tmp_path, capsys):
     assert res[0][0] == target and abs(res[0][1] - 1.0) < 1e-3 and len(res) == 5
     # row order == sorted path order: compare every stored row with the oracle decode
     rows = index.reconstruct_n(0, 40)
+    ref_rows = []
     for i, p in enumerate(want_paths):
         _, z = c2df_ref.decode_clip(open(p, "rb").read())
         assert np.abs(rows[i] - z).max() < 6e-4
+        ref_rows.append(z)
+    # the IxFI files are BYTE-identical to what build.py:91-99 writes: fp32 rows of the reference decode (the u8
+    # codes are retained on the host and re-expanded with numpy's operation order, not read back from fp16 HBM)
+    c2df_ref.write_ixfi(tmp_path / "ref.index", np.stack(ref_rows).astype(np.float32))
+    assert (out / "faiss.index").read_bytes() == (tmp_path / "ref.index").read_bytes()
     # CLI: stdout is exactly the JSON document webapp.py:249 parses
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
@@ -168,6 +174,101 @@ def test_build_index_from_c2df_dir_and_cli(tmp_path, capsys):
         (legacy / n).write_bytes((out / n).read_bytes())
     index2, paths2, meta2 = retrieval.load_index(legacy)
     assert paths2 == want_paths and meta2 == {"dim": 512, "model_id": "ViT-B-32:laion2b_s34b_b79k"}
+
+
+def test_build_ixfi_is_byte_identical_through_both_decode_routes(tmp_path):
+    """A corpus large enough for several device-decode slabs plus files the device profile rejects (raw-stored
+    frames go through libzstd on the host): codes are retained on either route and in file order."""
+    from sgic_b200 import c2df as c2, faiss_compat as faiss, zstd
+    from sgic_b200.index_build import quantize_u8_and_compress
+    rng = np.random.default_rng(21)
+    n, d = 70_000, 64                                  # > one slab of 65 536 files
+    vecs = rng.standard_normal((n, d)).astype(np.float32)
+    vecs /= np.linalg.norm(vecs, axis=1, keepdims=True)
+    blobs, codes = [], []
+    for i, v in enumerate(vecs):
+        stream, meta = quantize_u8_and_compress(v)
+        if i % 1000 == 7:                               # level-1 frame of noise: a raw block, host route
+            q = rng.integers(0, 256, d, dtype=np.uint8)
+            stream = zstd.compress(q.tobytes(), 1)
+        codes.append(np.frombuffer(zstd.decompress(stream), dtype=np.uint8))
+        blobs.append(c2.pack_c2df({"clip_stream": stream, "clip_meta": meta}, {"version": 2}))
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in blobs], out=offs[1:])
+    index = faiss.IndexFlatIP(d, device=0, retain_fp32=False, retain_codes=True)
+    added, status = index.add_c2df(np.frombuffer(b"".join(blobs), dtype=np.uint8), offs)
+    assert added == n and not status.any()
+    assert index.stat("retained_code_rows") == n
+    codes = np.stack(codes)
+    assert np.array_equal(index.codes(), codes)
+    faiss.write_index(index, str(tmp_path / "a.index"))
+    want = np.stack([c2df_ref.dequantize_clip_u8(q) for q in codes[:3000]])
+    got = c2df_ref.read_ixfi(tmp_path / "a.index")
+    assert got.shape == (n, d) and np.array_equal(got[:3000].view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(got, faiss.codes_to_f32(codes))
+    # an fp32 add afterwards invalidates the code copy: the writer falls back to the HBM rows
+    index.add(vecs[:2])
+    assert index.stat("retained_code_rows") == -1
+    with pytest.raises(RuntimeError, match="u8 codes"):
+        index.codes(0, 1)
+
+
+def test_build_fails_as_a_whole_on_mixed_dimensions(tmp_path):
+    """np.concatenate in build.py:91 raises when a decodable file has another dimension; nothing is written."""
+    from sgic_b200 import index_build
+    rng = np.random.default_rng(8)
+    src = tmp_path / "bitstreams"
+    src.mkdir()
+    v = rng.standard_normal((4, 512)).astype(np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    _write_corpus(src, v, rng)
+    w = rng.standard_normal((1, 768)).astype(np.float32)
+    w /= np.linalg.norm(w)
+    _write_corpus(src / "other", w, rng)
+    with pytest.raises(ValueError, match="must match exactly"):
+        index_build.build_index_from_c2df_dir(src, tmp_path / "faiss")
+    assert not (tmp_path / "faiss" / "faiss.index").exists()
+
+
+def test_calls_on_different_streams_are_ordered_by_the_library(tmp_path):
+    """add_torch on a side stream WITHOUT synchronising, then host-buffer search / reconstruct / save on the
+    index's own stream, then a device search on yet another stream: every call must see the rows (include/sgic.h,
+    "Streams")."""
+    import torch
+    from sgic_b200 import faiss_compat as faiss
+    dev = torch.device("cuda", 0)
+    d, n = 512, 600_000
+    g = torch.Generator(device=dev).manual_seed(5)
+    index = faiss.IndexFlatIP(d, device=0, retain_fp32=False, capacity=2 * n)
+    side, side2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    xs = []
+    for _ in range(2):
+        x = torch.randn((n, d), device=dev, generator=g)
+        x /= x.norm(dim=1, keepdim=True)
+        xs.append(x)
+    torch.cuda.synchronize(dev)
+    for rep, x in enumerate(xs):
+        with torch.cuda.stream(side):
+            big = torch.randn((4096, 4096), device=dev)
+            for _ in range(20):                       # keep the side stream busy so the add is still queued
+                big = big @ big * 1e-3
+            index.add_torch(x)
+        q = x[n - 1:n].cpu().numpy()
+        D, I = index.search(q, 1)                     # own stream, host buffers: no sync in between
+        assert I[0, 0] == (rep + 1) * n - 1 and abs(D[0, 0] - 1.0) < 2e-3
+        rows = index.reconstruct_n(index.ntotal - 1, 1)
+        assert np.abs(rows[0] - q[0]).max() < 1e-3
+    x = xs[1]
+    faiss.write_shard(index, str(tmp_path / "s.sgi2"))
+    back = faiss.read_index(str(tmp_path / "s.sgi2"), device=0)
+    assert back.ntotal == 2 * n and np.abs(back.reconstruct_n(2 * n - 1, 1)[0] - x[n - 1].cpu().numpy()).max() < 1e-3
+    back.close()
+    with torch.cuda.stream(side):
+        index.add_torch(x[:1000].clone())
+    with torch.cuda.stream(side2):
+        Dd, Id = index.search_torch(x[999:1000].contiguous(), 2)
+    side2.synchronize()
+    assert sorted(Id[0].tolist()) == [n + 999, 2 * n + 999]
 
 
 def test_from_npy_dir_matches_sorted_glob_order(tmp_path):

@@ -128,3 +128,26 @@ def test_oracle_decode_matches_reference_generated_vectors(golden):
         pos += d
     _, z = c2df_ref.decode_clip((golden / "apple.c2df").read_bytes())
     assert np.array_equal(z, g["apple_vec_from_c2df"])
+
+
+def test_codes_to_f32_is_bit_identical_to_the_reference_arithmetic(golden):
+    """sgic_codes_to_f32 (what write_index uses for an index that retains its u8 codes) against the reference's
+    own expression run by numpy, row by row as build.py:82 does: identical bits, every width."""
+    from oracle import c2df_ref
+    from sgic_b200 import faiss_compat
+    rng = np.random.default_rng(11)
+    for d in (8, 16, 64, 104, 128, 136, 256, 512, 520, 768, 1024, 1280, 2048):
+        q = rng.integers(0, 256, (300, d), dtype=np.uint8)
+        q[0] = 0
+        q[1] = 255
+        q[2] = 128                                   # z ~ 0.0039: tiny norm, eps guard not hit but close to it
+        q[3] = rng.integers(120, 136, d)             # CLIP-like narrow codes
+        got = faiss_compat.codes_to_f32(q)
+        want = np.stack([c2df_ref.dequantize_clip_u8(r) for r in q])
+        assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), want.view(np.uint32)), d
+    # the shipped pair: codes of apple.c2df -> the vector search.py derives from it (golden, reference-run)
+    g = np.load(golden / "c2df_golden.npz")
+    _, z = c2df_ref.decode_clip((golden / "apple.c2df").read_bytes())
+    codes = np.clip(np.round((np.load(golden / "apple.npy") * 0.5 + 0.5) * 255.0), 0, 255).astype(np.uint8)
+    assert np.array_equal(faiss_compat.codes_to_f32(codes[None, :])[0], g["apple_vec_from_c2df"])
+    assert np.array_equal(z, g["apple_vec_from_c2df"])

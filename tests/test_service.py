@@ -105,3 +105,44 @@ def test_ndjson_event_stream_and_socket_front_end(svc):
     finally:
         srv.shutdown()
         srv.server_close()
+
+
+def test_untrusted_requests_are_clamped_confined_and_told_little(svc, tmp_path):
+    """The TCP front end: topk clamped to max_topk, server-side paths only below an allowed root, no exception
+    text in error events; a huge-topk request from a trusted caller runs in a batch of its own."""
+    s, idx, xb = svc
+    s.max_topk = 8
+    ev = list(s.ndjson_events({"type": "image", "vec": xb[5].tolist(), "topk": 10 ** 9}, trusted=False))
+    assert ev[0]["topk"] == 8 and ev[1]["count"] == 8 and ev[-1]["type"] == "done"
+    # paths: nothing is served from the file system unless a root is configured, and never outside it
+    secret = tmp_path / "secret.npy"
+    np.save(secret, xb[9])
+    ev = list(s.ndjson_events({"type": "image", "vec_path": str(secret), "topk": 2}, trusted=False))
+    assert ev[-1] == {"type": "error", "detail": "path not allowed"}
+    root = tmp_path / "served"
+    root.mkdir()
+    np.save(root / "q.npy", xb[9])
+    s.allowed_roots = [root.resolve()]
+    ev = list(s.ndjson_events({"type": "image", "vec_path": str(root / "q.npy"), "topk": 2}, trusted=False))
+    assert ev[-1]["type"] == "done" and ev[2]["path"].endswith("img0009.c2df")
+    ev = list(s.ndjson_events({"type": "image", "vec_path": str(root / ".." / "secret.npy"), "topk": 2}, trusted=False))
+    assert ev[-1] == {"type": "error", "detail": "path not allowed"}
+    ev = list(s.ndjson_events({"type": "c2df", "path": str(root / "missing.c2df")}, trusted=False))
+    assert ev[-1] == {"type": "error", "detail": "file not found"}
+    assert str(root) not in json.dumps(ev)
+    ev = list(s.ndjson_events({"type": "image", "vec": [1.0, 2.0], "topk": "many"}, trusted=False))
+    assert ev[-1] == {"type": "error", "detail": "bad request"} and ev[0]["topk"] == 8
+    # trusted callers keep the reference's semantics (any topk), but a huge request never shares a batch
+    idx.calls.clear()
+    out = {}
+    barrier = threading.Barrier(9)
+
+    def worker(i, k):
+        barrier.wait()
+        out[i] = s.search_vec(xb[i], topk=k)
+
+    th = [threading.Thread(target=worker, args=(i, 3)) for i in range(8)] + [threading.Thread(target=worker, args=(8, 400))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert len(out[8]) == 400 and all(len(out[i]) == 3 for i in range(8))
+    assert (1, 400) in idx.calls and all(k == 3 for nq, k in idx.calls if (nq, k) != (1, 400))
