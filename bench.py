@@ -37,6 +37,8 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "queries/sec at k=10 on 100M×512 fp16 index (batch 1 / 4096); % HBM/TC roofline"
+TRAFFIC_NOTE = ("static: DRAM bytes per row from the committed ncu --set full capture of this kernel "
+                "(profiles/traffic.json) x the rows of this launch — not measured in this run")
 
 
 def parse_args():
@@ -50,8 +52,15 @@ def parse_args():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
-    ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=0,
+                    help="rows of the fp32 sample the CPU arm scans (0 = as many as fit a quarter of the free host "
+                         "RAM, at most 10M: 20 GB at d=512)")
+    ap.add_argument("--verify-queries", type=int, default=24,
+                    help="queries per batch size whose answer is re-scored by an independent torch matmul + topk")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--single-process", action="store_true",
+                    help="N GPUs behind ONE index object in THIS process (faiss.IndexFlatIP(d, devices=[0..N-1])), "
+                         "the way the reference's single-process callers would use them; not for torchrun")
     return ap.parse_args()
 
 
@@ -136,6 +145,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
+def auto_sample_rows(rows_full: int, d: int, requested: int) -> int:
+    """Rows of the CPU arm's fp32 sample: the request, or what a quarter of the free host RAM holds, capped at
+    10M rows (the largest N that fits; the flat scan is exactly linear in N)."""
+    if requested > 0:
+        return min(rows_full, requested)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 16 << 30
+    return int(max(1_000_000, min(rows_full, 10_000_000, (avail // 4) // (d * 4))))
+
+
+_SAMPLE_CACHE = {}
+
+
 def cpu_baseline(rows_full: int, d: int, k: int, batch: int, sample_rows: int, steps: int, warmup: int):
     """FAISS CPU flat-IP restatement on a bounded sample; qps scaled linearly to `rows_full`."""
     import numpy as np
@@ -143,13 +168,19 @@ def cpu_baseline(rows_full: int, d: int, k: int, batch: int, sample_rows: int, s
     from oracle import flat_ip_c
     L = flat_ip_c.load(native=True)
     blas = flat_ip_c.try_attach_blas(L) if batch >= 20 else None
-    n = min(rows_full, sample_rows)
+    n = auto_sample_rows(rows_full, d, sample_rows)
     if batch >= 20:   # sgemm path: keep one call near 1e12 flop so that the arm finishes in seconds
         n = min(n, max(100_000, int(1e12 / (2.0 * batch * d))))
     g = torch.Generator().manual_seed(1234)
-    xb = torch.randn((n, d), generator=g)
-    xb /= xb.norm(dim=1, keepdim=True)
-    xb = xb.numpy()
+    if (n, d) not in _SAMPLE_CACHE:
+        _SAMPLE_CACHE.clear()
+        xb = torch.empty((n, d))
+        for r0 in range(0, n, 1 << 20):          # chunked: no second copy of a 20 GB sample
+            blk = torch.randn((min(1 << 20, n - r0), d), generator=g)
+            blk /= blk.norm(dim=1, keepdim=True)
+            xb[r0:r0 + blk.shape[0]] = blk
+        _SAMPLE_CACHE[(n, d)] = xb.numpy()
+    xb = _SAMPLE_CACHE[(n, d)]
     q = torch.randn((batch, d), generator=g)
     q /= q.norm(dim=1, keepdim=True)
     q = q.numpy()
@@ -175,7 +206,11 @@ def cpu_baseline(rows_full: int, d: int, k: int, batch: int, sample_rows: int, s
         for _ in range(steps):
             flat_ip_c.flat_ip_search_c(xb, q, k, rowpar=True, native=True)
         dt2 = (time.perf_counter() - t0) / steps
-        out["optimistic_all_threads"] = {"value": batch / dt2 * n / rows_full, "cores": threads_avail}
+        # flat keys: what a reader of the line sees next to the faithful one-thread-per-query number
+        out["optimistic_all_threads_value"] = batch / dt2 * n / rows_full
+        out["optimistic_all_threads_cores"] = threads_avail
+        out["optimistic_all_threads_note"] = ("the single query's rows split over every host thread — NOT what FAISS "
+                                              "does for nq < 20, reported so that the GPU/CPU ratio is not flattered")
     return out
 
 
@@ -187,12 +222,15 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * args.batch / cb["value"], "higher_is_better": True, "scaling": "strong",
+        # the step that was actually timed: one search over the SAMPLE; `value` is that rate scaled to all rows
+        "ms_per_step": cb["ms_per_step_sample"], "ms_per_step_scaled_to_all_rows": 1e3 * args.batch / cb["value"],
+        "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.rows}x{args.dim} flat inner-product index, batch {args.batch}, k={args.k}",
                    "rows": args.rows, "dim": args.dim, "k": args.k, "batch": args.batch,
                    "note": "FAISS CPU flat-IP path restated in C (faiss-cpu not installable offline); "
-                           "bounded row sample scaled linearly"},
+                           "bounded row sample scaled linearly; one thread per query for nq < 20 as FAISS does "
+                           "(cpu_baseline.optimistic_all_threads_value = every host thread on the one query)"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -220,11 +258,25 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()
     d, k, nq, R = args.dim, args.k, args.batch, args.rows
+    n_front = args.gpus if (args.single_process and world == 1) else 1   # GPUs behind one index in this process
 
     # ---- the index: R rows, contiguous shard per rank ------------------------------------
     lo, hi = shard_range(R, world, rank)
     chunk = 500_000   # generator granularity: shard starts of 100M/{1,2,4,8} fall on chunk boundaries
-    if world > 1:
+    parts = None      # [(single-GPU index, first global row)] of the rows this process holds, for the re-score
+    if n_front > 1:
+        index = faiss.IndexFlatIP(d, dtype=args.dtype, devices=list(range(n_front)), retain_fp32=False)
+        parts = []
+        for g in range(n_front):
+            glo, ghi = shard_range(R, n_front, g)
+            if glo % chunk:
+                raise SystemExit(f"rows/gpus must keep shard starts on {chunk}-row boundaries")
+            sh = index.shard(g)
+            fill_index_random(sh, ghi - glo, row0=glo, chunk_rows=chunk)
+            parts.append((sh, glo))
+        index.adopt_shards()
+        local = index
+    elif world > 1:
         index = ShardedIndexFlatIP(d, dtype=args.dtype)
         # seeds are per chunk of the GLOBAL row number: any sharding holds the same database
         lo_al = (lo // chunk) * chunk
@@ -239,7 +291,9 @@ def run_ours(args):
         index = faiss.IndexFlatIP(d, dtype=args.dtype, device=local_rank, retain_fp32=False)
         fill_index_random(index, R, chunk_rows=chunk)
         local = index
-    n_local = local.ntotal
+    n_local = local.ntotal if n_front == 1 else parts[0][0].ntotal   # rows one GPU scans per search
+    if parts is None:
+        parts = [(local, lo)]
 
     def barrier():
         if world > 1:
@@ -247,6 +301,72 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     clk = ClockSampler(local_rank) if rank == 0 else None
+
+    def verify_one(q, out_dev, nq):
+        from sgic_b200.verify import compare_topk, rescore_topk
+        nv = min(nq, args.verify_queries)
+        sel = np.unique(np.linspace(0, nq - 1, nv).astype(np.int64))
+        st = torch.from_numpy(sel).to(dev)
+        refs = []
+        for part, base in parts:               # every GPU of this process re-scores its own rows
+            pdev = torch.device("cuda", part.device)
+            rs, ri = rescore_topk(part, q[st].contiguous().to(pdev), k, id_base=base)
+            refs.append((rs.to(dev), ri.to(dev)))
+        if len(refs) > 1:
+            cs, ci = torch.cat([r[0] for r in refs], 1).cpu().numpy(), torch.cat([r[1] for r in refs], 1).cpu().numpy()
+            kk = max(r[0].shape[1] for r in refs)
+            order = np.lexsort((ci, -cs), axis=1)[:, :kk]
+            ref_s = torch.from_numpy(np.take_along_axis(cs, order, 1)).to(dev)
+            ref_i = torch.from_numpy(np.take_along_axis(ci, order, 1)).to(dev)
+        else:
+            ref_s, ref_i = refs[0]
+        if world > 1:
+            kk = torch.tensor([ref_s.shape[1]], device=dev)
+            dist.all_reduce(kk, op=dist.ReduceOp.MAX)
+            kk = int(kk.item())
+            pad_s = torch.full((len(sel), kk), -1e30, dtype=torch.float64, device=dev)
+            pad_i = torch.full((len(sel), kk), -1, dtype=torch.int64, device=dev)
+            pad_s[:, :ref_s.shape[1]] = ref_s
+            pad_i[:, :ref_i.shape[1]] = ref_i
+            all_s = [torch.empty_like(pad_s) for _ in range(world)]
+            all_i = [torch.empty_like(pad_i) for _ in range(world)]
+            dist.all_gather(all_s, pad_s)
+            dist.all_gather(all_i, pad_i)
+            cs, ci = torch.cat(all_s, 1).cpu().numpy(), torch.cat(all_i, 1).cpu().numpy()
+            order = np.lexsort((np.where(ci < 0, 1 << 62, ci), -cs), axis=1)[:, :kk]
+            ref_s_h, ref_i_h = np.take_along_axis(cs, order, 1), np.take_along_axis(ci, order, 1)
+        else:
+            ref_s_h, ref_i_h = ref_s.cpu().numpy(), ref_i.cpu().numpy()
+        D, I = out_dev
+        return compare_topk(D[st].cpu().numpy(), I[st].cpu().numpy(), ref_s_h, ref_i_h, k, score_tol=3e-5)
+
+    def verify(q, out_dev, nq, search_dev):
+        """T3: the answer the timed loop produced, re-scored for a sample of its queries by a chunked
+        fp32 torch.matmul + topk over the stored rows (no kernel of this package), candidates re-scored in fp64.
+        Small batches are followed by further batches of fresh queries (untimed) until `--verify-queries` queries
+        have been checked.  N > 1: every GPU re-scores its own shard, the candidate lists are gathered and merged,
+        and the sharded answer must equal that merged reference — the N-GPU answer is checked, not assumed."""
+        if args.verify_queries <= 0:
+            return None
+        rec = verify_one(q, out_dev, nq)
+        rounds = 1
+        while rec["ok"] and rec["queries"] < args.verify_queries and rounds < 32:
+            q2 = torch.from_numpy(random_unit_queries(nq, d, seed=977 + rounds)).to(dev)
+            r2 = verify_one(q2, search_dev(q2), nq)
+            rounds += 1
+            rec = {"queries": rec["queries"] + r2["queries"], "k": k,
+                   "max_score_err": max(rec["max_score_err"], r2["max_score_err"]),
+                   "ids_outside_ties": rec["ids_outside_ties"] + r2["ids_outside_ties"],
+                   "unsorted_rows": rec["unsorted_rows"] + r2["unsorted_rows"],
+                   "padding_errors": rec["padding_errors"] + r2["padding_errors"], "ok": rec["ok"] and r2["ok"]}
+        rec["batches_checked"] = rounds
+        rec["method"] = ("independent chunked torch fp32 matmul + topk over the stored rows, fp64 re-score of the "
+                         "candidates" + (f"; per-shard candidates all-gathered over {world} ranks and merged" if world > 1 else "")
+                         + (f"; per-GPU candidates of the {n_front} shards of this process merged" if n_front > 1 else ""))
+        rec["score_tol"] = 3e-5
+        if not rec["ok"]:
+            raise SystemExit(f"PARITY FAILURE at batch {nq}: {rec}")
+        return rec
 
     def measure(nq, steps, warmup):
         """One batch size: device-resident throughput, end-to-end throughput, roofline of the scan kernel."""
@@ -278,18 +398,26 @@ def run_ours(args):
             search_dev(q)
         barrier()
         launches0 = local.stat("launches")
+        # "timing" = 2: every scan kernel of the timed loop is bracketed by a pair of CUDA events on its stream,
+        # recorded WITHOUT a synchronise and read back after the loop — roofline.kernel_ms is the mean launch
+        # duration inside the timed region itself, not of a separate loop
+        local.set_option("timing", 2)
+        local.scan_times_ms()
         if clk:
             clk.begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            search_dev(q)
+            out_dev = search_dev(q)
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
         if clk:
             windows.append(clk.end())
+        scan_ms_all = local.scan_times_ms(steps)
+        local.set_option("timing", 0)
         # + the exchange's own kernels per step: K5x push + wait/merge, or K5 merge after the NCCL all_gather
+        # (single-process multi-GPU: the merge on the home GPU is counted by the index itself)
         xk = 0 if world == 1 else (2 if (index.exchange == "peer" and nq * k <= index._peer.max_cands) else 1)
         launches = local.stat("launches") - launches0 + xk * steps
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -314,14 +442,12 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_qps = nq * steps / float(t.item())
-        # ---- roofline of the dominant kernel (the scan), CUDA events on its stream ---------------
-        local.set_option("timing", 1)
-        scan_ns = []
-        for _ in range(max(3, min(steps, 20))):
-            search_dev(q)
-            scan_ns.append(local.stat("last_scan_ns"))
-        local.set_option("timing", 0)
-        scan_ms = statistics.mean(scan_ns) / 1e6
+        # ---- parity of the timed answers: independent torch re-score of sampled queries --------------
+        parity = verify(q, out_dev, nq, search_dev)
+        # ---- roofline of the dominant kernel (the scan): its launches inside the timed region ----------
+        scan_ms = float(scan_ms_all.mean()) if len(scan_ms_all) else float("nan")
+        if len(scan_ms_all) == min(steps, 256) and not scan_ms <= (ms_total / steps) * 1.0005:
+            raise SystemExit(f"inconsistent timing: scan kernel {scan_ms} ms > step {ms_total / steps} ms")
         dense = nq >= local.stat("dense_min_nq")
         kernel = {0: "scan_small_kernel", 1: "scan_dense_kernel", 2: "scan_dense_t_kernel", 3: "scan_dense2_kernel",
                   4: "scan_dense2_kernel", 5: "scan_dense2b_kernel"}[local.stat("last_kernel")]
@@ -335,11 +461,13 @@ def run_ours(args):
                         "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"],
                         "peak_kind": "cuBLAS bf16 sustained (kernel timed inside a long step)",
                         "kernel": kernel, "algorithmic_flops_per_launch": flops, "kernel_ms": scan_ms,
+                        "kernel_ms_source": f"CUDA events around each of the {len(scan_ms_all)} launches of the timed region",
                         "frac_of_burst": achieved / pk["bf16_tflops"], "frac_of_nominal_2250": achieved / 2250.0}
             # DRAM bytes per launch from the committed ncu capture: the database-resident pair kernel reads every
             # row once per block of <= 4096 queries by construction
             if kernel == "scan_dense2b_kernel" and d == 512 and "dense2b_dram_bytes_per_row_d512" in tj:
                 roofline["traffic"] = tj["dense2b_dram_bytes_per_row_d512"] * n_local * ((nq + 4095) // 4096)
+                roofline["traffic_source"] = TRAFFIC_NOTE
         else:
             alg_bytes = n_local * d * 2
             achieved = alg_bytes / (scan_ms / 1e3) / 1e9
@@ -347,17 +475,21 @@ def run_ours(args):
                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
                         "kernel": kernel,
                         "algorithmic_bytes_per_launch": alg_bytes,
-                        "kernel_ms": scan_ms, "frac_of_nominal_8TBs": achieved / 8000.0}
+                        "kernel_ms": scan_ms,
+                        "kernel_ms_source": f"CUDA events around each of the {len(scan_ms_all)} launches of the timed region",
+                        "frac_of_nominal_8TBs": achieved / 8000.0}
             if not dense and "dram_bytes_per_row_d512" in tj and d == 512:   # from the committed ncu capture
                 roofline["traffic"] = tj["dram_bytes_per_row_d512"] * n_local
+                roofline["traffic_source"] = TRAFFIC_NOTE
             elif kernel == "scan_dense_t_kernel" and "dense_t_dram_bytes_per_row_d512" in tj and d == 512:
                 roofline["traffic"] = tj["dense_t_dram_bytes_per_row_d512"] * n_local
+                roofline["traffic_source"] = TRAFFIC_NOTE
         return {"batch": nq, "value": value, "ms_per_step": ms_total / steps, "steps": steps, "warmup": warmup,
                 "extra_warmup_steps": extra,
                 "gpu_launches": int(launches),
                 "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(nq * d * 4),
                         "d2h_bytes_per_step": int(nq * k * 12)},
-                "roofline": roofline, "_windows": windows}
+                "roofline": roofline, "parity": parity, "_windows": windows}
 
     nq = args.batch
     main = measure(nq, args.steps, args.warmup)
@@ -381,24 +513,37 @@ def run_ours(args):
 
     main = public(main)
     line = {
-        "metric": METRIC, "value": main["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": main["value"], "unit": "queries/s", "n_gpus": max(world, n_front), "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
-        "config": {"workload": f"{R}x{d} {args.dtype} index row-sharded over {world} GPU(s), batch {nq}, k={k}",
+        "config": {"workload": f"{R}x{d} {args.dtype} index row-sharded over {max(world, n_front)} GPU(s), batch {nq}, k={k}",
                    "rows": R, "dim": d, "k": k, "batch": nq, "rows_per_gpu": n_local,
-                   "exchange": (index.exchange if world > 1 else None),
+                   "processes": world, "gpus_per_process": n_front,
+                   "exchange": (index.exchange if world > 1 else
+                                "peer stores from the shards' final writers into the home GPU (one process)" if n_front > 1 else None),
                    "l2": f"inputs larger than L2: every step streams the {n_local * d * 2 / 1e9:.1f} GB shard from HBM"},
         "clocks": main["clocks"], "gpu_launches": main["gpu_launches"], "extra_warmup_steps": main["extra_warmup_steps"],
         "e2e": main["e2e"],
         "roofline": main["roofline"],
+        "parity": main["parity"],
     }
     for name, m in others.items():
         line[name] = public(m)
-    if world == 1:
+        # the batch regimes of the metric also ride inside `roofline`, which readers of the line keep whole
+        line["roofline"][name] = {"value": m["value"], "unit": "queries/s", "e2e": m["e2e"]["value"],
+                                  "ms_per_step": m["ms_per_step"], "kernel": m["roofline"]["kernel"],
+                                  "bound": m["roofline"]["bound"], "achieved": m["roofline"]["achieved"],
+                                  "achieved_unit": m["roofline"]["unit"], "peak": m["roofline"]["peak"],
+                                  "frac": m["roofline"]["frac"], "kernel_ms": m["roofline"]["kernel_ms"],
+                                  "traffic": m["roofline"].get("traffic"),
+                                  "parity": m["parity"]}
+    if world == 1 and n_front == 1:
         line["cpu_baseline"] = cpu_baseline(R, d, k, nq, args.cpu_sample_rows, max(3, min(args.steps, 10)), 1)
         if not args.no_extras:
             if "batch4096" in line:
                 line["batch4096"]["cpu_baseline"] = cpu_baseline(R, d, k, 4096, args.cpu_sample_rows, 2, 1)
+                line["roofline"]["batch4096"]["cpu_baseline_value"] = line["batch4096"]["cpu_baseline"]["value"]
+                line["roofline"]["batch4096"]["cpu_baseline_cores"] = line["batch4096"]["cpu_baseline"]["cores"]
             index.close()   # free the 100 GB index before the side configs allocate theirs
             line["extras"] = extras(faiss, fill_index_random, random_unit_queries, torch, dev, pk)
     print(json.dumps(line), flush=True)
@@ -489,7 +634,12 @@ def extras(faiss, fill_index_random, random_unit_queries, torch, dev, pk):
         m = statistics.median(ms)
         gbs = rows * d * 2 / m / 1e6
         md = statistics.median(ms_dirty)
+        from sgic_b200.verify import verify_search
+        par, _ = verify_search(idx, q, D, I, k)
+        if not par["ok"]:
+            raise SystemExit(f"PARITY FAILURE in {name}: {par}")
         res.append({"workload": name, "ms_per_step": m, "ms_best": min(ms), "queries_per_s": nq / m * 1e3, "GBs": gbs,
+                    "parity": par,
                     "frac_of_measured_hbm": gbs / pk["hbm_gbs"],
                     "l2": "flushed between iterations: 256 MB memset, then a 256 MB read so that no dirty lines are left",
                     "write_only_flush": {"ms_per_step": md, "GBs": rows * d * 2 / md / 1e6,
@@ -514,7 +664,13 @@ def extras(faiss, fill_index_random, random_unit_queries, torch, dev, pk):
         torch.cuda.synchronize(dev)
         m = e0.elapsed_time(e1) / 5
         tf = 2.0 * nq * rows * d / (m / 1e3) / 1e12
+        import numpy as np
+        from sgic_b200.verify import verify_search
+        par, _ = verify_search(idx, q, D, I, k, sample=np.linspace(0, nq - 1, 24).astype(np.int64))
+        if not par["ok"]:
+            raise SystemExit(f"PARITY FAILURE in C3: {par}")
         res.append({"workload": "C3: 10Mx768 fp16, batch 4096, k=100", "ms_per_step": m, "queries_per_s": nq / m * 1e3,
+                    "parity": par,
                     "TFLOPs": tf, "frac_of_measured_bf16_sustained": tf / pk["bf16_tflops_sustained"],
                     "frac_of_nominal_2250": tf / 2250.0, "l2": "database (15.4 GB) larger than L2"})
         idx.close()
@@ -524,7 +680,50 @@ def extras(faiss, fill_index_random, random_unit_queries, torch, dev, pk):
         res.append({"ingest": ingest_extra(faiss, dev)})
     except Exception as e:   # the ingest figure is a side measurement: never lose the headline line over it
         res.append({"ingest": {"error": repr(e)}})
+    try:
+        res.append({"index_load": load_rate_extra(faiss, fill_index_random, dev)})
+    except Exception as e:
+        res.append({"index_load": {"error": repr(e)}})
     return res
+
+
+def load_rate_extra(faiss, fill_index_random, dev, rows=5_000_000, d=512):
+    """how fast an index comes off the disk into HBM.  The reference re-reads the whole fp32 IxFI file
+    in every query process (src/search.py:69,76); here the same rows are written once as IxFI (fp32, interchange) and
+    once as an SGI2 shard file (rows as stored in HBM, half the bytes) and loaded back — fread into pinned memory
+    overlapped with the H2D copy of the previous chunk.  Files are read back right after they were written, i.e. from
+    the page cache: the figure is the loader's, not the disk's."""
+    import shutil
+    idx = faiss.IndexFlatIP(d, device=dev.index, retain_fp32=False)
+    fill_index_random(idx, rows)
+    tmp = Path(tempfile.mkdtemp(prefix="sgic_load_"))
+    out = {"workload": f"{rows}x{d} fp16 rows ({rows * d * 2 / 1e9:.2f} GB in HBM)", "page_cache": "warm"}
+    try:
+        t0 = time.perf_counter()
+        faiss.write_shard(idx, str(tmp / "a.sgi2"))
+        out["sgi2_write_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        back = faiss.read_index(str(tmp / "a.sgi2"), device=dev.index, retain_fp32=False)
+        dt = time.perf_counter() - t0
+        assert back.ntotal == rows
+        back.close()
+        gb = rows * d * 2 / 1e9
+        out["sgi2_load"] = {"seconds": dt, "GB_per_s": gb / dt, "rows_per_s": rows / dt,
+                            "seconds_for_100M_rows_at_this_rate": 100e6 * d * 2 / 1e9 / (gb / dt)}
+        small = min(rows, 1_000_000)   # the fp32 interchange file of a tenth of the rows: 4 bytes per element + conversion
+        sub = faiss.IndexFlatIP(d, device=dev.index, retain_fp32=False)
+        sub.add(idx.reconstruct_n(0, small))
+        faiss.write_index(sub, str(tmp / "a.index"))
+        sub.close()
+        t0 = time.perf_counter()
+        back = faiss.read_index(str(tmp / "a.index"), device=dev.index, retain_fp32=False)
+        dt = time.perf_counter() - t0
+        back.close()
+        out["ixfi_load"] = {"rows": small, "seconds": dt, "file_GB_per_s": small * d * 4 / 1e9 / dt, "rows_per_s": small / dt}
+    finally:
+        idx.close()
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
 
 
 if __name__ == "__main__":

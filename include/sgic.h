@@ -71,6 +71,33 @@ int sgic_version(void);
 int sgic_index_create(int d, int dtype, int device, int64_t capacity_rows, int flags, sgic_index** out);
 int sgic_index_destroy(sgic_index* h);
 
+/* The same index row-sharded over n_dev GPUs of this box, behind ONE handle and driven by ONE process — the
+ * reference's caller is a single process (src/search.py:149-162, webapp.py:246-248), so faiss.IndexFlatIP(d) has
+ * to be able to stand for all the GPUs.  Every entry point of this header takes the handle:
+ *   add*        large blocks are cut into n_dev contiguous slices (one per GPU), small ones go whole to one GPU;
+ *               add_c2df cuts the FILE list into n_dev slices that are walked / decoded concurrently, and a
+ *               file's row number is the count of good files before it, exactly as build.py:80-88 numbers them;
+ *   search      queries replicated, every GPU scans its rows on its own stream, the shards' final writers store
+ *               their (nq, k) answers with global row numbers straight into the home GPU's memory over NVLink
+ *               (peer access, no collective), one merge ordered (score desc, row asc) -> the answer is identical
+ *               to the single-GPU answer on the same rows;
+ *   *_dev       device buffers live on the HOME GPU = dev_ids[0] (sgic_index_device), `stream` is a stream of it;
+ *   write       IxFI in global row order; sgic_index_save_shards / sgic_index_load_shards keep one SGI2 file per GPU.
+ * dev_ids may name a GPU twice (two shards on one GPU: how the sharded logic is tested on a one-GPU box).
+ * capacity_rows is split evenly. */
+int sgic_index_create_sharded(int d, int dtype, int n_dev, const int* dev_ids, int64_t capacity_rows, int flags,
+                              sgic_index** out);
+/* shards behind a handle (1 for an ordinary index); the g-th shard as a BORROWED single-GPU handle — rows may be
+ * appended to the shards directly (bulk loaders, generators), after which sgic_index_adopt_shards makes them the
+ * index's rows: shard 0's rows first, then shard 1's, ... (one contiguous global range per GPU). */
+int sgic_index_n_shards(const sgic_index* h);
+int sgic_index_shard(sgic_index* h, int g, sgic_index** out);
+int sgic_index_adopt_shards(sgic_index* h);
+/* one "shard-%05d-of-%05d.sgi2" file per GPU under dir (written / read concurrently, rows as stored in HBM);
+ * load needs as many devices as there are files. */
+int sgic_index_save_shards(sgic_index* h, const char* dir);
+int sgic_index_load_shards(const char* dir, int n_dev, const int* dev_ids, int flags, sgic_index** out);
+
 /* index.ntotal / index.d — src/search.py:78,114; src/build.py:101,120,240. */
 int64_t sgic_index_ntotal(const sgic_index* h);
 int sgic_index_d(const sgic_index* h);
@@ -139,6 +166,11 @@ int sgic_xchg_export(sgic_xchg* x, uint8_t* handle64);
 int sgic_xchg_open(sgic_xchg* x, const uint8_t* handles /* world * 64 bytes, rank order */);
 int sgic_xchg_merge_dev(sgic_xchg* x, int64_t nq, int64_t k, const float* dev_D_local, const int64_t* dev_I_local,
                         float* dev_D, int64_t* dev_I, int tie_by_position, void* stream);
+/* A rank's whole search step with HOST buffers in one call (what sgic_index_search is for one GPU): H2D of the
+ * queries, local scan with id_base added to the row numbers, sgic_xchg_merge_dev, D2H of the merged answer.
+ * Collective like sgic_xchg_merge_dev; every rank receives the same (D, I). */
+int sgic_xchg_search(sgic_xchg* x, sgic_index* h, int64_t nq, const float* host_q, int64_t k, float* host_D,
+                     int64_t* host_I, int64_t id_base, int tie_by_position);
 int sgic_xchg_error(sgic_xchg* x);
 int sgic_xchg_destroy(sgic_xchg* x);
 
@@ -170,6 +202,10 @@ int sgic_index_reconstruct(sgic_index* h, int64_t i0, int64_t n, float* host_out
 /* Device pointer of the packed database and timing of the last search (kernel-only, ms,
  * measured with CUDA events on the index's stream when enabled). */
 const void* sgic_index_data_dev(const sgic_index* h);
+/* Option "timing" = 2 brackets the scan kernel of every search with a pair of CUDA events on the search's stream
+ * and does NOT synchronise; this call waits for the most recent of them and returns the durations (ms) of the
+ * last min(max_n, 256, searches since the previous call) scan kernels, oldest first, then forgets them. */
+int sgic_index_scan_times(sgic_index* h, int max_n, float* ms_out, int* n_out);
 int sgic_index_set_option(sgic_index* h, const char* name, int64_t value);
 int64_t sgic_index_get_stat(const sgic_index* h, const char* name);
 

@@ -1,0 +1,156 @@
+#!/usr/bin/env python
+"""Config C5 as BASELINE.json states it: a 1B x 512 fp16 index (~1 TB) row-sharded over 8 B200s, FILLED THROUGH THE
+BATCHED .c2df INGEST (build.py:71-103 -> sgic_index_add_c2df on a multi-GPU handle), then batch-256 / k = 10 searches
+— all from ONE process through the faiss-style object (faiss.IndexFlatIP(512, devices=[0..7])).
+
+    python scripts/c5_front.py [--gpus 8] [--rows 1000000000] [--distinct 1000000] [--batch 256] [--out file.json]
+
+The corpus is `--distinct` reference-style .c2df files (codec streams + clip_stream (zstd-19 of the u8 codes) +
+clip_meta, ~2.2 KB each) built once on the host cores; the 1B rows are that corpus replayed rows/distinct times
+(the replay factor is part of the record — 1B distinct files would be 2.2 TB of host memory).  Reported: ingest
+files/s and container GB/s including the HBM appends, the rows per GPU, search throughput device-resident and
+end to end, and the parity record of the timed answers (independent torch re-score on every GPU, merged)."""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+import numpy as np
+
+
+def _make_blobs(args):
+    seed, n, d = args
+    from sgic_b200 import c2df
+    from sgic_b200.index_build import quantize_u8_and_compress
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal((n, d)).astype(np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    fz = bytes(rng.integers(0, 256, 769, dtype=np.uint8))
+    fh = bytes(rng.integers(0, 256, 807, dtype=np.uint8))
+    out, lens = [], []
+    for z in v:
+        payload, meta = quantize_u8_and_compress(z)
+        b = c2df.pack_c2df({"z_bit_stream": fz, "h_bit_stream": fh, "img_shape": [1, 3, 256, 256], "token_length": 256,
+                            "clip_stream": payload, "clip_meta": meta}, {"version": 2})
+        out.append(b)
+        lens.append(len(b))
+    return b"".join(out), lens
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=8)
+    ap.add_argument("--rows", type=int, default=1_000_000_000)
+    ap.add_argument("--distinct", type=int, default=1_000_000)
+    ap.add_argument("--files-per-call", type=int, default=4_000_000)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    d = 512
+    # ---- corpus on the host cores (before CUDA is touched: the pool forks) ------------------------------------
+    import multiprocessing as mp
+    ncpu = os.cpu_count() or 8
+    per = 5000
+    t0 = time.perf_counter()
+    with mp.Pool(min(ncpu, 64)) as pool:
+        parts = pool.map(_make_blobs, [(1000 + i, min(per, a.distinct - i * per), d) for i in range((a.distinct + per - 1) // per)])
+    one = b"".join(p[0] for p in parts)
+    lens = np.concatenate([np.asarray(p[1], dtype=np.int64) for p in parts])
+    t_corpus = time.perf_counter() - t0
+    tile = max(1, a.files_per_call // a.distinct)
+    blob = np.frombuffer(one * tile, dtype=np.uint8)
+    offs = np.zeros(a.distinct * tile + 1, dtype=np.int64)
+    np.cumsum(np.tile(lens, tile), out=offs[1:])
+    files_per_call = a.distinct * tile
+    calls = a.rows // files_per_call
+    rows = calls * files_per_call
+    print(f"corpus: {a.distinct} files, {len(one) / 1e9:.2f} GB, built in {t_corpus:.1f} s on {min(ncpu, 64)} processes; "
+          f"{files_per_call} files per call x {calls} calls = {rows} rows", flush=True)
+
+    import torch
+    from sgic_b200 import faiss_compat as faiss
+    from sgic_b200.synth import random_unit_queries
+    from sgic_b200.verify import compare_topk, rescore_topk
+    G = a.gpus
+    index = faiss.IndexFlatIP(d, devices=list(range(G)), retain_fp32=False)
+    index.reserve(rows)
+    added, status = index.add_c2df(blob[:offs[200_000]], offs[:200_001])     # warm-up: buffers, contexts, kernels
+    assert added == 200_000 and not status.any()
+    index.reset()
+    t0 = time.perf_counter()
+    for c in range(calls):
+        added, status = index.add_c2df(blob, offs)
+        assert added == files_per_call, (added, int(status.sum()))
+    for g in range(G):
+        torch.cuda.synchronize(g)
+    t_ing = time.perf_counter() - t0
+    assert index.ntotal == rows
+    rec = {"config": f"C5: {rows}x{d} fp16 over {G} B200 in one process, filled through add_c2df", "rows": rows, "gpus": G,
+           "rows_per_gpu": [index.shard(g).ntotal for g in range(G)], "host_threads": ncpu,
+           "corpus": {"distinct_files": a.distinct, "bytes": len(one), "mean_file_bytes": len(one) / a.distinct,
+                      "replay_factor": rows / a.distinct, "build_seconds": t_corpus},
+           "ingest": {"seconds": t_ing, "files_per_s": rows / t_ing, "container_GB_per_s": len(one) * tile * calls / t_ing / 1e9,
+                      "hbm_GB_appended": rows * d * 2 / 1e9, "frames_decoded_on_device": index.stat("zl_device_frames"),
+                      "rows_decoded_on_host": index.stat("zl_host_rows"), "fallback_slabs": index.stat("zl_fallback_slabs")}}
+    print(json.dumps(rec["ingest"]), flush=True)
+
+    home = torch.device("cuda", 0)
+    searches = {}
+    for nq in (a.batch, 1):
+        qh = random_unit_queries(nq, d)
+        # a few queries are corpus rows pushed through the quantiser: their top-1 must be every replay of that file
+        q = torch.from_numpy(qh).to(home)
+        for _ in range(3):
+            D, I = index.search_torch(q, a.k)
+        torch.cuda.synchronize(home)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            D, I = index.search_torch(q, a.k)
+        e1.record()
+        torch.cuda.synchronize(home)
+        ms = e0.elapsed_time(e1) / a.steps
+        for _ in range(2):
+            index.search(qh, a.k)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            Dh, Ih = index.search(qh, a.k)
+        e2e_ms = (time.perf_counter() - t0) / a.steps * 1e3
+        # parity: every GPU re-scores its own rows for a sample of the queries, candidates merged on the host
+        sel = np.unique(np.linspace(0, nq - 1, min(nq, 16)).astype(np.int64))
+        cs, ci, start = [], [], 0
+        for g in range(G):
+            sh = index.shard(g)
+            pdev = torch.device("cuda", sh.device)
+            rs, ri = rescore_topk(sh, q[torch.from_numpy(sel).to(home)].to(pdev), a.k, id_base=start, chunk_rows=1 << 19)
+            cs.append(rs.cpu().numpy())
+            ci.append(ri.cpu().numpy())
+            start += sh.ntotal
+        cs, ci = np.concatenate(cs, 1), np.concatenate(ci, 1)
+        order = np.lexsort((ci, -cs), axis=1)[:, :a.k + 16]
+        par = compare_topk(D[torch.from_numpy(sel).to(home)].cpu().numpy(), I[torch.from_numpy(sel).to(home)].cpu().numpy(),
+                           np.take_along_axis(cs, order, 1), np.take_along_axis(ci, order, 1), a.k, score_tol=3e-5)
+        assert par["ok"], par
+        assert np.array_equal(Ih, I.cpu().numpy())
+        n_local = max(rec["rows_per_gpu"])
+        searches[f"batch{nq}"] = {"ms_per_step": ms, "queries_per_s": nq / ms * 1e3, "e2e_ms_per_step": e2e_ms,
+                                  "e2e_queries_per_s": nq / e2e_ms * 1e3, "parity": par,
+                                  "per_gpu_TFLOPs": 2.0 * nq * n_local * d / (ms / 1e3) / 1e12,
+                                  "per_gpu_GBs": n_local * d * 2 / (ms / 1e3) / 1e9}
+        print(json.dumps({f"batch{nq}": searches[f"batch{nq}"]}), flush=True)
+    rec["search"] = searches
+    print(json.dumps(rec), flush=True)
+    if a.out:
+        Path(a.out).write_text(json.dumps(rec, indent=1))
+    index.close()
+
+
+if __name__ == "__main__":
+    main()

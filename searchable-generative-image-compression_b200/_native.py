@@ -25,6 +25,13 @@ _SIGNATURES = {
     "sgic_version": (C.c_int, []),
     "sgic_index_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
     "sgic_index_destroy": (C.c_int, [C.c_void_p]),
+    "sgic_index_create_sharded": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int64, C.c_int,
+                                            C.POINTER(C.c_void_p)]),
+    "sgic_index_n_shards": (C.c_int, [C.c_void_p]),
+    "sgic_index_shard": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "sgic_index_adopt_shards": (C.c_int, [C.c_void_p]),
+    "sgic_index_save_shards": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "sgic_index_load_shards": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "sgic_index_ntotal": (C.c_int64, [C.c_void_p]),
     "sgic_index_d": (C.c_int, [C.c_void_p]),
     "sgic_index_dtype": (C.c_int, [C.c_void_p]),
@@ -50,6 +57,8 @@ _SIGNATURES = {
     "sgic_xchg_open": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sgic_xchg_merge_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int, C.c_void_p]),
+    "sgic_xchg_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_int64, C.c_int]),
     "sgic_xchg_error": (C.c_int, [C.c_void_p]),
     "sgic_xchg_destroy": (C.c_int, [C.c_void_p]),
     "sgic_index_write": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -60,6 +69,7 @@ _SIGNATURES = {
     "sgic_index_codes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "sgic_codes_to_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "sgic_index_data_dev": (C.c_void_p, [C.c_void_p]),
+    "sgic_index_scan_times": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "sgic_index_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "sgic_index_get_stat": (C.c_int64, [C.c_void_p, C.c_char_p]),
 }

@@ -43,6 +43,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// one lane of the (converged) warp: elect.sync.  The MMA issuers run their loops on the whole warp with
+// warp-uniform operands (descriptors, ring slots, TMEM addresses then live in uniform registers) and issue under
+// this predicate — a loop run by `lane == 0` alone makes the compiler shuttle every operand from vector to uniform
+// registers with an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence in front of every UTCHMMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }

@@ -759,7 +759,11 @@ scan_dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
+    // whole warp, warp-uniform operands, one elected lane issues (see ptx::elect_one)
+    {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t stages_u = ptx::smem_u32(stages);
+      const uint32_t idesc = p.idesc, kcs = p.kc, a_region = p.a_region;
       uint32_t s = 0, round = 0, tc = 0;
       for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t slice = item / p.m_tiles;
@@ -768,23 +772,27 @@ scan_dense_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
           const uint32_t as = tc & 1, ua = tc >> 1;
           if (ua > 0) ptx::mbar_wait(&acc_empty[as], (ua - 1) & 1);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * BN;
-          for (uint32_t kc = 0; kc < p.kc; ++kc) {
+          const uint32_t d_tmem = tmem_u + as * BN;
+          for (uint32_t kc = 0; kc < kcs; ++kc) {
             ptx::mbar_wait(&full[s], round & 1);
             ptx::tc_fence_after();
-            const uint32_t a_addr = ptx::smem_u32(stages + static_cast<size_t>(s) * stage_bytes);
+            const uint32_t a_addr = stages_u + s * stage_bytes;
             const uint64_t a_desc = ptx::umma_desc_k_sw128(a_addr);
-            const uint64_t b_desc = ptx::umma_desc_k_sw128(a_addr + p.a_region);
+            const uint64_t b_desc = ptx::umma_desc_k_sw128(a_addr + a_region);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (uint32_t kk = 0; kk < kDenseBK / 16; ++kk)
-              ptx::tc_mma_f16(d_tmem, a_desc + kk * 2, b_desc + kk * 2, p.idesc, (kc | kk) != 0 ? 1u : 0u);
-            ptx::tc_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
+              for (uint32_t kk = 0; kk < kDenseBK / 16; ++kk)
+                ptx::tc_mma_f16(d_tmem, a_desc + kk * 2, b_desc + kk * 2, idesc, (kc | kk) != 0 ? 1u : 0u);
+              ptx::tc_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
+            }
+            __syncwarp();
             if (++s == ns) {
               s = 0;
               ++round;
             }
           }
-          ptx::tc_commit(&acc_full[as]);  // accumulator of this tile complete
+          if (ptx::elect_one()) ptx::tc_commit(&acc_full[as]);  // accumulator of this tile complete
+          __syncwarp();
         }
       }
     }
@@ -897,9 +905,13 @@ scan_dense_t_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
+    // whole warp, warp-uniform operands, one elected lane issues (see ptx::elect_one)
+    {
       ptx::mbar_wait(q_full, 0);
       ptx::tc_fence_after();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t stages_u = ptx::smem_u32(stages), q_res_u = ptx::smem_u32(q_res);
+      const uint32_t idesc = p.idesc, kcs = p.kc, n_pad = p.n_pad;
       uint32_t s = 0, round = 0, tc = 0;
       for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t t0 = item * p.tiles_per_slice, t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
@@ -907,27 +919,31 @@ scan_dense_t_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           const uint32_t as = tc & 1, ua = tc >> 1;
           if (ua > 0) ptx::mbar_wait(&acc_empty[as], (ua - 1) & 1);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * 256u;
-          for (uint32_t kc = 0; kc < p.kc; ++kc) {
+          const uint32_t d_tmem = tmem_u + as * 256u;
+          for (uint32_t kc = 0; kc < kcs; ++kc) {
             ptx::mbar_wait(&full[s], round & 1);
             ptx::tc_fence_after();
-            const uint32_t db_addr = ptx::smem_u32(stages + static_cast<size_t>(s) * kDtStageBytes);
-            const uint64_t q_desc = ptx::umma_desc_k_sw128(ptx::smem_u32(q_res + static_cast<size_t>(kc) * q_chunk));
+            const uint32_t db_addr = stages_u + s * kDtStageBytes;
+            const uint64_t q_desc = ptx::umma_desc_k_sw128(q_res_u + kc * q_chunk);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (uint32_t sub = 0; sub < 2; ++sub) {
-              const uint64_t db_desc = ptx::umma_desc_k_sw128(db_addr + sub * (128u * kDenseBK * 2u));
+              for (uint32_t sub = 0; sub < 2; ++sub) {
+                const uint64_t db_desc = ptx::umma_desc_k_sw128(db_addr + sub * (128u * kDenseBK * 2u));
 #pragma unroll
-              for (uint32_t kk = 0; kk < kDenseBK / 16; ++kk)
-                ptx::tc_mma_f16(d_tmem + sub * p.n_pad, db_desc + kk * 2, q_desc + kk * 2, p.idesc,
-                                (kc | kk) != 0 ? 1u : 0u);
+                for (uint32_t kk = 0; kk < kDenseBK / 16; ++kk)
+                  ptx::tc_mma_f16(d_tmem + sub * n_pad, db_desc + kk * 2, q_desc + kk * 2, idesc,
+                                  (kc | kk) != 0 ? 1u : 0u);
+              }
+              ptx::tc_commit(&empty[s]);
             }
-            ptx::tc_commit(&empty[s]);
+            __syncwarp();
             if (++s == ns) {
               s = 0;
               ++round;
             }
           }
-          ptx::tc_commit(&acc_full[as]);
+          if (ptx::elect_one()) ptx::tc_commit(&acc_full[as]);
+          __syncwarp();
         }
       }
     }
@@ -1193,8 +1209,14 @@ scan_dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
-      uint32_t it = 0, tc = 0, ic = 0;
+    // The whole warp runs the loops on warp-uniform values and one elected lane issues (ptx::elect_one): the
+    // descriptors stay in uniform registers.  ncu on C3 (10M x 768, nq = 4096) showed the issuing thread itself was
+    // the critical path — ~105 instructions per K chunk, 663 cycles against 512 cycles of tensor work.
+    if (leader) {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t stages_u = ptx::smem_u32(stages), a_res_u = ptx::smem_u32(a_res);
+      const uint32_t idesc = p.idesc, kcs = p.kc;
+      uint32_t s = 0, ph = 0, tc = 0, ic = 0;  // ring slot and its phase bit (no division in the loop)
       for (uint32_t item = pair; item < n_items; item += n_pairs, ++ic) {
         const uint32_t slice = item / p.m_tiles;
         const uint32_t t0 = slice * p.tiles_per_slice, t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
@@ -1206,23 +1228,33 @@ scan_dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           const uint32_t as = tc & 1, ua = tc >> 1;
           if (ua > 0) ptx::mbar_wait(&acc_empty[as], (ua - 1) & 1);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * BN;
-          for (uint32_t kc = 0; kc < p.kc; ++kc, ++it) {
-            const uint32_t s = it % NS;
-            ptx::mbar_wait(&full[s], (it / NS) & 1);
+          const uint32_t d_tmem = tmem_u + as * BN;
+          for (uint32_t kc = 0; kc < kcs; ++kc) {
+            ptx::mbar_wait(&full[s], ph);
             ptx::tc_fence_after();
-            const uint32_t st_addr = ptx::smem_u32(stages + static_cast<size_t>(s) * kStage);
-            const uint32_t a_addr = ARES ? ptx::smem_u32(a_res + static_cast<size_t>(kc) * kD2HalfBytes) : st_addr;
+            const uint32_t st_addr = stages_u + s * kStage;
+            const uint32_t a_addr = ARES ? a_res_u + kc * kD2HalfBytes : st_addr;
             const uint64_t a_desc = ptx::umma_desc_k_sw128(a_addr);
             const uint64_t b_desc = ptx::umma_desc_k_sw128(ARES ? st_addr : st_addr + kD2HalfBytes);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (uint32_t kk = 0; kk < kDenseBK / 16; ++kk)
-              ptx2::tc_mma2_f16(d_tmem, a_desc + kk * 2, b_desc + kk * 2, p.idesc, (kc | kk) != 0 ? 1u : 0u);
-            ptx2::tc_commit2(&empty[s], 3);
+              for (uint32_t kk = 0; kk < kDenseBK / 16; ++kk)
+                ptx2::tc_mma2_f16(d_tmem, a_desc + kk * 2, b_desc + kk * 2, idesc, (kc | kk) != 0 ? 1u : 0u);
+              ptx2::tc_commit2(&empty[s], 3);
+            }
+            __syncwarp();
+            if (++s == NS) {
+              s = 0;
+              ph ^= 1u;
+            }
           }
-          ptx2::tc_commit2(&acc_full[as], 3);
+          if (ptx::elect_one()) ptx2::tc_commit2(&acc_full[as], 3);
+          __syncwarp();
         }
-        if (ARES) ptx2::tc_commit2(a_free, 3);
+        if (ARES) {
+          if (ptx::elect_one()) ptx2::tc_commit2(a_free, 3);
+          __syncwarp();
+        }
       }
     }
   } else {
@@ -1370,29 +1402,37 @@ scan_dense2b_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    // whole warp, warp-uniform operands, one elected lane issues (see ptx::elect_one)
+    if (leader) {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t stages_u = ptx::smem_u32(stages), b_res_u = ptx::smem_u32(b_res);
+      const uint32_t idesc = p.idesc;
       uint32_t g = 0, tc = 0;
       for (uint32_t ti = 0; ti < n_my; ++ti) {
         for (uint32_t mi = 0; mi < MT; ++mi, ++tc) {
           const uint32_t as = tc & 1, ua = tc >> 1;
           if (ua > 0) ptx::mbar_wait(&acc_empty[as], (ua - 1) & 1);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * BN;
+          const uint32_t d_tmem = tmem_u + as * BN;
           for (uint32_t kc = 0; kc < KC; ++kc, ++g) {
             const uint32_t s = g % NS;
             const uint32_t b = ti * KC + kc, slot = b % NB;
             ptx::mbar_wait(&b_full[slot], (b / NB) & 1);  // completes once per tile; later query tiles pass at once
             ptx::mbar_wait(&full[s], (g / NS) & 1);
             ptx::tc_fence_after();
-            const uint64_t a_desc = ptx::umma_desc_k_sw128(ptx::smem_u32(stages + static_cast<size_t>(s) * kD2HalfBytes));
-            const uint64_t b_desc = ptx::umma_desc_k_sw128(ptx::smem_u32(b_res + static_cast<size_t>(slot) * kD2HalfBytes));
+            const uint64_t a_desc = ptx::umma_desc_k_sw128(stages_u + s * kD2HalfBytes);
+            const uint64_t b_desc = ptx::umma_desc_k_sw128(b_res_u + slot * kD2HalfBytes);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (uint32_t kk = 0; kk < kDenseBK / 16; ++kk)
-              ptx2::tc_mma2_f16(d_tmem, a_desc + kk * 2, b_desc + kk * 2, p.idesc, (kc | kk) != 0 ? 1u : 0u);
-            ptx2::tc_commit2(&empty[s], 3);
-            if (mi + 1 == MT) ptx2::tc_commit2(&b_free[slot], 3);  // last query tile: the chunk slot may be refilled
+              for (uint32_t kk = 0; kk < kDenseBK / 16; ++kk)
+                ptx2::tc_mma2_f16(d_tmem, a_desc + kk * 2, b_desc + kk * 2, idesc, (kc | kk) != 0 ? 1u : 0u);
+              ptx2::tc_commit2(&empty[s], 3);
+              if (mi + 1 == MT) ptx2::tc_commit2(&b_free[slot], 3);  // last query tile: the chunk slot may be refilled
+            }
+            __syncwarp();
           }
-          ptx2::tc_commit2(&acc_full[as], 3);
+          if (ptx::elect_one()) ptx2::tc_commit2(&acc_full[as], 3);
+          __syncwarp();
         }
       }
     }

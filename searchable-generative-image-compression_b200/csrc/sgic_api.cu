@@ -4,7 +4,12 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -69,7 +74,17 @@ struct DeviceGuard {
 
 }  // namespace sgic
 
+namespace sgic {
+struct ShardSeg {  // a run of consecutive rows of a shard: global rows [g0, g0 + cnt) = local rows [l0, l0 + cnt)
+  int64_t g0, l0, cnt;
+};
+}  // namespace sgic
+
 struct sgic_index {
+  // multi-GPU front (sgic_index_create_sharded): `shards` holds one ordinary index per GPU and `front` the
+  // gather / staging state (sharded_front.inl); d, dtype, device (= home GPU) and ntotal describe the whole index
+  std::vector<sgic_index*> shards;
+  void* front = nullptr;
   int d = 0, dtype = SGIC_F16, device = 0, flags = 0;
   int64_t ntotal = 0, capacity = 0;
   void* db = nullptr;
@@ -116,6 +131,12 @@ struct sgic_index {
   void* opin = nullptr;
   size_t opin_bytes = 0;
   cudaEvent_t t0 = nullptr, t1 = nullptr, tm = nullptr;
+  // "timing" = 2: the scan kernel of every search is bracketed by a pair of events from this ring WITHOUT a
+  // synchronise, so that a caller can time its own loop and read the kernels' durations afterwards
+  // (sgic_index_scan_times) — the roofline figure of bench.py comes from inside its timed region this way
+  static constexpr int kTimeRing = 256;
+  std::vector<cudaEvent_t> ring_a, ring_b;
+  int64_t ring_n = 0;
   // Cross-stream ordering.  The *_dev entry points enqueue on the CALLER's stream, the host-buffer calls on the
   // index's own stream, and all of them share the database and the search workspaces: every call first makes its
   // stream wait for the work the previous call left on a different stream (order_begin / order_end below).
@@ -160,6 +181,26 @@ static int order_end(sgic_index* h, cudaStream_t st) {
   h->last_stream = st;
   h->last_stream_valid = true;
   if (st != h->stream) SGIC_CUDA(cudaEventRecord(h->ev_order, st));
+  return 0;
+}
+
+static int ring_mark(sgic_index* h, bool begin, cudaStream_t st) {
+  if (h->opt_timing != 2) return 0;
+  if (h->ring_a.empty()) {
+    h->ring_a.resize(sgic_index::kTimeRing);
+    h->ring_b.resize(sgic_index::kTimeRing);
+    for (int i = 0; i < sgic_index::kTimeRing; ++i) {
+      SGIC_CUDA(cudaEventCreate(&h->ring_a[i]));
+      SGIC_CUDA(cudaEventCreate(&h->ring_b[i]));
+    }
+  }
+  const int slot = static_cast<int>(h->ring_n % sgic_index::kTimeRing);
+  if (begin) {
+    SGIC_CUDA(cudaEventRecord(h->ring_a[slot], st));
+  } else {
+    SGIC_CUDA(cudaEventRecord(h->ring_b[slot], st));
+    h->ring_n++;
+  }
   return 0;
 }
 
@@ -463,7 +504,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
   int rc = make_tmap_rows(&tm_db, h->db, n_rows, static_cast<uint32_t>(h->d), pairs ? kDenseBM : kDenseBN, h->dtype);
   if (rc) return rc;
 
-  if (h->opt_timing) SGIC_CUDA(cudaEventRecord(h->t0, st));
+  if (h->opt_timing == 1) SGIC_CUDA(cudaEventRecord(h->t0, st));
   for (int64_t q0 = 0; q0 < nq; q0 += kDenseQueryBlock) {
     const uint32_t nqb = static_cast<uint32_t>(std::min<int64_t>(kDenseQueryBlock, nq - q0));
     const uint32_t m_tiles = (nqb + q_tile - 1) / q_tile;
@@ -578,13 +619,15 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
                                          static_cast<int>(kSmemBudget)));
           b_configured[h->device & 63] = true;
         }
+        if (q0 == 0 && (rc = ring_mark(h, true, st))) return rc;
         scan_dense2b_kernel<<<units_b * 2, kDenseThreads, dense_b_smem_bytes(m_tiles), st>>>(tm_qb, tm_db, bp);
         h->stat_launches++;
         SGIC_CUDA(cudaGetLastError());
+        if (q0 == 0 && (rc = ring_mark(h, false, st))) return rc;
         h->stat_last_grid = units_b * 2;
         h->stat_last_stages = kD2bStages;
         h->stat_last_kernel = 5;
-        if (h->opt_timing && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));
+        if (h->opt_timing == 1 && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));
         rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nqb, units_b, static_cast<uint32_t>(k),
                                dev_D + static_cast<size_t>(q0) * k, dev_I + static_cast<size_t>(q0) * k, id_base, st,
                                /*sorted_lists=*/cap_b <= 64u);
@@ -650,6 +693,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     // empty lists where a CTA resumes its own slot; the by-slice schedule writes every list in full
     if (transposed || !by_slice) SGIC_CUDA(cudaMemsetAsync(h->ws, 0, partial_bytes, st));
     if (!transposed && p.gthr) SGIC_CUDA(cudaMemsetAsync(p.gthr, 0, gthr_bytes, st));
+    if (q0 == 0 && (rc = ring_mark(h, true, st))) return rc;
     if (transposed) {
       DenseTParams tp_;
       tp_.partial = p.partial;
@@ -682,13 +726,14 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     h->stat_last_grid = grid;
     h->stat_last_stages = transposed ? t_stages : pairs ? 4 : p.n_stages;
     h->stat_last_kernel = transposed ? 2 : !pairs ? 1 : a_resident ? 3 : 4;
-    if (h->opt_timing && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));
+    if (q0 == 0 && (rc = ring_mark(h, false, st))) return rc;
+    if (h->opt_timing == 1 && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));
     rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nqb, transposed ? grid_units : n_lists,
                            static_cast<uint32_t>(k), dev_D + static_cast<size_t>(q0) * k,
                            dev_I + static_cast<size_t>(q0) * k, id_base, st, /*sorted_lists=*/tp || transposed);
     if (rc) return rc;
   }
-  if (h->opt_timing) {
+  if (h->opt_timing == 1) {
     SGIC_CUDA(cudaEventRecord(h->t1, st));
     SGIC_CUDA(cudaEventSynchronize(h->t1));
     float ms = 0.f;
@@ -816,7 +861,7 @@ static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     h->ws_counter = counter;
   }
 
-  if (h->opt_timing) SGIC_CUDA(cudaEventRecord(h->t0, st));
+  if (h->opt_timing == 1) SGIC_CUDA(cudaEventRecord(h->t0, st));
   for (int64_t q0 = 0; q0 < nq; q0 += NQ) {
     const uint32_t nq_here = static_cast<uint32_t>(std::min<int64_t>(NQ, nq - q0));
     ScanSmallParams p;
@@ -844,6 +889,10 @@ static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.bound = bound;
     p.trace = reinterpret_cast<unsigned long long*>(static_cast<uintptr_t>(h->opt_trace));
     cudaError_t e;
+    if (q0 == 0) {
+      int rrc = ring_mark(h, true, st);
+      if (rrc) return rrc;
+    }
     if (n_rows > 0) {
       if (h->dtype == SGIC_F16) e = launch_scan_t<__half>(p, NQ, cfg.cpl, cfg.rb, grid, smem, st);
       else e = launch_scan_t<__nv_bfloat16>(p, NQ, cfg.cpl, cfg.rb, grid, smem, st);
@@ -855,13 +904,17 @@ static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     } else {
       SGIC_CUDA(cudaMemsetAsync(h->ws, 0, static_cast<size_t>(NQ) * grid * k * 8, st));
     }
-    if (h->opt_timing && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));  // first scan launch alone
+    if (q0 == 0) {
+      int rrc = ring_mark(h, false, st);
+      if (rrc) return rrc;
+    }
+    if (h->opt_timing == 1 && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));  // first scan launch alone
     if (fused) continue;
     int rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nq_here, grid, static_cast<uint32_t>(k),
                                dev_D + static_cast<size_t>(q0) * k, dev_I + static_cast<size_t>(q0) * k, id_base, st);
     if (rc) return rc;
   }
-  if (h->opt_timing) {
+  if (h->opt_timing == 1) {
     SGIC_CUDA(cudaEventRecord(h->t1, st));
     SGIC_CUDA(cudaEventSynchronize(h->t1));
     float ms = 0.f;
@@ -953,6 +1006,25 @@ static_assert(sizeof(IxfiHeader) == 45, "IxFI header is 45 bytes (SURVEY.md §8a
 
 using namespace sgic;
 
+namespace sgic {
+static bool is_front(const sgic_index* h) { return h != nullptr && !h->shards.empty(); }
+static void front_destroy(sgic_index* f);
+static int front_search_host(sgic_index* f, int64_t nq, const float* host_q, int64_t k, float* host_D, int64_t* host_I);
+static int front_search_dev(sgic_index* f, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
+                            int64_t id_base, cudaStream_t stream);
+static int front_add_host(sgic_index* f, int64_t n, const void* host, int kind);
+static int front_add_dev(sgic_index* f, int64_t n, const void* dev, int kind, cudaStream_t stream);
+static int front_add_c2df(sgic_index* f, const uint8_t* blob, const int64_t* offsets, int64_t n, int32_t* status_out,
+                          int64_t* n_added, int n_threads);
+static int front_reconstruct(sgic_index* f, int64_t i0, int64_t n, float* host_out);
+static int front_codes(sgic_index* f, int64_t i0, int64_t n, uint8_t* host_out);
+static int front_write_mode(const sgic_index* f);
+static int front_rows_for_write(sgic_index* f, int mode, int64_t i0, int64_t n, float* out);
+static int front_set_option(sgic_index* f, const std::string& name, int64_t value);
+static int64_t front_get_stat(const sgic_index* f, const std::string& name, bool* handled);
+static int front_reset(sgic_index* f);
+}  // namespace sgic
+
 extern "C" {
 
 const char* sgic_last_error(void) { return g_err.c_str(); }
@@ -1009,6 +1081,11 @@ int sgic_index_create(int d, int dtype, int device, int64_t capacity_rows, int f
 
 int sgic_index_destroy(sgic_index* h) {
   if (!h) return 0;
+  if (is_front(h) || h->front) {
+    front_destroy(h);
+    delete h;
+    return 0;
+  }
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (int i = 0; i < 2; ++i) {
@@ -1041,6 +1118,8 @@ int sgic_index_destroy(sgic_index* h) {
   if (h->t1) cudaEventDestroy(h->t1);
   if (h->tm) cudaEventDestroy(h->tm);
   if (h->ev_order) cudaEventDestroy(h->ev_order);
+  for (cudaEvent_t e : h->ring_a) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ring_b) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -1054,6 +1133,14 @@ const void* sgic_index_data_dev(const sgic_index* h) { return h ? h->db : nullpt
 
 int sgic_index_reserve(sgic_index* h, int64_t rows) {
   SGIC_REQUIRE(h != nullptr, "index is NULL");
+  if (is_front(h)) {  // equal shares: what a bulk load or large appends fill
+    const int64_t G = static_cast<int64_t>(h->shards.size());
+    for (sgic_index* s : h->shards) {
+      int rc = sgic_index_reserve(s, (rows + G - 1) / G);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   if (rows <= h->capacity) return 0;
@@ -1079,6 +1166,7 @@ int sgic_index_reserve(sgic_index* h, int64_t rows) {
 
 int sgic_index_reset(sgic_index* h) {
   SGIC_REQUIRE(h != nullptr, "index is NULL");
+  if (is_front(h)) return front_reset(h);
   std::lock_guard<std::mutex> lk(h->mu);
   h->ntotal = 0;
   h->retained.clear();
@@ -1090,6 +1178,7 @@ int sgic_index_reset(sgic_index* h) {
 
 int sgic_index_add_f32(sgic_index* h, int64_t n, const float* host_x) {
   SGIC_REQUIRE(h != nullptr, "index is NULL");
+  if (is_front(h)) return front_add_host(h, n, host_x, 0);
   SGIC_REQUIRE(n >= 0, "n must be >= 0");
   if (n == 0) return 0;
   SGIC_REQUIRE(host_x != nullptr, "x is NULL");
@@ -1122,6 +1211,7 @@ int sgic_index_add_f32(sgic_index* h, int64_t n, const float* host_x) {
 
 int sgic_index_add_f32_dev(sgic_index* h, int64_t n, const float* dev_x, void* stream) {
   SGIC_REQUIRE(h != nullptr, "index is NULL");
+  if (is_front(h)) return front_add_dev(h, n, dev_x, 0, static_cast<cudaStream_t>(stream));
   SGIC_REQUIRE(n >= 0, "n must be >= 0");
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(h->mu);
@@ -1143,6 +1233,7 @@ int sgic_index_add_f32_dev(sgic_index* h, int64_t n, const float* dev_x, void* s
 
 int sgic_index_add_packed_dev(sgic_index* h, int64_t n, const void* dev_rows, void* stream) {
   SGIC_REQUIRE(h != nullptr, "index is NULL");
+  if (is_front(h)) return front_add_dev(h, n, dev_rows, 2, static_cast<cudaStream_t>(stream));
   SGIC_REQUIRE(n >= 0, "n must be >= 0");
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(h->mu);
@@ -1164,6 +1255,7 @@ int sgic_index_add_packed_dev(sgic_index* h, int64_t n, const void* dev_rows, vo
 
 int sgic_index_add_u8(sgic_index* h, int64_t n, const uint8_t* host_q) {
   SGIC_REQUIRE(h != nullptr, "index is NULL");
+  if (is_front(h)) return front_add_host(h, n, host_q, 1);
   SGIC_REQUIRE(n >= 0, "n must be >= 0");
   if (n == 0) return 0;
   SGIC_REQUIRE(host_q != nullptr, "q is NULL");
@@ -1188,6 +1280,7 @@ int sgic_index_add_u8(sgic_index* h, int64_t n, const uint8_t* host_q) {
 
 int sgic_index_add_u8_dev(sgic_index* h, int64_t n, const uint8_t* dev_q, void* stream) {
   SGIC_REQUIRE(h != nullptr, "index is NULL");
+  if (is_front(h)) return front_add_dev(h, n, dev_q, 1, static_cast<cudaStream_t>(stream));
   SGIC_REQUIRE(n >= 0, "n must be >= 0");
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(h->mu);
@@ -1356,6 +1449,7 @@ static int zl_slab_finalize(sgic_index* h, sgic_index::ZlSlab& z, bool* bad) {
 int sgic_index_add_c2df(sgic_index* h, const uint8_t* blob, const int64_t* offsets, int64_t n, int32_t* status_out,
                         int64_t* n_added, int n_threads) {
   SGIC_REQUIRE(h != nullptr, "index is NULL");
+  if (is_front(h)) return front_add_c2df(h, blob, offsets, n, status_out, n_added, n_threads);
   SGIC_REQUIRE(n >= 0 && offsets != nullptr && status_out != nullptr, "bad arguments");
   if (n_added) *n_added = 0;
   if (n == 0) return 0;
@@ -1510,6 +1604,7 @@ int sgic_index_add_c2df(sgic_index* h, const uint8_t* blob, const int64_t* offse
 int sgic_index_search_dev(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
                           int64_t id_base, void* stream) {
   SGIC_REQUIRE(h != nullptr, "index is NULL");
+  if (is_front(h)) return front_search_dev(h, nq, dev_q, k, dev_D, dev_I, id_base, static_cast<cudaStream_t>(stream));
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
@@ -1522,6 +1617,7 @@ int sgic_index_search_dev(sgic_index* h, int64_t nq, const float* dev_q, int64_t
 
 int sgic_index_search(sgic_index* h, int64_t nq, const float* host_q, int64_t k, float* host_D, int64_t* host_I) {
   SGIC_REQUIRE(h != nullptr, "index is NULL");
+  if (is_front(h)) return front_search_host(h, nq, host_q, k, host_D, host_I);
   SGIC_REQUIRE(k >= 1, "k must be >= 1");
   SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
   if (nq == 0) return 0;
@@ -1722,6 +1818,41 @@ int sgic_xchg_merge_dev(sgic_xchg* x, int64_t nq, int64_t k, const float* dev_D_
   return 0;
 }
 
+// One rank's whole search step with HOST buffers, in one call: pinned staging, H2D of the queries, the local scan
+// with global row numbers, the peer exchange + merge, D2H of the merged answer, one synchronise.  (The Python
+// host did the staging with torch calls before: ~70 us per step, more than the exchange itself.)
+int sgic_xchg_search(sgic_xchg* x, sgic_index* h, int64_t nq, const float* host_q, int64_t k, float* host_D,
+                     int64_t* host_I, int64_t id_base, int tie_by_position) {
+  SGIC_REQUIRE(x != nullptr && h != nullptr, "NULL argument");
+  SGIC_REQUIRE(!is_front(h), "the peer exchange joins single-GPU indexes of different processes");
+  SGIC_REQUIRE(k >= 1 && nq >= 1 && host_q && host_D && host_I, "bad arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  const size_t qbytes = static_cast<size_t>(nq) * h->d * 4, cand = static_cast<size_t>(nq) * k;
+  int rc = ensure_buf(&h->qdev, &h->qdev_bytes, qbytes, false);
+  if (rc) return rc;
+  if ((rc = ensure_buf(&h->odev, &h->odev_bytes, 2 * cand * 12, false))) return rc;
+  if ((rc = ensure_buf(&h->opin, &h->opin_bytes, std::max(qbytes, cand * 12), true))) return rc;
+  if ((rc = order_begin(h, h->stream))) return rc;
+  if ((rc = order_end(h, h->stream))) return rc;
+  std::memcpy(h->opin, host_q, qbytes);
+  SGIC_CUDA(cudaMemcpyAsync(h->qdev, h->opin, qbytes, cudaMemcpyHostToDevice, h->stream));
+  uint8_t* o = static_cast<uint8_t*>(h->odev);
+  int64_t* mI = reinterpret_cast<int64_t*>(o);                 // merged answer first: ids then scores, contiguous
+  float* mD = reinterpret_cast<float*>(o + cand * 8);
+  int64_t* lI = reinterpret_cast<int64_t*>(o + cand * 12);     // this rank's local answer
+  float* lD = reinterpret_cast<float*>(o + cand * 20);
+  rc = search_dev_impl(h, nq, static_cast<const float*>(h->qdev), k, lD, lI, id_base, h->stream);
+  if (rc) return rc;
+  rc = sgic_xchg_merge_dev(x, nq, k, lD, lI, mD, mI, tie_by_position, h->stream);
+  if (rc) return rc;
+  SGIC_CUDA(cudaMemcpyAsync(h->opin, h->odev, cand * 12, cudaMemcpyDeviceToHost, h->stream));
+  SGIC_CUDA(cudaStreamSynchronize(h->stream));
+  std::memcpy(host_I, h->opin, cand * 8);
+  std::memcpy(host_D, static_cast<uint8_t*>(h->opin) + cand * 8, cand * 4);
+  return 0;
+}
+
 int sgic_xchg_error(sgic_xchg* x) {
   SGIC_REQUIRE(x != nullptr, "exchange is NULL");
   DeviceGuard g(x->device);
@@ -1744,6 +1875,7 @@ int sgic_xchg_destroy(sgic_xchg* x) {
 
 int sgic_index_reconstruct(sgic_index* h, int64_t i0, int64_t n, float* host_out) {
   SGIC_REQUIRE(h != nullptr, "index is NULL");
+  if (is_front(h)) return front_reconstruct(h, i0, n, host_out);
   SGIC_REQUIRE(i0 >= 0 && n >= 0 && i0 + n <= h->ntotal, "row range out of bounds");
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(h->mu);
@@ -1791,6 +1923,27 @@ int sgic_index_write(sgic_index* h, const char* path) {
   hd.metric_type = 0;  // METRIC_INNER_PRODUCT
   hd.count = static_cast<uint64_t>(h->ntotal) * h->d;
   bool ok = std::fwrite(&hd, sizeof(hd), 1, f) == 1;
+  if (is_front(h)) {  // rows in global order, from the shards' host copies when all of them still hold theirs
+    std::lock_guard<std::mutex> lk(h->mu);
+    const int mode = front_write_mode(h);
+    const int64_t chunk = std::max<int64_t>(1, static_cast<int64_t>((16u << 20) / (h->d * 4)));
+    std::vector<float> buf(static_cast<size_t>(std::min<int64_t>(chunk, std::max<int64_t>(h->ntotal, 1))) * h->d);
+    for (int64_t i0 = 0; ok && i0 < h->ntotal; i0 += chunk) {
+      const int64_t rows = std::min(chunk, h->ntotal - i0);
+      int rc = front_rows_for_write(h, mode, i0, rows, buf.data());
+      if (rc) {
+        std::fclose(f);
+        return rc;
+      }
+      ok = std::fwrite(buf.data(), sizeof(float), static_cast<size_t>(rows) * h->d, f) == static_cast<size_t>(rows) * h->d;
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) {
+      set_error(std::string("write error on ") + path);
+      return 3;
+    }
+    return 0;
+  }
   const bool from_host =
       h->retain_ok && h->retained.size() == static_cast<size_t>(h->ntotal) * static_cast<size_t>(h->d);
   if (ok && h->ntotal > 0) {
@@ -1855,6 +2008,7 @@ constexpr uint64_t kSgi2Payload = 4096;
 int sgic_index_write_v2(sgic_index* h, const char* path, int64_t row_start, int64_t total_rows, int shard,
                         int n_shards) {
   SGIC_REQUIRE(h != nullptr && path != nullptr, "NULL argument");
+  SGIC_REQUIRE(!is_front(h), "a multi-GPU index is written with sgic_index_save_shards (one SGI2 file per GPU)");
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   int rc = ensure_staging(h);
@@ -1975,6 +2129,13 @@ static int read_v2_body(FILE* f, const char* path, const Sgi2Header& hd, int dev
 
 int sgic_index_shard_info(const sgic_index* h, int64_t* out4) {
   SGIC_REQUIRE(h != nullptr && out4 != nullptr, "NULL argument");
+  if (is_front(h)) {
+    out4[0] = 0;
+    out4[1] = h->ntotal;
+    out4[2] = 0;
+    out4[3] = static_cast<int64_t>(h->shards.size());
+    return 0;
+  }
   out4[0] = h->shard_row_start;
   out4[1] = h->shard_total_rows < 0 ? h->ntotal : h->shard_total_rows;
   out4[2] = h->shard_id;
@@ -2050,8 +2211,26 @@ int sgic_index_read(const char* path, int dtype, int device, int flags, sgic_ind
   return 0;
 }
 
+int sgic_index_scan_times(sgic_index* h, int max_n, float* ms_out, int* n_out) {
+  SGIC_REQUIRE(h != nullptr && ms_out != nullptr && n_out != nullptr && max_n >= 0, "bad arguments");
+  if (is_front(h)) return sgic_index_scan_times(h->shards[0], max_n, ms_out, n_out);  // the home GPU's scans
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  const int64_t have = std::min<int64_t>(h->ring_n, sgic_index::kTimeRing);
+  const int n = static_cast<int>(std::min<int64_t>(have, max_n));
+  for (int i = 0; i < n; ++i) {  // oldest of the last n first
+    const int slot = static_cast<int>((h->ring_n - n + i) % sgic_index::kTimeRing);
+    SGIC_CUDA(cudaEventSynchronize(h->ring_b[slot]));
+    SGIC_CUDA(cudaEventElapsedTime(&ms_out[i], h->ring_a[slot], h->ring_b[slot]));
+  }
+  *n_out = n;
+  h->ring_n = 0;
+  return 0;
+}
+
 int sgic_index_codes(sgic_index* h, int64_t i0, int64_t n, uint8_t* host_out) {
   SGIC_REQUIRE(h != nullptr && (host_out != nullptr || n == 0), "NULL argument");
+  if (is_front(h)) return front_codes(h, i0, n, host_out);
   std::lock_guard<std::mutex> lk(h->mu);
   SGIC_REQUIRE(h->codes_ok && h->codes.size() == static_cast<size_t>(h->ntotal) * static_cast<size_t>(h->d),
                "this index does not hold the u8 codes of all its rows (SGIC_RETAIN_U8, rows added as codes only)");
@@ -2069,6 +2248,7 @@ int sgic_codes_to_f32(const uint8_t* host_q, int64_t n, int d, float* host_out) 
 int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   SGIC_REQUIRE(h != nullptr && name != nullptr, "NULL argument");
   const std::string n(name);
+  if (is_front(h)) return front_set_option(h, n, value);
   if (n == "timing") h->opt_timing = value;
   else if (n == "evict_first") h->opt_evict_first = value;
   else if (n == "grid") h->opt_grid = value;
@@ -2101,6 +2281,13 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
 int64_t sgic_index_get_stat(const sgic_index* h, const char* name) {
   if (!h || !name) return -1;
   const std::string n(name);
+  if (is_front(h)) {
+    bool handled = false;
+    const int64_t v = front_get_stat(h, n, &handled);
+    if (handled) return v;
+    return sgic_index_get_stat(h->shards[0], name);
+  }
+  if (n == "n_shards") return 1;
   if (n == "launches") return h->stat_launches;
   if (n == "last_search_ns") return h->stat_last_search_ns;
   if (n == "last_scan_ns") return h->stat_last_scan_ns;
@@ -2124,6 +2311,187 @@ int64_t sgic_index_get_stat(const sgic_index* h, const char* name) {
   if (n == "retained_rows") return h->retain_ok ? static_cast<int64_t>(h->retained.size() / h->d) : -1;
   if (n == "retained_code_rows") return h->codes_ok ? static_cast<int64_t>(h->codes.size() / h->d) : -1;
   return -1;
+}
+
+}  // extern "C"
+
+#include "sharded_front.inl"
+
+namespace sgic {
+static int front_reset(sgic_index* f) {
+  std::lock_guard<std::mutex> lk(f->mu);
+  for (sgic_index* s : f->shards) {
+    int rc = sgic_index_reset(s);
+    if (rc) return rc;
+  }
+  FrontState* S = fs(f);
+  for (size_t g = 0; g < S->segs.size(); ++g) {
+    S->segs[g].clear();
+    S->seg_dirty[g] = 1;
+  }
+  f->ntotal = 0;
+  return 0;
+}
+static int front_set_option(sgic_index* f, const std::string& name, int64_t value) {
+  if (name == "workers") {  // 1: one launch thread per GPU (default); 0: the caller launches every shard itself
+    fs(f)->opt_workers = value ? 1 : 0;
+    return 0;
+  }
+  for (sgic_index* s : f->shards) {
+    int rc = sgic_index_set_option(s, name.c_str(), value);
+    if (rc) return rc;
+  }
+  return 0;
+}
+static int64_t front_get_stat(const sgic_index* f, const std::string& name, bool* handled) {
+  *handled = true;
+  if (name == "n_shards") return static_cast<int64_t>(f->shards.size());
+  if (name == "launches") {  // the shards' kernels + the merges on the home GPU
+    int64_t v = fs(f)->stat_merge_launches;
+    for (const sgic_index* s : f->shards) v += s->stat_launches;
+    return v;
+  }
+  if (name == "capacity") {
+    int64_t v = 0;
+    for (const sgic_index* s : f->shards) v += s->capacity;
+    return v;
+  }
+  if (name == "n_segments") {
+    int64_t v = 0;
+    for (const auto& sv : fs(f)->segs) v += static_cast<int64_t>(sv.size());
+    return v;
+  }
+  if (name == "direct_shards") {
+    int64_t v = 0;
+    for (uint8_t d : fs(f)->direct) v += d;
+    return v;
+  }
+  if (name == "retained_rows") return front_write_mode(f) == 1 ? f->ntotal : -1;
+  if (name == "retained_code_rows") return front_write_mode(f) == 2 ? f->ntotal : -1;
+  if (name == "zl_device_frames" || name == "zl_host_rows" || name == "zl_fallback_slabs") {
+    int64_t v = 0;
+    for (const sgic_index* s : f->shards) v += sgic_index_get_stat(s, name.c_str());
+    return v;
+  }
+  *handled = false;
+  return -1;
+}
+}  // namespace sgic
+
+extern "C" {
+
+int sgic_index_create_sharded(int d, int dtype, int n_dev, const int* dev_ids, int64_t capacity_rows, int flags,
+                              sgic_index** out) {
+  SGIC_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  SGIC_REQUIRE(n_dev >= 1 && n_dev <= 64 && dev_ids != nullptr, "n_dev must be 1..64 with a device list");
+  std::vector<sgic_index*> shards;
+  for (int g = 0; g < n_dev; ++g) {
+    sgic_index* s = nullptr;
+    int rc = sgic_index_create(d, dtype, dev_ids[g], capacity_rows > 0 ? (capacity_rows + n_dev - 1) / n_dev : 0, flags, &s);
+    if (rc) {
+      for (sgic_index* t : shards) sgic_index_destroy(t);
+      return rc;
+    }
+    shards.push_back(s);
+  }
+  sgic_index* f = new sgic_index();
+  f->flags = flags;
+  int rc = front_init(f, shards);
+  if (rc) {
+    sgic_index_destroy(f);
+    return rc;
+  }
+  *out = f;
+  return 0;
+}
+
+int sgic_index_n_shards(const sgic_index* h) { return h ? (is_front(h) ? static_cast<int>(h->shards.size()) : 1) : -1; }
+
+int sgic_index_shard(sgic_index* h, int g, sgic_index** out) {
+  SGIC_REQUIRE(h != nullptr && out != nullptr, "NULL argument");
+  if (!is_front(h)) {
+    SGIC_REQUIRE(g == 0, "shard number out of range");
+    *out = h;
+    return 0;
+  }
+  SGIC_REQUIRE(g >= 0 && g < static_cast<int>(h->shards.size()), "shard number out of range");
+  *out = h->shards[static_cast<size_t>(g)];
+  return 0;
+}
+
+int sgic_index_adopt_shards(sgic_index* h) {
+  SGIC_REQUIRE(h != nullptr, "index is NULL");
+  if (!is_front(h)) return 0;
+  std::lock_guard<std::mutex> lk(h->mu);
+  front_adopt_contiguous(h);
+  return 0;
+}
+
+static std::string shard_file(const char* dir, int g, int G) {
+  char name[64];
+  std::snprintf(name, sizeof(name), "shard-%05d-of-%05d.sgi2", g, G);
+  return std::string(dir) + "/" + name;
+}
+
+int sgic_index_save_shards(sgic_index* h, const char* dir) {
+  SGIC_REQUIRE(h != nullptr && dir != nullptr, "NULL argument");
+  if (!is_front(h)) return sgic_index_write_v2(h, shard_file(dir, 0, 1).c_str(), 0, h->ntotal, 0, 1);
+  std::lock_guard<std::mutex> lk(h->mu);
+  FrontState* S = fs(h);
+  const int G = static_cast<int>(h->shards.size());
+  for (int g = 0; g < G; ++g)
+    SGIC_REQUIRE(S->segs[static_cast<size_t>(g)].size() <= 1,
+                 "save needs one contiguous row range per GPU (reserve + bulk load, or large appends)");
+  return for_shards(h, true, [&](int g) -> int {
+    const auto& v = S->segs[static_cast<size_t>(g)];
+    return sgic_index_write_v2(h->shards[static_cast<size_t>(g)], shard_file(dir, g, G).c_str(), v.empty() ? 0 : v[0].g0,
+                               h->ntotal, g, G);
+  });
+}
+
+int sgic_index_load_shards(const char* dir, int n_dev, const int* dev_ids, int flags, sgic_index** out) {
+  SGIC_REQUIRE(dir != nullptr && out != nullptr && n_dev >= 1 && n_dev <= 64 && dev_ids != nullptr, "bad arguments");
+  *out = nullptr;
+  std::vector<sgic_index*> shards(static_cast<size_t>(n_dev), nullptr);
+  std::vector<int> rcs(static_cast<size_t>(n_dev), 0);
+  std::vector<std::string> errs(static_cast<size_t>(n_dev));
+  {
+    std::vector<std::thread> th;  // one reader per GPU: every shard streams over its own PCIe link
+    for (int g = 0; g < n_dev; ++g)
+      th.emplace_back([&, g] {
+        rcs[static_cast<size_t>(g)] = sgic_index_read(shard_file(dir, g, n_dev).c_str(), SGIC_F16, dev_ids[g], flags,
+                                                       &shards[static_cast<size_t>(g)]);
+        if (rcs[static_cast<size_t>(g)]) errs[static_cast<size_t>(g)] = g_err;
+      });
+    for (auto& t : th) t.join();
+  }
+  auto fail = [&](int rc, const std::string& msg) {
+    for (sgic_index* s : shards) sgic_index_destroy(s);
+    set_error(msg);
+    return rc;
+  };
+  for (int g = 0; g < n_dev; ++g)
+    if (rcs[static_cast<size_t>(g)]) return fail(rcs[static_cast<size_t>(g)], errs[static_cast<size_t>(g)]);
+  int64_t start = 0;
+  for (int g = 0; g < n_dev; ++g) {
+    const sgic_index* s = shards[static_cast<size_t>(g)];
+    if (s->shard_count != n_dev || s->shard_id != g || s->d != shards[0]->d || s->dtype != shards[0]->dtype ||
+        s->shard_row_start != start)
+      return fail(3, std::string(dir) + ": shard files do not describe one index split over " + std::to_string(n_dev) +
+                         " GPUs");
+    start += s->ntotal;
+  }
+  sgic_index* f = new sgic_index();
+  f->flags = flags;
+  int rc = front_init(f, shards);
+  if (rc) {
+    sgic_index_destroy(f);
+    return rc;
+  }
+  front_adopt_contiguous(f);
+  *out = f;
+  return 0;
 }
 
 }  // extern "C"

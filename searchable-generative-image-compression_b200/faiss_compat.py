@@ -84,22 +84,52 @@ class IndexFlatIP(Index):
     reference's ``dequantize_clip_u8`` would have given faiss (src/build.py:82-99).
     """
 
-    def __init__(self, d: int, *, dtype="fp16", device: int | None = None, capacity: int = 0,
-                 retain_fp32: bool = True, retain_codes: bool = False, _handle=None):
+    def __init__(self, d: int, *, dtype="fp16", device: int | None = None, devices: Sequence[int] | None = None,
+                 capacity: int = 0, retain_fp32: bool = True, retain_codes: bool = False, _handle=None,
+                 _borrowed: bool = False):
         self._lib = _native.lib()
         self._h = C.c_void_p()
+        self._borrowed = _borrowed
         if _handle is not None:
             self._h = _handle
             return
         flags = (SGIC_RETAIN_F32 if retain_fp32 else 0) | (SGIC_RETAIN_U8 if retain_codes else 0)
+        if devices is not None:
+            # ``devices=[0, 1, ...]``: the rows are sharded over these GPUs behind this one object, driven by this
+            # one process (the reference's caller is one process: src/search.py:149-162); devices[0] is the home GPU
+            devs = (C.c_int * len(devices))(*[int(x) for x in devices])
+            check(self._lib.sgic_index_create_sharded(int(d), _dtype_code(dtype), len(devices), devs, int(capacity),
+                                                      flags, C.byref(self._h)))
+            return
         dev = _default_device() if device is None else int(device)
         check(self._lib.sgic_index_create(int(d), _dtype_code(dtype), dev, int(capacity), flags, C.byref(self._h)))
 
     # -- lifetime ---------------------------------------------------------------------
     def close(self) -> None:
         h, self._h = self._h, C.c_void_p()
-        if h:
+        if h and not self._borrowed:
             self._lib.sgic_index_destroy(h)
+
+    # -- shards (``devices=[...]``) --------------------------------------------------------
+    @property
+    def n_shards(self) -> int:
+        return int(self._lib.sgic_index_n_shards(self._h))
+
+    def shard(self, g: int) -> "IndexFlatIP":
+        """The g-th GPU's rows as a borrowed single-GPU index (bulk loaders append to it directly and then call
+        :meth:`adopt_shards`)."""
+        h = C.c_void_p()
+        check(self._lib.sgic_index_shard(self._h, int(g), C.byref(h)))
+        return IndexFlatIP(0, _handle=h, _borrowed=True)
+
+    def adopt_shards(self) -> None:
+        """Make the rows the shards hold the index's rows: shard 0's first, then shard 1's, ..."""
+        check(self._lib.sgic_index_adopt_shards(self._h))
+
+    def save_shards(self, directory) -> None:
+        """One ``shard-%05d-of-%05d.sgi2`` file per GPU (rows as stored in HBM)."""
+        os.makedirs(str(directory), exist_ok=True)
+        check(self._lib.sgic_index_save_shards(self._h, os.fsencode(str(directory))))
 
     def __del__(self):  # pragma: no cover - interpreter shutdown order
         try:
@@ -257,6 +287,14 @@ class IndexFlatIP(Index):
     def set_option(self, name: str, value: int) -> None:
         check(self._lib.sgic_index_set_option(self._h, name.encode(), int(value)))
 
+    def scan_times_ms(self, max_n: int = 256) -> np.ndarray:
+        """Durations of the scan kernels of the last searches made under ``set_option("timing", 2)`` (CUDA events
+        on the search's stream, recorded without a synchronise)."""
+        out = np.zeros(max_n, dtype=np.float32)
+        n = C.c_int(0)
+        check(self._lib.sgic_index_scan_times(self._h, int(max_n), _ptr(out), C.byref(n)))
+        return out[:n.value].copy()
+
     def stat(self, name: str) -> int:
         return int(self._lib.sgic_index_get_stat(self._h, name.encode()))
 
@@ -290,6 +328,17 @@ def codes_to_f32(q) -> np.ndarray:
     out = np.empty(q.shape, dtype=np.float32)
     check(_native.lib().sgic_codes_to_f32(_ptr(q), q.shape[0], q.shape[1], _ptr(out)))
     return out
+
+
+def read_index_shards(directory, devices: Sequence[int], *, retain_fp32: bool = False) -> IndexFlatIP:
+    """Load a directory of ``shard-*-of-*.sgi2`` files (``IndexFlatIP.save_shards`` / ``ShardedIndexFlatIP.save``)
+    onto ``devices``, one file per GPU, behind one index object."""
+    lib = _native.lib()
+    h = C.c_void_p()
+    devs = (C.c_int * len(devices))(*[int(x) for x in devices])
+    check(lib.sgic_index_load_shards(os.fsencode(str(directory)), len(devices), devs,
+                                     SGIC_RETAIN_F32 if retain_fp32 else 0, C.byref(h)))
+    return IndexFlatIP(0, _handle=h)
 
 
 def write_index(index: IndexFlatIP, path: str) -> None:

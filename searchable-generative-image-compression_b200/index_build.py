@@ -27,7 +27,7 @@ from . import zstd
 from .c2df import unpack_c2df
 from .retrieval import decode_clip_from_c2df, load_index  # build.py carries its own copies (:26-43, :106-126)
 
-__all__ = ["build_index_from_c2df_dir", "quantize_u8_and_compress", "FaissDB", "load_index", "from_npy_dir"]
+__all__ = ["build_index_from_c2df_dir", "quantize_u8_and_compress", "FaissDB", "load_index", "from_npy_dir", "pack_npy_dir"]
 
 
 def quantize_u8_and_compress(z_unit: np.ndarray, model_id: str = "ViT-B-32:laion2b_s34b_b79k"):
@@ -156,19 +156,70 @@ class FaissDB:
                 f.write(_id + "\n")
 
 
-def from_npy_dir(clip_vecs_dir, bitstream_dir, index_dir, **index_kwargs) -> FaissDB:
-    """The rank-0 tail of ``compress.test`` (src/compress.py:295-306): every
-    ``clip_vecs/<stem>.npy`` in sorted order → ``FaissDB.add`` with id
-    ``<bitstream_dir>/<stem>.c2df`` → ``persist``.  Vectors are appended block-wise."""
-    files = sorted(Path(clip_vecs_dir).glob("*.npy"))
+PACKED_SUBDIR = "_packed"      # clip_vecs/_packed/{vecs.npy, stems.txt}: not matched by the reference's glob("*.npy")
+
+
+def pack_npy_dir(clip_vecs_dir) -> Path:
+    """On-disk v2 of ``IO/clip_vecs``: ONE ``(N, d)`` fp32 ``.npy`` + the stems, in the order
+    ``sorted(glob("*.npy"))`` gives (src/compress.py:296), instead of one 2 KB file per vector (:286) that the
+    index build re-opens one by one (:300-305).  Written next to the per-vector files; they stay valid."""
+    clip_vecs_dir = Path(clip_vecs_dir)
+    files = sorted(clip_vecs_dir.glob("*.npy"))
     if not files:
         raise RuntimeError(f"Empty folder: {clip_vecs_dir}")
-    first = np.load(files[0])
-    db = FaissDB(str(index_dir), int(first.shape[-1]), **index_kwargs)
+    d = int(np.load(files[0]).reshape(-1).shape[0])
+    out = clip_vecs_dir / PACKED_SUBDIR
+    out.mkdir(exist_ok=True)
+    mm = np.lib.format.open_memmap(out / "vecs.npy.tmp", mode="w+", dtype=np.float32, shape=(len(files), d))
+    for i, f in enumerate(files):
+        mm[i] = np.load(f).astype(np.float32).reshape(-1)
+    mm.flush()
+    del mm
+    (out / "stems.txt").write_text("".join(f.stem + "\n" for f in files), encoding="utf-8")
+    os.replace(out / "vecs.npy.tmp", out / "vecs.npy")
+    return out / "vecs.npy"
+
+
+def _packed_vectors(clip_vecs_dir: Path):
+    """(memory-mapped (N, d) array, stems) when a packed copy exists and covers the per-vector files; else None."""
+    vecs, stems = clip_vecs_dir / PACKED_SUBDIR / "vecs.npy", clip_vecs_dir / PACKED_SUBDIR / "stems.txt"
+    if not (vecs.exists() and stems.exists()):
+        return None
+    names = [ln for ln in stems.read_text(encoding="utf-8").splitlines() if ln]
+    arr = np.load(vecs, mmap_mode="r")
+    if arr.ndim != 2 or arr.shape[0] != len(names):
+        return None
+    loose = sorted(p.stem for p in clip_vecs_dir.glob("*.npy"))
+    if loose and loose != names:            # per-vector files were added / removed since: the packed copy is stale
+        return None
+    return arr, names
+
+
+def from_npy_dir(clip_vecs_dir, bitstream_dir, index_dir, *, require_bitstream: bool = True, **index_kwargs) -> FaissDB:
+    """The rank-0 tail of ``compress.test`` (src/compress.py:295-306): every ``clip_vecs/<stem>.npy`` in sorted
+    order whose ``<bitstream_dir>/<stem>.c2df`` exists (:304) → ``FaissDB.add`` with that id → ``persist``.
+    Vectors are appended block-wise; when ``clip_vecs/_packed`` holds an up-to-date packed copy
+    (:func:`pack_npy_dir`) the rows come out of that one file instead of N small ones."""
+    clip_vecs_dir = Path(clip_vecs_dir)
+    packed = _packed_vectors(clip_vecs_dir)
+    if packed is not None:
+        arr, stems = packed
+        source = ((stems[i], arr[i]) for i in range(len(stems)))
+        d = int(arr.shape[1])
+    else:
+        files = sorted(clip_vecs_dir.glob("*.npy"))
+        if not files:
+            raise RuntimeError(f"Empty folder: {clip_vecs_dir}")
+        d = int(np.load(files[0]).shape[-1])
+        source = ((f.stem, np.load(f)) for f in files)
+    db = FaissDB(str(index_dir), d, **index_kwargs)
     block, ids = [], []
-    for f in files:
-        block.append(np.load(f).astype(np.float32).reshape(-1))
-        ids.append(os.path.join(str(bitstream_dir), f.stem + ".c2df"))
+    for stem, vec in source:
+        doc_id = os.path.join(str(bitstream_dir), stem + ".c2df")
+        if require_bitstream and not os.path.exists(doc_id):
+            continue
+        block.append(np.asarray(vec, dtype=np.float32).reshape(-1))
+        ids.append(doc_id)
         if len(block) >= 65536:
             db.add_many(np.stack(block), ids)
             block, ids = [], []

@@ -12,6 +12,7 @@ accept a pre-computed embedding (``--vec file.npy``); ``query-c2df`` is complete
 from __future__ import annotations
 
 import argparse
+import os
 import json
 import sys
 import traceback
@@ -61,15 +62,57 @@ def decode_clip_from_c2df(c2df_path) -> Tuple[np.ndarray, Dict]:
     return dequantize_clip_u8(q).astype("float32"), header
 
 
-def load_index(index_dir) -> Tuple[faiss.Index, List[str], Dict]:
+def _shard_files(index_dir: Path) -> List[Path]:
+    """``shard-00000-of-0000G.sgi2`` … in order, when the directory holds one complete set (additive layout:
+    ``IndexFlatIP.save_shards`` / ``ShardedIndexFlatIP.save``)."""
+    files = sorted(index_dir.glob("shard-*-of-*.sgi2"))
+    if not files:
+        return []
+    try:
+        total = int(files[0].stem.split("-of-")[1])
+    except (IndexError, ValueError):
+        return []
+    want = [index_dir / f"shard-{g:05d}-of-{total:05d}.sgi2" for g in range(total)]
+    return want if all(p.exists() for p in want) else []
+
+
+def _default_devices(n_files: int):
+    env = os.environ.get("SGIC_DEVICES")
+    if env:
+        return [int(t) for t in env.split(",") if t.strip() != ""]
+    return list(range(n_files))
+
+
+def load_index(index_dir, devices=None) -> Tuple[faiss.Index, List[str], Dict]:
     """Open an index directory in either naming scheme — src/search.py:65-88.
 
     ``faiss.index`` + ``paths.json`` (+ optional ``meta.json``) is preferred; otherwise
     ``index.faiss`` + ``ids.txt`` with ``meta = {"dim": index.d}`` and ``model_id`` sniffed
     from the first listed ``.c2df`` header when it can be read.
+
+    Additive: a directory that holds a set of ``shard-*-of-*.sgi2`` files next to ``paths.json`` / ``ids.txt`` is
+    loaded onto ``devices`` (default: ``SGIC_DEVICES`` or GPUs 0..G-1), one file per GPU, behind one index object —
+    the id list and ``meta`` are read exactly as for the single-file layouts.
     """
     index_dir = Path(index_dir)
     new_idx, old_idx = index_dir / "faiss.index", index_dir / "index.faiss"
+    shards = _shard_files(index_dir)
+    if shards and ((index_dir / "paths.json").exists() or (index_dir / "ids.txt").exists()):
+        devs = list(devices) if devices is not None else _default_devices(len(shards))
+        if len(devs) != len(shards):
+            raise RuntimeError(f"{index_dir} holds {len(shards)} shard files, {len(devs)} devices were given")
+        index = faiss.read_index_shards(index_dir, devs)
+        if (index_dir / "paths.json").exists():
+            paths = json.loads((index_dir / "paths.json").read_text(encoding="utf-8"))
+            try:
+                meta = json.loads((index_dir / "meta.json").read_text(encoding="utf-8"))
+            except Exception:
+                meta = {}
+        else:
+            lines = (index_dir / "ids.txt").read_text(encoding="utf-8").splitlines()
+            paths = [ln.strip() for ln in lines if ln.strip()]
+            meta = {"dim": index.d}
+        return index, paths, meta
     if new_idx.exists() and (index_dir / "paths.json").exists():
         index = faiss.read_index(str(new_idx))
         paths = json.loads((index_dir / "paths.json").read_text(encoding="utf-8"))

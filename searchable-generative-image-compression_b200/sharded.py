@@ -85,6 +85,16 @@ class PeerExchange:
                                                     _torch_stream(D_local.device)))
         return D, I
 
+    def search_host(self, local: IndexFlatIP, x: np.ndarray, k: int, id_base: int, by_position: bool):
+        """The whole step in one C call: staging, local scan, exchange + merge, answer back on the host."""
+        nq = x.shape[0]
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        _native.check(self._lib.sgic_xchg_search(self._h, local._h, nq, C.c_void_p(x.ctypes.data), k,
+                                                 C.c_void_p(D.ctypes.data), C.c_void_p(I.ctypes.data), int(id_base),
+                                                 1 if by_position else 0))
+        return D, I
+
     def check(self) -> None:
         _native.check(self._lib.sgic_xchg_error(self._h))
 
@@ -280,8 +290,12 @@ class ShardedIndexFlatIP(Index):
         if not self._cuda:
             D, I = self.search_torch(torch.from_numpy(x).to(self._dev), k)
             return D.cpu().numpy(), I.cpu().numpy()
-        # pinned staging both ways, one synchronisation per call (what sgic_index_search does on one GPU)
         nq = x.shape[0]
+        if (self._peer is not None and nq * k <= self._peer.max_cands and len(self._segments) == 1
+                and isinstance(self.local, IndexFlatIP)):
+            base = self._segments[0][0] - self._segments[0][1]
+            return self._peer.search_host(self.local, x, k, base, self._ntotal >= (1 << 32))
+        # pinned staging both ways, one synchronisation per call (what sgic_index_search does on one GPU)
         need_in, need_out = nq * self._d, nq * k
         if self._pin_q is None or self._pin_q.numel() < need_in:
             self._pin_q = torch.empty(max(need_in, 1 << 16), dtype=torch.float32).pin_memory()

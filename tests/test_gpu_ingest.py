@@ -276,15 +276,41 @@ def test_from_npy_dir_matches_sorted_glob_order(tmp_path):
     rng = np.random.default_rng(9)
     vecs = rng.standard_normal((25, 512)).astype(np.float32)
     (tmp_path / "clip_vecs").mkdir()
+    (tmp_path / "bitstreams").mkdir()
+    names = [f"im{(i * 7) % 25:03d}" for i in range(25)]
     for i, v in enumerate(vecs):
-        np.save(tmp_path / "clip_vecs" / f"im{(i * 7) % 25:03d}.npy", v)
-    db = index_build.from_npy_dir(tmp_path / "clip_vecs", "../IO/bitstreams", tmp_path / "faiss", device=0)
-    assert db.index.ntotal == 25
-    assert db.ids[0] == "../IO/bitstreams/im000.c2df" and db.ids == sorted(db.ids)
+        np.save(tmp_path / "clip_vecs" / f"{names[i]}.npy", v)
+        if names[i] not in ("im003", "im017"):          # compress.py:304: vectors without a bitstream are not indexed
+            (tmp_path / "bitstreams" / f"{names[i]}.c2df").write_bytes(b"C2DF")
+    bit = str(tmp_path / "bitstreams")
+    db = index_build.from_npy_dir(tmp_path / "clip_vecs", bit, tmp_path / "faiss", device=0)
+    assert db.index.ntotal == 23
+    assert db.ids[0] == f"{bit}/im000.c2df" and db.ids == sorted(db.ids) and f"{bit}/im003.c2df" not in db.ids
     x = c2df_ref.read_ixfi(tmp_path / "faiss" / "index.faiss")
-    order = sorted(range(25), key=lambda i: f"im{(i * 7) % 25:03d}")
+    order = [i for i in sorted(range(25), key=lambda i: names[i]) if names[i] not in ("im003", "im017")]
     want = vecs[order] / (np.linalg.norm(vecs[order], axis=1, keepdims=True) + 1e-12)
     assert np.array_equal(x, want.astype(np.float32))         # fp32 rows kept bit-exact on disk
+    # on-disk v2 of clip_vecs: one packed (N, d) .npy + stems; the index built from it is byte-identical
+    packed = index_build.pack_npy_dir(tmp_path / "clip_vecs")
+    arr = np.load(packed)
+    assert arr.shape == (25, 512) and arr.dtype == np.float32
+    assert np.array_equal(arr, vecs[sorted(range(25), key=lambda i: names[i])])
+    assert sorted(p.name for p in (tmp_path / "clip_vecs").glob("*.npy")) == sorted(n + ".npy" for n in names)  # untouched
+    db2 = index_build.from_npy_dir(tmp_path / "clip_vecs", bit, tmp_path / "faiss2", device=0)
+    assert db2.ids == db.ids
+    assert (tmp_path / "faiss2" / "index.faiss").read_bytes() == (tmp_path / "faiss" / "index.faiss").read_bytes()
+    for f in (tmp_path / "clip_vecs").glob("*.npy"):           # the packed copy alone is enough
+        f.unlink()
+    db3 = index_build.from_npy_dir(tmp_path / "clip_vecs", bit, tmp_path / "faiss3", device=0)
+    assert (tmp_path / "faiss3" / "index.faiss").read_bytes() == (tmp_path / "faiss" / "index.faiss").read_bytes()
+    # a stale packed copy (a vector file appeared since) is ignored
+    np.save(tmp_path / "clip_vecs" / "zz_new.npy", vecs[0])
+    (tmp_path / "bitstreams" / "zz_new.c2df").write_bytes(b"C2DF")
+    db4 = index_build.from_npy_dir(tmp_path / "clip_vecs", bit, tmp_path / "faiss4", device=0)
+    assert db4.index.ntotal == 1 and db4.ids == [f"{bit}/zz_new.c2df"]
+    # opting out of the existence check indexes everything (additive)
+    db5 = index_build.from_npy_dir(tmp_path / "clip_vecs", "nowhere", tmp_path / "faiss5", require_bitstream=False, device=0)
+    assert db5.index.ntotal == 1
 
 
 def _c2df_blobs(vecs, rng, full_size=True):
