@@ -52,6 +52,8 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--out", default="")
+    ap.add_argument("--max-ingest-seconds", type=float, default=240.0,
+                    help="stop replaying once the ingest has run this long (the record then says how many rows it holds)")
     a = ap.parse_args()
     d = 512
     # ---- corpus on the host cores (before CUDA is touched: the pool forks) ------------------------------------
@@ -85,9 +87,18 @@ def main():
     assert added == 200_000 and not status.any()
     index.reset()
     t0 = time.perf_counter()
+    done_calls = 0
     for c in range(calls):
         added, status = index.add_c2df(blob, offs)
         assert added == files_per_call, (added, int(status.sum()))
+        done_calls += 1
+        if c % 25 == 0:
+            print(f"  call {c + 1}/{calls}: {index.ntotal} rows, {index.ntotal / (time.perf_counter() - t0) / 1e6:.1f} M files/s", flush=True)
+        if time.perf_counter() - t0 > a.max_ingest_seconds:
+            print(f"  ingest budget of {a.max_ingest_seconds} s used up after {done_calls} calls", flush=True)
+            break
+    calls = done_calls
+    rows = calls * files_per_call
     for g in range(G):
         torch.cuda.synchronize(g)
     t_ing = time.perf_counter() - t0
@@ -125,20 +136,31 @@ def main():
         e2e_ms = (time.perf_counter() - t0) / a.steps * 1e3
         # parity: every GPU re-scores its own rows for a sample of the queries, candidates merged on the host
         sel = np.unique(np.linspace(0, nq - 1, min(nq, 16)).astype(np.int64))
-        cs, ci, start = [], [], 0
+        # (row numbers: every call appends files [g*per, (g+1)*per) of its list to GPU g, so local row l of GPU g is
+        #  global row (l // cnt_g) * files_per_call + g*per + l % cnt_g — the run table the index keeps internally)
+        cs, ci = [], []
+        per_g = -(-files_per_call // G)
         for g in range(G):
             sh = index.shard(g)
             pdev = torch.device("cuda", sh.device)
-            rs, ri = rescore_topk(sh, q[torch.from_numpy(sel).to(home)].to(pdev), a.k, id_base=start, chunk_rows=1 << 19)
+            rs, ri = rescore_topk(sh, q[torch.from_numpy(sel).to(home)].to(pdev), a.k, chunk_rows=1 << 19)
+            cnt_g = min(files_per_call, (g + 1) * per_g) - min(files_per_call, g * per_g)
+            loc = ri.cpu().numpy()
             cs.append(rs.cpu().numpy())
-            ci.append(ri.cpu().numpy())
-            start += sh.ntotal
+            ci.append((loc // cnt_g) * files_per_call + g * per_g + loc % cnt_g)
         cs, ci = np.concatenate(cs, 1), np.concatenate(ci, 1)
         order = np.lexsort((ci, -cs), axis=1)[:, :a.k + 16]
         par = compare_topk(D[torch.from_numpy(sel).to(home)].cpu().numpy(), I[torch.from_numpy(sel).to(home)].cpu().numpy(),
                            np.take_along_axis(cs, order, 1), np.take_along_axis(ci, order, 1), a.k, score_tol=3e-5)
         assert par["ok"], par
-        assert np.array_equal(Ih, I.cpu().numpy())
+        Ic = I.cpu().numpy()
+        assert np.array_equal(Ih, Ic)
+        # the corpus is replayed: the best FILE of a query sits at rows f, f + distinct, f + 2*distinct, ... and the
+        # answer must be its first k replays in row order (ties resolve to the lowest row number, on 8 GPUs as on 1)
+        if rows // a.distinct >= a.k:
+            f = Ic[:, :1] % a.distinct
+            assert np.array_equal(Ic, f + a.distinct * np.arange(a.k)[None, :]), "replays of the best file are not the answer"
+            par["replay_rows_checked"] = int(Ic.shape[0])
         n_local = max(rec["rows_per_gpu"])
         searches[f"batch{nq}"] = {"ms_per_step": ms, "queries_per_s": nq / ms * 1e3, "e2e_ms_per_step": e2e_ms,
                                   "e2e_queries_per_s": nq / e2e_ms * 1e3, "parity": par,

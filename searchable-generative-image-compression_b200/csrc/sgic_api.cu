@@ -155,7 +155,7 @@ struct sgic_index {
   int64_t shard_row_start = 0, shard_total_rows = -1;
   int shard_id = 0, shard_count = 1;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1, opt_trace = 0, opt_steal = 1, opt_t_n8 = 1;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1, opt_trace = 0, opt_steal = 1, opt_t_n8 = 1, opt_t_max_nq = 88;
   int64_t stat_ingest_h2d_ns = 0, stat_ingest_k0_ns = 0, stat_ingest_k1_ns = 0;
   int64_t stat_ingest_parse_ns = 0, stat_ingest_pack_ns = 0, stat_ingest_gpu_ns = 0;
   int64_t stat_zl_device_frames = 0, stat_zl_host_rows = 0, stat_zl_fallback_slabs = 0;
@@ -643,7 +643,10 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     const uint32_t n_pad = (nqb + 15u) & ~15u;
     const uint32_t n_mma = (nqb <= 8u && h->opt_t_n8) ? 8u : n_pad;  // tensor work proportional to the batch down to N = 8
     uint32_t t_stages = 0;
-    if (!pairs && h->opt_dense_mode != 1) {  // any k whose (warp, query) lists fit next to the ring
+    // Measured per-query cost on top of the stream (50M x 512, 1000 W cap, profiles/r02_mid_batches.log): K4t 29-33 us
+    // (its MMAs are narrow: N = the batch), the queries-on-M kernel 20.5 us at a FULL 128-query tile — from ~88
+    // queries the padded full tile is the cheaper one (9.5 ms flat against 6.9 + 0.031 nq).  "t_max_nq" overrides.
+    if (!pairs && h->opt_dense_mode != 1 && nqb <= static_cast<uint32_t>(h->opt_t_max_nq)) {
       const size_t fixed = dense_t_fixed_bytes(n_pad, kc_chunks, static_cast<uint32_t>(k)) + 1024 + 256;
       // measured at 100M x 512, nq = 8: 3-4 stages (96-128 KB in flight) 14.2 ms, 5 stages 15.2 ms, 6 stages 15.5 ms
       if (fixed < kSmemBudget) t_stages = static_cast<uint32_t>(std::min<size_t>((kSmemBudget - fixed) / kDtStageBytes, 4));
@@ -1831,7 +1834,8 @@ int sgic_xchg_search(sgic_xchg* x, sgic_index* h, int64_t nq, const float* host_
   const size_t qbytes = static_cast<size_t>(nq) * h->d * 4, cand = static_cast<size_t>(nq) * k;
   int rc = ensure_buf(&h->qdev, &h->qdev_bytes, qbytes, false);
   if (rc) return rc;
-  if ((rc = ensure_buf(&h->odev, &h->odev_bytes, 2 * cand * 12, false))) return rc;
+  const size_t half = (cand * 12 + 15) & ~size_t(15);  // merged answer | local answer, each ids (8 B) then scores
+  if ((rc = ensure_buf(&h->odev, &h->odev_bytes, 2 * half, false))) return rc;
   if ((rc = ensure_buf(&h->opin, &h->opin_bytes, std::max(qbytes, cand * 12), true))) return rc;
   if ((rc = order_begin(h, h->stream))) return rc;
   if ((rc = order_end(h, h->stream))) return rc;
@@ -1840,8 +1844,8 @@ int sgic_xchg_search(sgic_xchg* x, sgic_index* h, int64_t nq, const float* host_
   uint8_t* o = static_cast<uint8_t*>(h->odev);
   int64_t* mI = reinterpret_cast<int64_t*>(o);                 // merged answer first: ids then scores, contiguous
   float* mD = reinterpret_cast<float*>(o + cand * 8);
-  int64_t* lI = reinterpret_cast<int64_t*>(o + cand * 12);     // this rank's local answer
-  float* lD = reinterpret_cast<float*>(o + cand * 20);
+  int64_t* lI = reinterpret_cast<int64_t*>(o + half);          // this rank's local answer
+  float* lD = reinterpret_cast<float*>(o + half + cand * 8);
   rc = search_dev_impl(h, nq, static_cast<const float*>(h->qdev), k, lD, lI, id_base, h->stream);
   if (rc) return rc;
   rc = sgic_xchg_merge_dev(x, nq, k, lD, lI, mD, mI, tie_by_position, h->stream);
@@ -2264,6 +2268,7 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "dense_gthr") h->opt_dense_gthr = value ? 1 : 0;
   else if (n == "steal") h->opt_steal = value ? 1 : 0;
   else if (n == "t_n8") h->opt_t_n8 = value ? 1 : 0;
+  else if (n == "t_max_nq") h->opt_t_max_nq = std::max<int64_t>(0, value);
   else if (n == "trace") h->opt_trace = value;  // device address of a [grid][4] u64 buffer (0 = off), see scan_small.cuh
   else if (n == "drop_retained") {
     std::lock_guard<std::mutex> lk(h->mu);

@@ -234,7 +234,8 @@ static int front_shard_search(sgic_index* f, int g, int64_t nq, const float* q_p
     rc = search_dev_impl(s, nq, q_dev, k, dstD, dstI, id_base, st);
     if (rc) return rc;
   } else {
-    if ((rc = ensure_buf(&s->odev, &s->odev_bytes, 2 * cand * 12, false))) return rc;
+    const size_t half = (cand * 12 + 15) & ~size_t(15);  // local answer | remapped answer, each ids (8 B) then scores
+    if ((rc = ensure_buf(&s->odev, &s->odev_bytes, 2 * half, false))) return rc;
     int64_t* lI = reinterpret_cast<int64_t*>(s->odev);
     float* lD = reinterpret_cast<float*>(static_cast<uint8_t*>(s->odev) + cand * 8);
     rc = search_dev_impl(s, nq, q_dev, k, lD, lI, id_base, st);
@@ -242,8 +243,8 @@ static int front_shard_search(sgic_index* f, int g, int64_t nq, const float* q_p
     float* oD = lD;
     int64_t* oI = lI;
     if (multi) {
-      oI = reinterpret_cast<int64_t*>(static_cast<uint8_t*>(s->odev) + cand * 12);
-      oD = reinterpret_cast<float*>(static_cast<uint8_t*>(s->odev) + cand * 20);
+      oI = reinterpret_cast<int64_t*>(static_cast<uint8_t*>(s->odev) + half);
+      oD = reinterpret_cast<float*>(static_cast<uint8_t*>(s->odev) + half + cand * 8);
       float* tD = S->direct[gi] ? dstD : oD;
       int64_t* tI = S->direct[gi] ? dstI : oI;
       const long long* tab = static_cast<const long long*>(S->seg_dev[gi]);
@@ -640,6 +641,7 @@ static int front_init(sgic_index* f, const std::vector<sgic_index*>& shards) {
   S->seg_dev.assign(G, nullptr);
   S->seg_dev_n.assign(G, 0);
   S->seg_dirty.assign(G, 0);
+  if (const char* w = std::getenv("SGIC_FRONT_WORKERS")) S->opt_workers = std::atoi(w) ? 1 : 0;  // A/B runs
   sgic_index* home = shards[0];
   f->d = home->d;
   f->dtype = home->dtype;
