@@ -94,6 +94,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanS
   uint64_t* full_bar = lists + static_cast<size_t>(NQ) * W * p.kp;
   uint64_t* empty_bar = full_bar + kScanMaxStages;
   uint32_t* stage_tile = reinterpret_cast<uint32_t*>(empty_bar + kScanMaxStages);  // tile in each stage (producer -> consumers)
+  // the queries, staged once per CTA: p.q may point into the peer's HBM (multi-GPU front) or into pinned HOST memory
+  // (host-buffer searches skip the H2D copy) — one coalesced read per CTA instead of one per warp
+  float* q_s = reinterpret_cast<float*>(stage_tile + kScanMaxStages);
   constexpr uint32_t kEndOfStream = 0xffffffffu;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -145,6 +148,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanS
   } else {
     // ------------------------------------------------------------ consumers
     // query fragments, rounded to the storage dtype (same rounding the dense path applies)
+    {
+      const uint32_t n4 = (p.nq * p.d) >> 2;  // d is a multiple of 8
+      const float4* src = reinterpret_cast<const float4*>(p.q);
+      for (uint32_t i = tid; i < n4; i += W * 32) reinterpret_cast<float4*>(q_s)[i] = __ldg(src + i);
+      asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");  // the consumer warps only: the producer is already streaming
+    }
     uint32_t qf[NQ][CPL][4];
 #pragma unroll
     for (int qi = 0; qi < NQ; ++qi) {
@@ -152,8 +161,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanS
       for (int c = 0; c < CPL; ++c) {
         const uint32_t chunk = lane + 32 * c;
         if (qi < static_cast<int>(p.nq) && chunk < n_chunks) {
-          const float4* src = reinterpret_cast<const float4*>(p.q + static_cast<size_t>(qi) * p.d + chunk * 8);
-          const float4 a = __ldg(src), b = __ldg(src + 1);
+          const float4* src = reinterpret_cast<const float4*>(q_s + static_cast<size_t>(qi) * p.d + chunk * 8);
+          const float4 a = src[0], b = src[1];
           qf[qi][c][0] = pack2<T>(a.x, a.y);
           qf[qi][c][1] = pack2<T>(a.z, a.w);
           qf[qi][c][2] = pack2<T>(b.x, b.y);

@@ -59,6 +59,7 @@ constexpr size_t kSmemBudget = 232448;  // 227 KB opt-in maximum per CTA on sm_1
 constexpr int kMaxD = 2048;
 constexpr int64_t kMaxK = 1024;
 constexpr size_t kStageChunkBytes = 32u << 20;  // host->device staging granularity for add()
+constexpr size_t kZeroCopyBytes = 64u << 10;     // queries / answers up to this size are read / written in place in pinned host memory
 
 struct DeviceGuard {
   int prev = -1;
@@ -88,6 +89,14 @@ struct sgic_index {
   int d = 0, dtype = SGIC_F16, device = 0, flags = 0;
   int64_t ntotal = 0, capacity = 0;
   void* db = nullptr;
+  // The database lives in ONE virtual address range reserved up front (cuMemAddressReserve, the size of the GPU's
+  // memory) that physical chunks are mapped into as the index grows (cuMemCreate / cuMemMap): growing never copies
+  // and never needs old + new side by side, so an index can grow past half of HBM.  vmm_base == 0: the driver
+  // calls are not available (or SGIC_VMM=0) and the database is a cudaMalloc that is re-allocated to grow.
+  unsigned long long vmm_base = 0;
+  size_t vmm_va_bytes = 0, vmm_mapped = 0, vmm_gran = 0;
+  std::vector<unsigned long long> vmm_handles;
+  std::vector<size_t> vmm_sizes;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   std::mutex mu;
@@ -204,9 +213,138 @@ static int ring_mark(sgic_index* h, bool begin, cudaStream_t st) {
   return 0;
 }
 
-static int ensure_capacity(sgic_index* h, int64_t rows, cudaStream_t st) {
+// ---- virtual-memory backed database ------------------------------------------------------------------------
+struct VmmApi {
+  CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*addr_free)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  bool ok = false;
+};
+
+static const VmmApi& vmm_api() {
+  static VmmApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* env = std::getenv("SGIC_VMM");
+    if (env && std::atoi(env) == 0) return;
+    auto get = [](const char* name, void** out) {
+      cudaDriverEntryPointQueryResult q;
+      return cudaGetDriverEntryPoint(name, out, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess &&
+             *out != nullptr;
+    };
+    api.ok = get("cuMemAddressReserve", reinterpret_cast<void**>(&api.reserve)) &&
+             get("cuMemAddressFree", reinterpret_cast<void**>(&api.addr_free)) &&
+             get("cuMemCreate", reinterpret_cast<void**>(&api.create)) &&
+             get("cuMemRelease", reinterpret_cast<void**>(&api.release)) &&
+             get("cuMemMap", reinterpret_cast<void**>(&api.map)) && get("cuMemUnmap", reinterpret_cast<void**>(&api.unmap)) &&
+             get("cuMemSetAccess", reinterpret_cast<void**>(&api.set_access)) &&
+             get("cuMemGetAllocationGranularity", reinterpret_cast<void**>(&api.granularity));
+    (void)cudaGetLastError();
+  });
+  return api;
+}
+
+static CUmemAllocationProp vmm_prop(int device) {
+  CUmemAllocationProp prop;
+  std::memset(&prop, 0, sizeof(prop));
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = device;
+  return prop;
+}
+
+// reserve the address range once (first growth); false: fall back to cudaMalloc
+static bool vmm_init(sgic_index* h) {
+  const VmmApi& v = vmm_api();
+  if (!v.ok || h->db != nullptr) return false;  // (an index that already holds a cudaMalloc database keeps that scheme)
+  if (h->vmm_base) return true;
+  const CUmemAllocationProp prop = vmm_prop(h->device);
+  size_t gran = 0;
+  if (v.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) return false;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+  const size_t va = ((total_b + gran - 1) / gran) * gran;
+  CUdeviceptr base = 0;
+  if (v.reserve(&base, va, 0, 0, 0) != CUDA_SUCCESS) return false;
+  h->vmm_base = base;
+  h->vmm_va_bytes = va;
+  h->vmm_gran = gran;
+  return true;
+}
+
+// map `bytes` (rounded up to the granularity) more physical memory behind what is mapped already
+static int vmm_grow(sgic_index* h, size_t bytes) {
+  const VmmApi& v = vmm_api();
+  bytes = ((bytes + h->vmm_gran - 1) / h->vmm_gran) * h->vmm_gran;
+  if (h->vmm_mapped + bytes > h->vmm_va_bytes) return 3;
+  const CUmemAllocationProp prop = vmm_prop(h->device);
+  CUmemGenericAllocationHandle handle = 0;
+  if (v.create(&handle, bytes, &prop, 0) != CUDA_SUCCESS) return 3;  // out of memory: the caller may retry smaller
+  if (v.map(h->vmm_base + h->vmm_mapped, bytes, 0, handle, 0) != CUDA_SUCCESS) {
+    v.release(handle);
+    return 2;
+  }
+  CUmemAccessDesc acc;
+  std::memset(&acc, 0, sizeof(acc));
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = h->device;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  if (v.set_access(h->vmm_base + h->vmm_mapped, bytes, &acc, 1) != CUDA_SUCCESS) {
+    v.unmap(h->vmm_base + h->vmm_mapped, bytes);
+    v.release(handle);
+    return 2;
+  }
+  h->vmm_handles.push_back(handle);
+  h->vmm_sizes.push_back(bytes);
+  h->vmm_mapped += bytes;
+  return 0;
+}
+
+static void vmm_destroy(sgic_index* h) {
+  if (!h->vmm_base) return;
+  const VmmApi& v = vmm_api();
+  size_t off = 0;
+  for (size_t i = 0; i < h->vmm_handles.size(); ++i) {
+    v.unmap(h->vmm_base + off, h->vmm_sizes[i]);
+    v.release(h->vmm_handles[i]);
+    off += h->vmm_sizes[i];
+  }
+  v.addr_free(h->vmm_base, h->vmm_va_bytes);
+  h->vmm_handles.clear();
+  h->vmm_sizes.clear();
+  h->vmm_base = 0;
+  h->vmm_mapped = 0;
+  h->db = nullptr;
+}
+
+// exact = true: an explicit reserve() — no geometric slack
+static int grow_database(sgic_index* h, int64_t rows, cudaStream_t st, bool exact) {
   if (rows <= h->capacity) return 0;
-  int64_t cap = std::max<int64_t>(rows, std::max<int64_t>(1024, h->capacity + h->capacity / 2));
+  const size_t row_bytes = static_cast<size_t>(h->d) * 2;
+  if (vmm_init(h)) {
+    const size_t need = static_cast<size_t>(rows) * row_bytes;
+    if (need > h->vmm_mapped) {
+      size_t more = need - h->vmm_mapped;
+      // appends without a reserve(): grow by half of what is there (at least 256 MB) so that n small adds map O(log n) chunks
+      const size_t slack = exact ? more : std::max<size_t>(more, std::max<size_t>(h->vmm_mapped / 2, size_t(256) << 20));
+      int rc = vmm_grow(h, slack);
+      if (rc == 3 && slack > more) rc = vmm_grow(h, more);
+      if (rc) {
+        set_error("mapping " + std::to_string(more) + " more bytes for the database failed (" +
+                  std::to_string(h->vmm_mapped) + " mapped): out of device memory");
+        return 2;
+      }
+    }
+    h->db = reinterpret_cast<void*>(static_cast<uintptr_t>(h->vmm_base));
+    h->capacity = static_cast<int64_t>(h->vmm_mapped / row_bytes);
+    return 0;
+  }
+  int64_t cap = exact ? rows : std::max<int64_t>(rows, std::max<int64_t>(1024, h->capacity + h->capacity / 2));
   void* nb = nullptr;
   cudaError_t e = cudaMalloc(&nb, elt_rows_bytes(h, cap));
   if (e != cudaSuccess && cap > rows) {
@@ -229,6 +367,8 @@ static int ensure_capacity(sgic_index* h, int64_t rows, cudaStream_t st) {
   h->capacity = cap;
   return 0;
 }
+
+static int ensure_capacity(sgic_index* h, int64_t rows, cudaStream_t st) { return grow_database(h, rows, st, false); }
 
 static int ensure_buf(void** p, size_t* cur, size_t need, bool pinned) {
   if (need <= *cur) return 0;
@@ -828,7 +968,8 @@ static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
   const uint32_t R = kScanConsumerWarps * cfg.rb;
   const uint32_t stage_bytes = ((R * h->d * 2u) + 127u) & ~127u;
   const size_t list_bytes = static_cast<size_t>(NQ) * kScanConsumerWarps * kp * 8;
-  const size_t bar_bytes = 2 * kScanMaxStages * 8 + kScanMaxStages * 4;  // full / empty barriers + the stages' tile numbers
+  // full / empty barriers + the stages' tile numbers + the staged queries (fp32)
+  const size_t bar_bytes = 2 * kScanMaxStages * 8 + kScanMaxStages * 4 + static_cast<size_t>(NQ) * h->d * 4;
   SGIC_REQUIRE(list_bytes + bar_bytes + 2 * stage_bytes <= kSmemBudget, "k too large for shared memory");
   // Measured on B200 (profiles/r01_k3_stage_sweep.md): ~128 KB of bulk copies in flight per SM is
   // the sweet spot (7.4-7.5 TB/s); 160 KB and more drops to ~6.8 TB/s, 64 KB to ~6.4 TB/s.
@@ -1116,7 +1257,8 @@ int sgic_index_destroy(sgic_index* h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->odev) cudaFree(h->odev);
   if (h->opin) cudaFreeHost(h->opin);
-  if (h->db) cudaFree(h->db);
+  if (h->vmm_base) vmm_destroy(h);
+  else if (h->db) cudaFree(h->db);
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);
   if (h->tm) cudaEventDestroy(h->tm);
@@ -1149,22 +1291,7 @@ int sgic_index_reserve(sgic_index* h, int64_t rows) {
   if (rows <= h->capacity) return 0;
   int orc = order_begin(h, h->stream);
   if (orc) return orc;
-  // exact reservation: no geometric slack on an explicit request
-  void* nb = nullptr;
-  cudaError_t e = cudaMalloc(&nb, elt_rows_bytes(h, rows));
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    set_error("cudaMalloc of " + std::to_string(elt_rows_bytes(h, rows)) + " bytes failed: " + cudaGetErrorString(e));
-    return 2;
-  }
-  if (h->ntotal > 0) {
-    SGIC_CUDA(cudaMemcpyAsync(nb, h->db, elt_rows_bytes(h, h->ntotal), cudaMemcpyDeviceToDevice, h->stream));
-    SGIC_CUDA(cudaStreamSynchronize(h->stream));
-  }
-  if (h->db) SGIC_CUDA(cudaFree(h->db));
-  h->db = nb;
-  h->capacity = rows;
-  return 0;
+  return grow_database(h, rows, h->stream, /*exact=*/true);
 }
 
 int sgic_index_reset(sgic_index* h) {
@@ -1637,6 +1764,25 @@ int sgic_index_search(sgic_index* h, int64_t nq, const float* host_q, int64_t k,
   if (rc) return rc;
   if ((rc = order_begin(h, h->stream))) return rc;
   if ((rc = order_end(h, h->stream))) return rc;
+  // Small transfers skip the copy engines (their start-up latency, ~8 us each way, is on the critical path of a
+  // short search): the kernels read the queries out of the pinned host buffer themselves (K3 stages them once per
+  // CTA, the tensor-core path converts them in one pass) and the final writer stores the answer straight into it.
+  // Large ones go host -> pinned -> device and back through cudaMemcpyAsync.
+  const bool zc_in = qbytes <= kZeroCopyBytes, zc_out = dbytes + ibytes <= kZeroCopyBytes;
+  if (zc_in && zc_out) {  // two halves of one pinned buffer: answer first, queries behind it
+    const size_t q_off = (dbytes + ibytes + 255) & ~size_t(255);
+    if ((rc = ensure_buf(&h->opin, &h->opin_bytes, q_off + qbytes, true))) return rc;
+    float* pq = reinterpret_cast<float*>(static_cast<uint8_t*>(h->opin) + q_off);
+    std::memcpy(pq, host_q, qbytes);
+    int64_t* pI = reinterpret_cast<int64_t*>(h->opin);
+    float* pD = reinterpret_cast<float*>(static_cast<uint8_t*>(h->opin) + ibytes);
+    rc = search_dev_impl(h, nq, pq, k, pD, pI, 0, h->stream);
+    if (rc) return rc;
+    SGIC_CUDA(cudaStreamSynchronize(h->stream));
+    std::memcpy(host_I, pI, ibytes);
+    std::memcpy(host_D, pD, dbytes);
+    return 0;
+  }
   // queries: host -> pinned -> device; results: device -> pinned -> host
   std::memcpy(h->opin, host_q, qbytes);
   SGIC_CUDA(cudaMemcpyAsync(h->qdev, h->opin, qbytes, cudaMemcpyHostToDevice, h->stream));
@@ -1839,13 +1985,30 @@ int sgic_xchg_search(sgic_xchg* x, sgic_index* h, int64_t nq, const float* host_
   if ((rc = ensure_buf(&h->opin, &h->opin_bytes, std::max(qbytes, cand * 12), true))) return rc;
   if ((rc = order_begin(h, h->stream))) return rc;
   if ((rc = order_end(h, h->stream))) return rc;
-  std::memcpy(h->opin, host_q, qbytes);
-  SGIC_CUDA(cudaMemcpyAsync(h->qdev, h->opin, qbytes, cudaMemcpyHostToDevice, h->stream));
   uint8_t* o = static_cast<uint8_t*>(h->odev);
-  int64_t* mI = reinterpret_cast<int64_t*>(o);                 // merged answer first: ids then scores, contiguous
-  float* mD = reinterpret_cast<float*>(o + cand * 8);
   int64_t* lI = reinterpret_cast<int64_t*>(o + half);          // this rank's local answer
   float* lD = reinterpret_cast<float*>(o + half + cand * 8);
+  if (qbytes <= kZeroCopyBytes && cand * 12 <= kZeroCopyBytes) {
+    // small step: queries read in place from pinned host memory, merged answer stored into it by the merge kernel
+    const size_t q_off = (cand * 12 + 255) & ~size_t(255);
+    if ((rc = ensure_buf(&h->opin, &h->opin_bytes, q_off + qbytes, true))) return rc;
+    float* pq = reinterpret_cast<float*>(static_cast<uint8_t*>(h->opin) + q_off);
+    std::memcpy(pq, host_q, qbytes);
+    int64_t* pI = reinterpret_cast<int64_t*>(h->opin);
+    float* pD = reinterpret_cast<float*>(static_cast<uint8_t*>(h->opin) + cand * 8);
+    rc = search_dev_impl(h, nq, pq, k, lD, lI, id_base, h->stream);
+    if (rc) return rc;
+    rc = sgic_xchg_merge_dev(x, nq, k, lD, lI, pD, pI, tie_by_position, h->stream);
+    if (rc) return rc;
+    SGIC_CUDA(cudaStreamSynchronize(h->stream));
+    std::memcpy(host_I, pI, cand * 8);
+    std::memcpy(host_D, pD, cand * 4);
+    return 0;
+  }
+  std::memcpy(h->opin, host_q, qbytes);
+  SGIC_CUDA(cudaMemcpyAsync(h->qdev, h->opin, qbytes, cudaMemcpyHostToDevice, h->stream));
+  int64_t* mI = reinterpret_cast<int64_t*>(o);                 // merged answer first: ids then scores, contiguous
+  float* mD = reinterpret_cast<float*>(o + cand * 8);
   rc = search_dev_impl(h, nq, static_cast<const float*>(h->qdev), k, lD, lI, id_base, h->stream);
   if (rc) return rc;
   rc = sgic_xchg_merge_dev(x, nq, k, lD, lI, mD, mI, tie_by_position, h->stream);

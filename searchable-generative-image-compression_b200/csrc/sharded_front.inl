@@ -17,9 +17,14 @@ namespace sgic {
 // host thread (each launch sequence costs ~5 us; at 8 GPUs the last shard would start ~40 us late) -------------
 class ShardPool {
  public:
-  explicit ShardPool(int n) : n_(n) {
+  // devices[g]: the GPU worker g launches on; made current once, so the DeviceGuards inside the jobs are no-ops
+  ShardPool(int n, const std::vector<int>& devices) : n_(n) {
     for (int g = 1; g < n_; ++g) slots_.emplace_back(new Slot());
-    for (int g = 1; g < n_; ++g) threads_.emplace_back([this, g] { loop(g); });
+    for (int g = 1; g < n_; ++g)
+      threads_.emplace_back([this, g, dev = devices[static_cast<size_t>(g)]] {
+        cudaSetDevice(dev);
+        loop(g);
+      });
   }
   ~ShardPool() {
     {
@@ -122,7 +127,11 @@ static int for_shards(sgic_index* f, bool parallel, const std::function<int(int)
     if (rcs[static_cast<size_t>(g)]) S->errs[static_cast<size_t>(g)] = g_err;
   };
   if (parallel && G > 1 && S->opt_workers) {
-    if (!S->pool) S->pool.reset(new ShardPool(G));
+    if (!S->pool) {
+      std::vector<int> devs;
+      for (const sgic_index* s : f->shards) devs.push_back(s->device);
+      S->pool.reset(new ShardPool(G, devs));
+    }
     S->pool->run(body);
   } else {
     for (int g = 0; g < G; ++g) body(g);
@@ -212,13 +221,17 @@ static int front_shard_search(sgic_index* f, int g, int64_t nq, const float* q_p
   const size_t qbytes = static_cast<size_t>(nq) * s->d * 4, cand = static_cast<size_t>(nq) * k;
   const float* q_dev = nullptr;
   if (q_pinned) {
-    if ((rc = ensure_buf(&s->qdev, &s->qdev_bytes, qbytes, false))) return rc;
-    SGIC_CUDA(cudaMemcpyAsync(s->qdev, q_pinned, qbytes, cudaMemcpyHostToDevice, st));
-    q_dev = static_cast<const float*>(s->qdev);
+    if (qbytes <= kZeroCopyBytes) {
+      q_dev = q_pinned;  // the kernels read the pinned host buffer themselves: no copy engine on the critical path
+    } else {
+      if ((rc = ensure_buf(&s->qdev, &s->qdev_bytes, qbytes, false))) return rc;
+      SGIC_CUDA(cudaMemcpyAsync(s->qdev, q_pinned, qbytes, cudaMemcpyHostToDevice, st));
+      q_dev = static_cast<const float*>(s->qdev);
+    }
   } else {
     SGIC_CUDA(cudaStreamWaitEvent(st, S->ev_q, 0));
-    if (s->device == home->device) {
-      q_dev = q_home;
+    if (s->device == home->device || (S->direct[gi] && qbytes <= kZeroCopyBytes)) {
+      q_dev = q_home;  // small batches are read out of the home GPU's memory over NVLink (K3: once per CTA)
     } else {
       if ((rc = ensure_buf(&s->qdev, &s->qdev_bytes, qbytes, false))) return rc;
       SGIC_CUDA(cudaMemcpyPeerAsync(s->qdev, s->device, q_home, home->device, qbytes, st));
@@ -336,10 +349,16 @@ static int front_search_host(sgic_index* f, int64_t nq, const float* host_q, int
   {
     std::lock_guard<std::mutex> hl(home->mu);
     DeviceGuard dg(home->device);
-    int64_t* oI = reinterpret_cast<int64_t*>(S->out_dev);
-    float* oD = reinterpret_cast<float*>(static_cast<uint8_t*>(S->out_dev) + cand * 8);
-    if ((rc = front_merge(f, nq, k, oD, oI, home->stream))) return rc;
-    SGIC_CUDA(cudaMemcpyAsync(S->pin_o, S->out_dev, cand * 12, cudaMemcpyDeviceToHost, home->stream));
+    if (cand * 12 <= kZeroCopyBytes) {  // the merge kernel stores the answer into the pinned host buffer itself
+      int64_t* oI = reinterpret_cast<int64_t*>(S->pin_o);
+      float* oD = reinterpret_cast<float*>(static_cast<uint8_t*>(S->pin_o) + cand * 8);
+      if ((rc = front_merge(f, nq, k, oD, oI, home->stream))) return rc;
+    } else {
+      int64_t* oI = reinterpret_cast<int64_t*>(S->out_dev);
+      float* oD = reinterpret_cast<float*>(static_cast<uint8_t*>(S->out_dev) + cand * 8);
+      if ((rc = front_merge(f, nq, k, oD, oI, home->stream))) return rc;
+      SGIC_CUDA(cudaMemcpyAsync(S->pin_o, S->out_dev, cand * 12, cudaMemcpyDeviceToHost, home->stream));
+    }
     SGIC_CUDA(cudaStreamSynchronize(home->stream));
   }
   std::memcpy(host_I, S->pin_o, cand * 8);

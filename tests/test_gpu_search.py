@@ -2,6 +2,9 @@
 Everything goes through the faiss-compatible surface, i.e. through the C ABI."""
 import numpy as np
 import pytest
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
 
 pytestmark = pytest.mark.gpu
 
@@ -145,3 +148,42 @@ def test_k_beyond_1024_runs_in_passes(n, nq, k):
     D1, I1 = idx.search(xq, 1024)
     assert np.array_equal(I[:, :1024], I1)
     np.testing.assert_allclose(D[:, :1024], D1, atol=2e-5, rtol=0)
+
+
+def test_database_grows_in_place_without_a_second_copy():
+    """The database sits in one reserved virtual range that physical chunks are mapped into (cuMemMap): growing keeps
+    the base address, copies nothing and never needs old + new buffers side by side — appends work past half of HBM
+    without a reserve()."""
+    import ctypes as C
+    from sgic_b200 import _native, faiss_compat as faiss
+    rng = np.random.default_rng(77)
+    d, step, rounds = 512, 60_000, 10
+    xb = rng.standard_normal((step * rounds, d)).astype(np.float32)
+    xb /= np.linalg.norm(xb, axis=1, keepdims=True)
+    idx = faiss.IndexFlatIP(d, device=0, retain_fp32=False)
+    lib = _native.lib()
+    ptrs, caps = [], []
+    for r in range(rounds):
+        idx.add(xb[r * step:(r + 1) * step])
+        ptrs.append(lib.sgic_index_data_dev(idx._h))
+        caps.append(idx.stat("capacity"))
+    assert len(set(ptrs)) == 1, "the database moved while growing"
+    assert caps == sorted(caps) and caps[-1] >= step * rounds and len(set(caps)) >= 2      # grew in several steps
+    got = idx.reconstruct_n(0, step * rounds)
+    assert np.array_equal(got, xb.astype(np.float16).astype(np.float32))                   # nothing lost on the way
+    idx.reserve(caps[-1] + 1_000_000)
+    assert lib.sgic_index_data_dev(idx._h) == ptrs[0] and idx.stat("capacity") >= caps[-1] + 1_000_000
+    D, I = idx.search(xb[-1:], 1)
+    assert I[0, 0] == step * rounds - 1
+    idx.reset()
+    assert idx.ntotal == 0 and lib.sgic_index_data_dev(idx._h) == ptrs[0]
+    idx.close()
+    # the cudaMalloc scheme (SGIC_VMM=0) stays available: same answers in a fresh process
+    import os, subprocess, sys
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); from sgic_b200 import faiss_compat as faiss;"
+            "rng=np.random.default_rng(1); x=rng.standard_normal((5000,64)).astype('float32');"
+            "i=faiss.IndexFlatIP(64, device=0);"
+            "[i.add(x[j*500:(j+1)*500]) for j in range(10)];"
+            "D,I=i.search(x[4321:4322],1); assert I[0,0]==4321; print('ok')") % str(ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SGIC_VMM="0"), capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr
