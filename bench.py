@@ -638,8 +638,18 @@ def extras(faiss, fill_index_random, random_unit_queries, torch, dev, pk):
         par, _ = verify_search(idx, q, D, I, k)
         if not par["ok"]:
             raise SystemExit(f"PARITY FAILURE in {name}: {par}")
+        # the same search end to end: host numpy in, numpy out (queries read in place from pinned memory, the answer
+        # stored into it by the kernel's last CTA; one synchronise) — back to back, L2 not flushed
+        qh = q.cpu().numpy()
+        for _ in range(20):
+            idx.search(qh, k)
+        lat = []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            idx.search(qh, k)
+            lat.append((time.perf_counter() - t0) * 1e3)
         res.append({"workload": name, "ms_per_step": m, "ms_best": min(ms), "queries_per_s": nq / m * 1e3, "GBs": gbs,
-                    "parity": par,
+                    "parity": par, "e2e_host_call_ms_median": statistics.median(lat), "e2e_host_call_ms_best": min(lat),
                     "frac_of_measured_hbm": gbs / pk["hbm_gbs"],
                     "l2": "flushed between iterations: 256 MB memset, then a 256 MB read so that no dirty lines are left",
                     "write_only_flush": {"ms_per_step": md, "GBs": rows * d * 2 / md / 1e6,

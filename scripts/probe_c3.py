@@ -27,9 +27,12 @@ def reader():
             pass
 threading.Thread(target=reader, daemon=True).start()
 print(f"rows={n} d={d} nq={nq}", flush=True)
-for k, dbg, name in ((100, 0, "k=100"), (100, 4, "k=100, epilogue off"), (10, 0, "k=10"), (10, 4, "k=10, epilogue off"), (100, 0, "k=100 again")):
+for k, dbg, seed, name in ((100, 0, 1, "k=100 (sample pass)"), (100, 0, 0, "k=100, no sample pass"), (100, 4, 0, "k=100, epilogue off"),
+                          (10, 0, 1, "k=10"), (10, 4, 1, "k=10, epilogue off"), (100, 0, 1, "k=100 (sample pass) again"),
+                          (100, 0, 0, "k=100, no sample pass again")):
     D = torch.empty((nq, k), device="cuda"); I = torch.empty((nq, k), dtype=torch.int64, device="cuda")
     idx.set_option("debug", dbg)
+    idx.set_option("dense_seed", seed)
     for _ in range(3): idx.search_torch(q, k, out=(D, I))
     torch.cuda.synchronize()
     t0 = time.time(); it = 0
@@ -43,7 +46,7 @@ for k, dbg, name in ((100, 0, "k=100"), (100, 4, "k=100, epilogue off"), (10, 0,
     ms = e0.elapsed_time(e1) / it
     clk = [s for (t, s, p) in samples if t0 + 0.5 < t < t1]
     pw = [p for (t, s, p) in samples if t0 + 0.5 < t < t1]
-    print(f"{name:22s} ms={ms:8.3f} TF={2*nq*n*d/ms/1e9:6.0f} sm_mhz={statistics.median(clk) if clk else None} "
+    print(f"{name:32s} ms={ms:8.3f} TF={2*nq*n*d/ms/1e9:6.0f} sm_mhz={statistics.median(clk) if clk else None} "
           f"power={statistics.median(pw) if pw else None}", flush=True)
 idx.set_option("debug", 0)
 smi.kill()

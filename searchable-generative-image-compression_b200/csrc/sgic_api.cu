@@ -2,6 +2,7 @@
 // IxFI (de)serialisation.  Host logic only; the kernels live in the .cuh files next to this.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -114,6 +115,8 @@ struct sgic_index {
   size_t qh_bytes = 0;
   void* lists_ws = nullptr;  // dense path, k > 32: per-query reservoirs
   size_t lists_ws_bytes = 0;
+  void* seed_ws = nullptr;   // dense path, k > 32: answer of the sample pass + the per-query start thresholds
+  size_t seed_ws_bytes = 0;
   // device-side clip_stream decode (K0): u8 row matrix, packed frames, descriptors, per-frame status
   // ingest pipeline (device-side clip_stream decode): kZlDepth slabs in flight — the host walks / packs slab i
   // while slab i-1 crosses PCIe on the copy stream and K0 decodes slab i-2 on the index's stream
@@ -164,7 +167,7 @@ struct sgic_index {
   int64_t shard_row_start = 0, shard_total_rows = -1;
   int shard_id = 0, shard_count = 1;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1, opt_trace = 0, opt_steal = 1, opt_t_n8 = 1, opt_t_max_nq = 88;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1, opt_trace = 0, opt_steal = 1, opt_t_n8 = 1, opt_t_max_nq = 88, opt_dense_seed = 1;
   int64_t stat_ingest_h2d_ns = 0, stat_ingest_k0_ns = 0, stat_ingest_k1_ns = 0;
   int64_t stat_ingest_parse_ns = 0, stat_ingest_pack_ns = 0, stat_ingest_gpu_ns = 0;
   int64_t stat_zl_device_frames = 0, stat_zl_host_rows = 0, stat_zl_fallback_slabs = 0;
@@ -261,8 +264,8 @@ static CUmemAllocationProp vmm_prop(int device) {
 // reserve the address range once (first growth); false: fall back to cudaMalloc
 static bool vmm_init(sgic_index* h) {
   const VmmApi& v = vmm_api();
-  if (!v.ok || h->db != nullptr) return false;  // (an index that already holds a cudaMalloc database keeps that scheme)
   if (h->vmm_base) return true;
+  if (!v.ok || h->db != nullptr) return false;  // (an index that already holds a cudaMalloc database keeps that scheme)
   const CUmemAllocationProp prop = vmm_prop(h->device);
   size_t gran = 0;
   if (v.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) return false;
@@ -590,10 +593,49 @@ static uint32_t gcd_u32(uint32_t a, uint32_t b) {
 constexpr int kDenseBN = 256;
 constexpr int64_t kDenseQueryBlock = 4096;  // queries per launch (FAISS blocks queries by 4096 too)
 
+// Per-query start thresholds for the reservoir epilogue (k > 32): seed[q] = the order-preserving word just below the
+// k-th best score of query q over a SAMPLE of the rows (0 = no bound).  At least k rows score above it, so every list
+// of the query may start from it instead of -inf — the same protocol as DenseParams::gthr (ties stay admissible).
+__global__ void seed_gthr_kernel(const float* D, const long long* I, uint32_t nq, uint32_t k, uint32_t* seed) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const size_t last = static_cast<size_t>(q) * k + (k - 1);
+  seed[q] = I[last] >= 0 ? score_to_ord(D[last]) - 1u : 0u;
+}
+
+// rows_limit > 0: only the first rows_limit rows are searched (the sample pass below); such a call never seeds itself
 static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
-                             int64_t id_base, cudaStream_t st) {
+                             int64_t id_base, cudaStream_t st, int64_t rows_limit = 0) {
   using Cfg = DenseCfg<kDenseBN>;
-  const uint32_t n_rows = static_cast<uint32_t>(h->ntotal);
+  const uint32_t n_rows = static_cast<uint32_t>(rows_limit > 0 ? std::min<int64_t>(rows_limit, h->ntotal) : h->ntotal);
+  // Sample pass.  With k > 32 every (query, slice) list fills from -inf: ~(C-k) ln(n/C)/ln(C/k) appends and a
+  // compaction of every lane's reservoir in lockstep at the start of each item.  A search of the first rows of the
+  // shard alone (0.5 % of the work at 10M rows) gives each query a bound that at least k rows beat; lists that start
+  // from it skip most of the warm-up.  "dense_seed" = 0 switches it off (A/B); the answer is the same either way.
+  const uint32_t* seed_all = nullptr;
+  const bool huge_shard = ((static_cast<size_t>(n_rows) * h->d * 2) >> 20) >= static_cast<size_t>(h->opt_dense_b_min_mb);
+  if (rows_limit == 0 && k > 32 && h->opt_dense_seed && h->opt_dense_gthr && nq >= 64 && h->ntotal >= (4ll << 20) &&
+      h->opt_dense_mode != 4 && !(h->opt_dense_mode == 0 && huge_shard && nq > 256 && h->d <= 512)) {
+    const int64_t sample = 65536;
+    const size_t cand = static_cast<size_t>(nq) * k;
+    const size_t need = cand * 12 + static_cast<size_t>(nq) * 4 + 64;
+    if (need > h->seed_ws_bytes) {
+      SGIC_CUDA(cudaStreamSynchronize(st));
+      int rc0 = ensure_buf(&h->seed_ws, &h->seed_ws_bytes, need, false);
+      if (rc0) return rc0;
+    }
+    int64_t* sI = reinterpret_cast<int64_t*>(h->seed_ws);
+    float* sD = reinterpret_cast<float*>(static_cast<uint8_t*>(h->seed_ws) + cand * 8);
+    uint32_t* seed = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(h->seed_ws) + cand * 12);
+    int rc0 = search_dense_impl(h, nq, dev_q, k, sD, sI, 0, st, sample);
+    if (rc0) return rc0;
+    seed_gthr_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, st>>>(sD, reinterpret_cast<const long long*>(sI),
+                                                                              static_cast<uint32_t>(nq),
+                                                                              static_cast<uint32_t>(k), seed);
+    h->stat_launches++;
+    SGIC_CUDA(cudaGetLastError());
+    seed_all = seed;
+  }
   const uint32_t kp = std::max<uint32_t>(2, next_pow2_u32(static_cast<uint32_t>(k)));
   // k <= 32: thread-private sorted lists in shared memory (k KB per CTA); larger k: per-query reservoirs of
   // res_cap keys in an L2-resident workspace, compacted by the warp when full (lists come out unsorted)
@@ -814,7 +856,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.n_lists = n_lists;
     p.by_slice = by_slice ? 1u : 0u;
     // items of one query tile that run one after the other inherit each other's bounds ("dense_gthr" = 0: off)
-    p.gthr = (by_slice && n_slices > 1 && h->opt_dense_gthr)
+    p.gthr = (by_slice && (n_slices > 1 || seed_all != nullptr) && h->opt_dense_gthr)
                  ? reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(h->ws) + gthr_off) : nullptr;
     p.kc = (static_cast<uint32_t>(h->d) + kDenseBK - 1) / kDenseBK;
     p.tp = tp ? 1u : 0u;
@@ -835,7 +877,10 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     h->ws_counter = nullptr;  // this launch overwrites the workspace: K3 must re-zero its "CTAs done" counter
     // empty lists where a CTA resumes its own slot; the by-slice schedule writes every list in full
     if (transposed || !by_slice) SGIC_CUDA(cudaMemsetAsync(h->ws, 0, partial_bytes, st));
-    if (!transposed && p.gthr) SGIC_CUDA(cudaMemsetAsync(p.gthr, 0, gthr_bytes, st));
+    if (!transposed && p.gthr) {
+      if (seed_all) SGIC_CUDA(cudaMemcpyAsync(p.gthr, seed_all + q0, gthr_bytes, cudaMemcpyDeviceToDevice, st));
+      else SGIC_CUDA(cudaMemsetAsync(p.gthr, 0, gthr_bytes, st));
+    }
     if (q0 == 0 && (rc = ring_mark(h, true, st))) return rc;
     if (transposed) {
       DenseTParams tp_;
@@ -1241,6 +1286,7 @@ int sgic_index_destroy(sgic_index* h) {
   if (h->qdev) cudaFree(h->qdev);
   if (h->qh) cudaFree(h->qh);
   if (h->lists_ws) cudaFree(h->lists_ws);
+  if (h->seed_ws) cudaFree(h->seed_ws);
   if (h->ws2) cudaFree(h->ws2);
   for (auto& z : h->zl) {
     if (z.rows) cudaFree(z.rows);
@@ -2258,28 +2304,69 @@ static int read_v2_body(FILE* f, const char* path, const Sgi2Header& hd, int dev
     set_error(msg);
     return code;
   };
-  if (std::fseek(f, static_cast<long>(hd.payload_offset), SEEK_SET) != 0) return fail(std::string("seek error in ") + path, 3);
   {
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
-    rc = ensure_staging(h);
-    if (rc) {
-      sgic_index_destroy(h);
-      return rc;
-    }
+    // Several readers, each with its own pair of pinned chunks and its own stream: chunk c is pread() by reader
+    // c % T into pinned memory while that reader's previous chunk crosses PCIe.  One reader is bound by the copy out
+    // of the page cache (~6 GB/s measured); four keep a PCIe 5 x16 link busy.
     const size_t total = elt_rows_bytes(h, hd.ntotal);
-    size_t done = 0;
-    int b = 0;
-    while (done < total) {
-      const size_t n = std::min(total - done, kStageChunkBytes);
-      if (cudaEventSynchronize(h->ev[b]) != cudaSuccess) return fail("cudaEventSynchronize failed while loading", 2);
-      if (std::fread(h->pin[b], 1, n, f) != n)
+    const int T = static_cast<int>(std::min<size_t>(4, std::max<size_t>(1, total / (8u << 20))));
+    // small files: small pinned chunks (pinning memory is not free), large ones: 32 MB
+    const size_t chunk = std::min<size_t>(kStageChunkBytes,
+                                          std::max<size_t>(size_t(1) << 20, ((total / (2 * static_cast<size_t>(T)) + 4095) & ~size_t(4095))));
+    const size_t n_chunks = (total + chunk - 1) / chunk;
+    const int fd = fileno(f);
+    std::vector<int> trc(static_cast<size_t>(T), 0);
+    std::vector<std::thread> readers;
+    const int device = h->device;
+    uint8_t* db = static_cast<uint8_t*>(h->db);
+    const uint64_t payload = hd.payload_offset;
+    for (int t = 0; t < T; ++t)
+      readers.emplace_back([&, t] {
+        cudaSetDevice(device);
+        void* pin[2] = {nullptr, nullptr};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        cudaStream_t st = nullptr;
+        int& rc_t = trc[static_cast<size_t>(t)];
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) rc_t = 2;
+        for (int b = 0; b < 2 && !rc_t; ++b)
+          if (cudaMallocHost(&pin[b], chunk) != cudaSuccess || cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming) != cudaSuccess)
+            rc_t = 2;
+        int b = 0;
+        for (size_t c = static_cast<size_t>(t); c < n_chunks && !rc_t; c += static_cast<size_t>(T), b ^= 1) {
+          const size_t off = c * chunk, n = std::min(chunk, total - off);
+          if (cudaEventSynchronize(ev[b]) != cudaSuccess) {
+            rc_t = 2;
+            break;
+          }
+          size_t got = 0;
+          while (got < n) {
+            const ssize_t r = pread(fd, static_cast<uint8_t*>(pin[b]) + got, n - got, static_cast<off_t>(payload + off + got));
+            if (r <= 0) break;
+            got += static_cast<size_t>(r);
+          }
+          if (got != n) {
+            rc_t = 3;
+            break;
+          }
+          if (cudaMemcpyAsync(db + off, pin[b], n, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+              cudaEventRecord(ev[b], st) != cudaSuccess)
+            rc_t = 2;
+        }
+        if (st) cudaStreamSynchronize(st);
+        for (int i = 0; i < 2; ++i) {
+          if (ev[i]) cudaEventDestroy(ev[i]);
+          if (pin[i]) cudaFreeHost(pin[i]);
+        }
+        if (st) cudaStreamDestroy(st);
+      });
+    for (auto& th : readers) th.join();
+    (void)cudaGetLastError();
+    for (int t = 0; t < T; ++t) {
+      if (trc[static_cast<size_t>(t)] == 3)
         return fail(std::string("read error in ") + path + ": file shorter than its header says", 3);
-      if (cudaMemcpyAsync(static_cast<uint8_t*>(h->db) + done, h->pin[b], n, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
-          cudaEventRecord(h->ev[b], h->stream) != cudaSuccess)
-        return fail("H2D copy failed while loading", 2);
-      done += n;
-      b ^= 1;
+      if (trc[static_cast<size_t>(t)]) return fail("H2D copy failed while loading", 2);
     }
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail("stream synchronise failed while loading", 2);
     h->ntotal = hd.ntotal;
@@ -2432,6 +2519,7 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "steal") h->opt_steal = value ? 1 : 0;
   else if (n == "t_n8") h->opt_t_n8 = value ? 1 : 0;
   else if (n == "t_max_nq") h->opt_t_max_nq = std::max<int64_t>(0, value);
+  else if (n == "dense_seed") h->opt_dense_seed = value ? 1 : 0;
   else if (n == "trace") h->opt_trace = value;  // device address of a [grid][4] u64 buffer (0 = off), see scan_small.cuh
   else if (n == "drop_retained") {
     std::lock_guard<std::mutex> lk(h->mu);
