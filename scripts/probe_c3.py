@@ -27,9 +27,12 @@ def reader():
             pass
 threading.Thread(target=reader, daemon=True).start()
 print(f"rows={n} d={d} nq={nq}", flush=True)
-for k, dbg, seed, name in ((100, 0, 1, "k=100 (sample pass)"), (100, 0, 0, "k=100, no sample pass"), (100, 4, 0, "k=100, epilogue off"),
-                          (10, 0, 1, "k=10"), (10, 4, 1, "k=10, epilogue off"), (100, 0, 1, "k=100 (sample pass) again"),
-                          (100, 0, 0, "k=100, no sample pass again")):
+for k, dbg, seed, slices, name in ((100, 0, 1, 0, "k=100 seeded, auto slices"), (100, 0, 1, 9, "k=100 seeded, 9 slices"),
+                                  (100, 0, 1, 18, "k=100 seeded, 18 slices"), (100, 0, 1, 37, "k=100 seeded, 37 slices"),
+                                  (100, 0, 1, 74, "k=100 seeded, 74 slices"), (100, 0, 0, 0, "k=100 unseeded (round 1)"),
+                                  (100, 0, 0, 37, "k=100 unseeded, 37 slices"), (100, 4, 0, 0, "k=100, epilogue off"),
+                                  (10, 0, 1, 0, "k=10"), (100, 0, 1, 0, "k=100 seeded, auto again")):
+    idx.set_option("dense_slices", slices)
     D = torch.empty((nq, k), device="cuda"); I = torch.empty((nq, k), dtype=torch.int64, device="cuda")
     idx.set_option("debug", dbg)
     idx.set_option("dense_seed", seed)

@@ -167,7 +167,7 @@ struct sgic_index {
   int64_t shard_row_start = 0, shard_total_rows = -1;
   int shard_id = 0, shard_count = 1;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1, opt_trace = 0, opt_steal = 1, opt_t_n8 = 1, opt_t_max_nq = 88, opt_dense_seed = 1;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1, opt_trace = 0, opt_steal = 1, opt_t_n8 = 1, opt_t_max_nq = 88, opt_dense_seed = 1, opt_dense_slices = 0;
   int64_t stat_ingest_h2d_ns = 0, stat_ingest_k0_ns = 0, stat_ingest_k1_ns = 0;
   int64_t stat_ingest_parse_ns = 0, stat_ingest_pack_ns = 0, stat_ingest_gpu_ns = 0;
   int64_t stat_zl_device_frames = 0, stat_zl_host_rows = 0, stat_zl_fallback_slabs = 0;
@@ -614,9 +614,11 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
   // from it skip most of the warm-up.  "dense_seed" = 0 switches it off (A/B); the answer is the same either way.
   const uint32_t* seed_all = nullptr;
   const bool huge_shard = ((static_cast<size_t>(n_rows) * h->d * 2) >> 20) >= static_cast<size_t>(h->opt_dense_b_min_mb);
-  if (rows_limit == 0 && k > 32 && h->opt_dense_seed && h->opt_dense_gthr && nq >= 64 && h->ntotal >= (4ll << 20) &&
+  const bool seed_forced = h->opt_dense_seed == 2 && h->ntotal >= 8192;  // tests: the sample pass on small shards too
+  if (rows_limit == 0 && k > 32 && h->opt_dense_seed && h->opt_dense_gthr &&
+      ((nq >= 64 && h->ntotal >= (4ll << 20)) || seed_forced) &&
       h->opt_dense_mode != 4 && !(h->opt_dense_mode == 0 && huge_shard && nq > 256 && h->d <= 512)) {
-    const int64_t sample = 65536;
+    const int64_t sample = std::min<int64_t>(65536, std::max<int64_t>(1024, (h->ntotal / 8) & ~int64_t(255)));
     const size_t cand = static_cast<size_t>(nq) * k;
     const size_t need = cand * 12 + static_cast<size_t>(nq) * 4 + 64;
     if (need > h->seed_ws_bytes) {
@@ -703,7 +705,10 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     // 33 ms with the epilogue off).  Fewer, longer slices cut that work in proportion; the price is an item count
     // that no longer divides the CTAs.  Pick the slice count that minimises (rounds * units / items) * (1 + 0.008
     // slices): 16 query tiles on 74 pairs -> 9 slices (144 items, 2 rounds, 2.7 % idle) instead of 37.
-    if (!tp && m_tiles * n_slices > n_units) {
+    // With the sample pass the lists start from a tight bound and their warm-up is cheap, so the short slices are
+    // back: the CTA pairs that share a slice re-align at every item boundary and meet in L2 (C3 with 9 long slices
+    // read 140-166 GB from DRAM for a 15 GB database, L2 hit rate 61 %).  "dense_slices" > 0 forces a slice count.
+    if (!tp && m_tiles * n_slices > n_units && seed_all == nullptr && h->opt_dense_slices == 0) {
       double best_cost = 1e30;
       uint32_t best = n_slices;
       for (uint32_t ns = 1; ns <= std::min(step, n_tiles); ++ns) {
@@ -718,6 +723,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
       }
       n_slices = best;
     }
+    if (h->opt_dense_slices > 0) n_slices = std::max<uint32_t>(1, std::min<uint32_t>(static_cast<uint32_t>(h->opt_dense_slices), n_tiles));
     const size_t tile_bytes = static_cast<size_t>(kDenseBN) * h->d * 2;
     const size_t l2_budget = static_cast<size_t>(h->opt_dense_l2_mb) << 20;
     if (l2_budget > 0 && m_tiles > 1 && static_cast<size_t>(n_tiles) * tile_bytes > l2_budget) {
@@ -2312,8 +2318,9 @@ static int read_v2_body(FILE* f, const char* path, const Sgi2Header& hd, int dev
     // of the page cache (~6 GB/s measured); four keep a PCIe 5 x16 link busy.
     const size_t total = elt_rows_bytes(h, hd.ntotal);
     const int T = static_cast<int>(std::min<size_t>(4, std::max<size_t>(1, total / (8u << 20))));
-    // small files: small pinned chunks (pinning memory is not free), large ones: 32 MB
-    const size_t chunk = std::min<size_t>(kStageChunkBytes,
+    // 4 MB chunks: pinning memory costs about as much per byte as reading it (the first version pinned 8 x 32 MB per
+    // load and was slower than one reader); 8 x 4 MB keeps four preads and four H2D copies in flight
+    const size_t chunk = std::min<size_t>(size_t(4) << 20,
                                           std::max<size_t>(size_t(1) << 20, ((total / (2 * static_cast<size_t>(T)) + 4095) & ~size_t(4095))));
     const size_t n_chunks = (total + chunk - 1) / chunk;
     const int fd = fileno(f);
@@ -2519,7 +2526,8 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "steal") h->opt_steal = value ? 1 : 0;
   else if (n == "t_n8") h->opt_t_n8 = value ? 1 : 0;
   else if (n == "t_max_nq") h->opt_t_max_nq = std::max<int64_t>(0, value);
-  else if (n == "dense_seed") h->opt_dense_seed = value ? 1 : 0;
+  else if (n == "dense_slices") h->opt_dense_slices = std::max<int64_t>(0, value);
+  else if (n == "dense_seed") h->opt_dense_seed = std::max<int64_t>(0, std::min<int64_t>(2, value));  // 2: force (tests)
   else if (n == "trace") h->opt_trace = value;  // device address of a [grid][4] u64 buffer (0 = off), see scan_small.cuh
   else if (n == "drop_retained") {
     std::lock_guard<std::mutex> lk(h->mu);

@@ -176,17 +176,31 @@ def main(argv=None) -> None:
         sp.add_argument("--topk", type=int, default=10)
         if name != "query-c2df":
             sp.add_argument("--vec", type=Path, default=None,
-                            help="pre-computed CLIP embedding (.npy); the CLIP encoders are out of scope here")
+                            help="pre-computed CLIP embedding (.npy)")
+            sp.add_argument("--clip_dir", type=Path, default=None,
+                            help="local CLIP checkpoint directory (Hugging Face layout): the query is embedded on the "
+                                 "index's GPU and searched without leaving it (query_encoders.ClipQueryEncoder)")
     args = ap.parse_args(argv)
     try:
         index, paths, _meta = load_index(args.index_dir)
         if args.cmd == "query-c2df":
             q = encode_c2df_query(args.c2df)
+        elif args.cmd in ("query-text", "query-image") and args.vec is None and args.clip_dir is not None:
+            from .query_encoders import ClipQueryEncoder
+            enc = ClipQueryEncoder(args.clip_dir, device=index.device)
+            if args.cmd == "query-text":
+                z = enc.encode_text([args.text])
+            else:
+                from PIL import Image
+                z = enc.encode_image([Image.open(args.image).convert("RGB")])
+            results = enc.search(index, z, paths, topk=args.topk)[0]
+            print(json.dumps([{"path": p, "score": s} for p, s in results], ensure_ascii=False, indent=2))
+            return
         elif args.cmd in ("query-text", "query-image"):
             if args.vec is None:
                 raise NotImplementedError(
-                    f"{args.cmd}: the OpenCLIP encoder is outside this path (no weights offline); "
-                    "pass the embedding with --vec file.npy")
+                    f"{args.cmd}: no CLIP weights can be fetched offline; pass a local checkpoint with --clip_dir DIR "
+                    "or the embedding with --vec file.npy")
             q = _load_vec(args.vec, index.d)
         else:
             raise ValueError(f"Unknown behavior: {args.cmd}")

@@ -256,3 +256,31 @@ def test_mixed_batch_sizes_share_the_workspace():
         if nq in ref:
             assert np.array_equal(ref[nq][1], I) and np.array_equal(ref[nq][0], D)
         ref[nq] = (D, I)
+
+
+def test_sample_pass_does_not_change_large_k_answers():
+    """k > 32: lists may start from the k-th best score of a SAMPLE of the rows instead of -inf (dense_seed).  The bound
+    is valid whatever the sample looks like — including a sample that holds the best rows, duplicates that tie with the
+    k-th score, and fewer than k good rows — so answers must be bit-identical with the pass forced on and off."""
+    rng = np.random.default_rng(53)
+    n, d, nq, k = 300_000, 512, 300, 100
+    xb, xq = unit(rng, n, d), unit(rng, nq, d)
+    xb[:60] = xq[0] * 0.9 + 0.1 * xb[:60]                 # the sample (first rows) holds query 0's best rows ...
+    xb[200_000:200_040] = xb[:40]                           # ... and 40 of them again far outside it: exact ties
+    xb[250_000:250_200] = xq[1] * 0.95 + 0.05 * xb[250_000:250_200]   # query 1's best rows lie outside the sample
+    xb /= np.linalg.norm(xb, axis=1, keepdims=True)
+    idx = make_index(xb, retain_fp32=False)
+    idx.set_option("dense_seed", 0)
+    D0, I0 = idx.search(xq, k)
+    idx.set_option("dense_seed", 2)
+    launches = idx.stat("launches")
+    D2, I2 = idx.search(xq, k)
+    assert idx.stat("launches") - launches >= 6             # the sample search + seed kernel ran in front of the real one
+    assert np.array_equal(I0, I2) and np.array_equal(D0, D2)
+    sel = np.array([0, 1, 2, 150, 299])
+    check_topk(D2[sel], I2[sel], f16(xb), f16(xq[sel]), k, score_tol=3e-5, tie_tol=1e-6)
+    assert set(I2[0].tolist()) == set(range(60)) | set(range(200_000, 200_040))            # the 60 planted rows + the 40 copies
+    for j in range(40):                                     # ties in row order
+        a, b = np.where(I2[0] == j)[0][0], np.where(I2[0] == 200_000 + j)[0][0]
+        assert a < b and D2[0, a] == D2[0, b]
+    idx.set_option("dense_seed", 1)
