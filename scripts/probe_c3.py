@@ -27,11 +27,10 @@ def reader():
             pass
 threading.Thread(target=reader, daemon=True).start()
 print(f"rows={n} d={d} nq={nq}", flush=True)
-for k, dbg, seed, slices, name in ((100, 0, 1, 0, "k=100 seeded, auto slices"), (100, 0, 1, 9, "k=100 seeded, 9 slices"),
-                                  (100, 0, 1, 18, "k=100 seeded, 18 slices"), (100, 0, 1, 37, "k=100 seeded, 37 slices"),
-                                  (100, 0, 1, 74, "k=100 seeded, 74 slices"), (100, 0, 0, 0, "k=100 unseeded (round 1)"),
-                                  (100, 0, 0, 37, "k=100 unseeded, 37 slices"), (100, 4, 0, 0, "k=100, epilogue off"),
-                                  (10, 0, 1, 0, "k=10"), (100, 0, 1, 0, "k=100 seeded, auto again")):
+for k, dbg, seed, slices, name in ((100, 0, 1, 0, "k=100: sample pass + early compaction"), (100, 8, 1, 0, "k=100: sample pass only"),
+                                  (100, 0, 0, 0, "k=100: early compaction only"), (100, 8, 0, 0, "k=100: neither (round 1)"),
+                                  (100, 4, 0, 0, "k=100, epilogue off"), (10, 0, 1, 0, "k=10"),
+                                  (100, 0, 1, 0, "k=100: both, again"), (100, 8, 0, 0, "k=100: neither, again")):
     idx.set_option("dense_slices", slices)
     D = torch.empty((nq, k), device="cuda"); I = torch.empty((nq, k), dtype=torch.int64, device="cuda")
     idx.set_option("debug", dbg)
@@ -49,7 +48,7 @@ for k, dbg, seed, slices, name in ((100, 0, 1, 0, "k=100 seeded, auto slices"), 
     ms = e0.elapsed_time(e1) / it
     clk = [s for (t, s, p) in samples if t0 + 0.5 < t < t1]
     pw = [p for (t, s, p) in samples if t0 + 0.5 < t < t1]
-    print(f"{name:32s} ms={ms:8.3f} TF={2*nq*n*d/ms/1e9:6.0f} sm_mhz={statistics.median(clk) if clk else None} "
+    print(f"{name:40s} ms={ms:8.3f} TF={2*nq*n*d/ms/1e9:6.0f} sm_mhz={statistics.median(clk) if clk else None} "
           f"power={statistics.median(pw) if pw else None}", flush=True)
 idx.set_option("debug", 0)
 smi.kill()

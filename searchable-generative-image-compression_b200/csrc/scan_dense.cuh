@@ -667,6 +667,14 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
       if (epi.gthr_q) epi.thr = gthr_read(p.gthr, q0 + t);
       for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
         const uint32_t as = tc & 1;
+        // Compact BEFORE taking the next accumulator, while this warp would only wait for it: a reservoir with
+        // fewer than 64 free slots is brought down to its k best now, so that (almost) no compaction happens while
+        // the warp holds a TMEM stage the MMA issuer is waiting to get back (ncu: the issuer spent 12 % of its time
+        // on acc_empty at k = 100).  A lane that still overflows inside a tile compacts there, as before.
+        if (warp_valid && !(p.debug & 8u)) {
+          const uint32_t soon = __ballot_sync(0xffffffffu, epi.cnt + 64u > epi.C && epi.cnt > epi.k);
+          if (soon) epi.compact(soon);
+        }
         ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t row0 = tile * BN;

@@ -333,8 +333,8 @@ static int grow_database(sgic_index* h, int64_t rows, cudaStream_t st, bool exac
     const size_t need = static_cast<size_t>(rows) * row_bytes;
     if (need > h->vmm_mapped) {
       size_t more = need - h->vmm_mapped;
-      // appends without a reserve(): grow by half of what is there (at least 256 MB) so that n small adds map O(log n) chunks
-      const size_t slack = exact ? more : std::max<size_t>(more, std::max<size_t>(h->vmm_mapped / 2, size_t(256) << 20));
+      // appends without a reserve(): grow by half of what is there (at least 32 MB) so that n small adds map O(log n) chunks
+      const size_t slack = exact ? more : std::max<size_t>(more, std::max<size_t>(h->vmm_mapped / 2, size_t(32) << 20));
       int rc = vmm_grow(h, slack);
       if (rc == 3 && slack > more) rc = vmm_grow(h, more);
       if (rc) {
@@ -705,10 +705,9 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     // 33 ms with the epilogue off).  Fewer, longer slices cut that work in proportion; the price is an item count
     // that no longer divides the CTAs.  Pick the slice count that minimises (rounds * units / items) * (1 + 0.008
     // slices): 16 query tiles on 74 pairs -> 9 slices (144 items, 2 rounds, 2.7 % idle) instead of 37.
-    // With the sample pass the lists start from a tight bound and their warm-up is cheap, so the short slices are
-    // back: the CTA pairs that share a slice re-align at every item boundary and meet in L2 (C3 with 9 long slices
-    // read 140-166 GB from DRAM for a 15 GB database, L2 hit rate 61 %).  "dense_slices" > 0 forces a slice count.
-    if (!tp && m_tiles * n_slices > n_units && seed_all == nullptr && h->opt_dense_slices == 0) {
+    // ("dense_slices" > 0 forces a slice count.  Measured on C3 with the sample pass on, one box: 9 slices 60.5 ms,
+    //  18: 61.5, 37: 62.6, 74: 64.6 — shorter slices do not pay although they re-align the pairs that share a slice.)
+    if (!tp && m_tiles * n_slices > n_units && h->opt_dense_slices == 0) {
       double best_cost = 1e30;
       uint32_t best = n_slices;
       for (uint32_t ns = 1; ns <= std::min(step, n_tiles); ++ns) {

@@ -95,6 +95,8 @@ struct FrontState {
   std::vector<cudaEvent_t> ev_done;              // per shard (created on its device): answer has landed at home
   std::vector<cudaEvent_t> ev_in;                // per shard: it has consumed the caller's device buffers
   cudaEvent_t ev_q = nullptr;                    // home device: the caller's stream has produced the queries
+  cudaEvent_t ev_merge = nullptr;                // home device: the previous search's merge has read the gather buffer
+  bool merged_once = false;
   std::vector<void*> seg_dev;                    // per shard: device copy of {l0[n], off[n]} (multi-segment only)
   std::vector<size_t> seg_dev_n;
   std::vector<uint8_t> seg_dirty;
@@ -218,6 +220,7 @@ static int front_shard_search(sgic_index* f, int g, int64_t nq, const float* q_p
   cudaStream_t st = s->stream;
   int rc = order_begin(s, st);
   if (rc) return rc;
+  if (S->merged_once) SGIC_CUDA(cudaStreamWaitEvent(st, S->ev_merge, 0));  // (long complete after a host-buffer search)
   const size_t qbytes = static_cast<size_t>(nq) * s->d * 4, cand = static_cast<size_t>(nq) * k;
   const float* q_dev = nullptr;
   if (q_pinned) {
@@ -301,7 +304,11 @@ static int front_merge(sgic_index* f, int64_t nq, int64_t k, float* dev_D, int64
     by_pos = 1;
   }
   S->stat_merge_launches++;
-  return sgic_merge_topk_dev(home->device, nq, G, k, Dl, Il, dev_D, dev_I, by_pos, st);
+  int rc = sgic_merge_topk_dev(home->device, nq, G, k, Dl, Il, dev_D, dev_I, by_pos, st);
+  if (rc) return rc;
+  SGIC_CUDA(cudaEventRecord(S->ev_merge, st));  // the next search's shards may not overwrite the slots before this
+  S->merged_once = true;
+  return 0;
 }
 
 static int front_ensure_gather(sgic_index* f, int64_t nq, int64_t k, float** D0, int64_t** I0) {
@@ -310,9 +317,13 @@ static int front_ensure_gather(sgic_index* f, int64_t nq, int64_t k, float** D0,
   const size_t i_off = (G * cand * 4 + 127) & ~size_t(127);
   const size_t need = i_off + G * cand * 8;
   if (need > S->gather_bytes) {
-    // nobody may still be writing into the old buffer: every shard stream is idle between searches (the
-    // previous search waited for all of them), the home stream is synchronised here
-    SGIC_CUDA(cudaStreamSynchronize(f->shards[0]->stream));
+    // nobody may still be writing into or merging out of the old buffer: a device-resident search returns without
+    // a synchronise, so drain every shard stream and everything on the home GPU before the buffer is replaced
+    for (sgic_index* s : f->shards) {
+      DeviceGuard dg(s->device);
+      SGIC_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    SGIC_CUDA(cudaDeviceSynchronize());
     int rc = ensure_buf(&S->gather, &S->gather_bytes, need, false);
     if (rc) return rc;
   }
@@ -623,6 +634,7 @@ static void front_destroy(sgic_index* f) {
     if (!f->shards.empty() && f->shards[0]) {
       DeviceGuard dg(f->shards[0]->device);
       if (S->ev_q) cudaEventDestroy(S->ev_q);
+      if (S->ev_merge) cudaEventDestroy(S->ev_merge);
       if (S->gather) cudaFree(S->gather);
       if (S->out_dev) cudaFree(S->out_dev);
       if (S->pin_q) cudaFreeHost(S->pin_q);
@@ -669,6 +681,7 @@ static int front_init(sgic_index* f, const std::vector<sgic_index*>& shards) {
   {
     DeviceGuard dg(home->device);
     SGIC_CUDA(cudaEventCreateWithFlags(&S->ev_q, cudaEventDisableTiming));
+    SGIC_CUDA(cudaEventCreateWithFlags(&S->ev_merge, cudaEventDisableTiming));
   }
   for (size_t g = 0; g < G; ++g) {
     sgic_index* s = shards[g];
