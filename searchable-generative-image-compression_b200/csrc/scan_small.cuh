@@ -19,6 +19,7 @@ namespace sgic {
 constexpr int kScanConsumerWarps = 8;
 constexpr int kScanThreads = (kScanConsumerWarps + 1) * 32;  // + producer warp
 constexpr int kScanMaxStages = 8;
+constexpr int kScanInlineQ = 1024;  // fp32 query elements that can ride in the kernel parameters (one query up to d = 1024)
 
 struct ScanSmallParams {
   const void* db;        // [n_rows][d] 16-bit, row-major
@@ -52,6 +53,10 @@ struct ScanSmallParams {
   // "trace" option: per CTA, %globaltimer at kernel entry / end of the scan / lists written / kernel exit
   // ([gridDim.x][4] u64, nullptr = off); scripts/probe_k3_trace.py turns it into the launch / ramp / tail picture
   unsigned long long* trace;
+  // q == nullptr: the (nq * d <= kScanInlineQ) query elements are HERE, in the kernel parameters — a host-buffer
+  // search of one or two queries then needs no H2D copy at all (a copy engine costs ~8 us of start-up latency, and
+  // 148 CTAs fetching 2 KB each from pinned host memory over PCIe were measured slower still: 32-byte reads)
+  float q_inline[kScanInlineQ];
 };
 
 // next pass's bound = key of the last answer slot of this pass (1 = "nothing left" if that slot is padding)
@@ -81,7 +86,7 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
 }
 
 template <typename T, int NQ, int CPL, int RB>
-__global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanSmallParams p) {
+__global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const __grid_constant__ ScanSmallParams p) {
   constexpr int W = kScanConsumerWarps;
   constexpr int R = W * RB;       // rows per tile
   constexpr int V = NQ * RB;      // partial sums per lane before the butterfly
@@ -150,8 +155,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const ScanS
     // query fragments, rounded to the storage dtype (same rounding the dense path applies)
     {
       const uint32_t n4 = (p.nq * p.d) >> 2;  // d is a multiple of 8
-      const float4* src = reinterpret_cast<const float4*>(p.q);
-      for (uint32_t i = tid; i < n4; i += W * 32) reinterpret_cast<float4*>(q_s)[i] = __ldg(src + i);
+      if (p.q != nullptr) {
+        const float4* src = reinterpret_cast<const float4*>(p.q);
+        for (uint32_t i = tid; i < n4; i += W * 32) reinterpret_cast<float4*>(q_s)[i] = __ldg(src + i);
+      } else {
+        const float4* src = reinterpret_cast<const float4*>(p.q_inline);  // constant bank (grid-constant parameter)
+        for (uint32_t i = tid; i < n4; i += W * 32) reinterpret_cast<float4*>(q_s)[i] = src[i];
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory");  // the consumer warps only: the producer is already streaming
     }
     uint32_t qf[NQ][CPL][4];

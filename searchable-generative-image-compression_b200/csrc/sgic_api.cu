@@ -138,6 +138,8 @@ struct sgic_index {
   cudaStream_t copy_stream = nullptr;
   void* qdev = nullptr;  // queries / outputs for the host-buffer search
   size_t qdev_bytes = 0;
+  void* qpin = nullptr;  // pinned staging of host queries on their way to qdev
+  size_t qpin_bytes = 0;
   void* odev = nullptr;
   size_t odev_bytes = 0;
   void* opin = nullptr;
@@ -938,8 +940,11 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
   return 0;
 }
 
+// host_q_inline != nullptr (and dev_q == nullptr): the queries are taken from host memory and travel in the kernel
+// parameters (nq * d <= kScanInlineQ)
 static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
-                             int64_t id_base, cudaStream_t st, const uint64_t* bound = nullptr);
+                             int64_t id_base, cudaStream_t st, const uint64_t* bound = nullptr,
+                             const float* host_q_inline = nullptr);
 
 // Smallest batch that goes to the tensor-core kernels ("dense_min_nq" overrides).  K3 owns lanes by 256-element
 // slabs of a row (8 elements per lane and chunk): at d = 512 / 768 / 1024 / 2048 every lane works and one query
@@ -1002,8 +1007,31 @@ static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_
   return search_small_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st);
 }
 
+// The same for queries in HOST memory.  One or two queries in the streaming regime ride in the kernel parameters (no
+// copy at all); anything else is staged through pinned memory (`pinned`: host_q already is pinned) and copied.
+static int search_hostq_impl(sgic_index* h, int64_t nq, const float* host_q, bool pinned, int64_t k, float* dev_D,
+                             int64_t* dev_I, int64_t id_base, cudaStream_t st) {
+  SGIC_REQUIRE(k >= 1, "k must be >= 1");
+  SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
+  if (nq == 0) return 0;
+  const bool small = h->ntotal == 0 || nq < auto_dense_min_nq(h);
+  if (small && k <= kMaxK && nq * h->d <= kScanInlineQ)
+    return search_small_impl(h, nq, nullptr, k, dev_D, dev_I, id_base, st, nullptr, host_q);
+  const size_t qbytes = static_cast<size_t>(nq) * h->d * 4;
+  int rc = ensure_buf(&h->qdev, &h->qdev_bytes, qbytes, false);
+  if (rc) return rc;
+  const void* src = host_q;
+  if (!pinned) {
+    if ((rc = ensure_buf(&h->qpin, &h->qpin_bytes, qbytes, true))) return rc;
+    std::memcpy(h->qpin, host_q, qbytes);
+    src = h->qpin;
+  }
+  SGIC_CUDA(cudaMemcpyAsync(h->qdev, src, qbytes, cudaMemcpyHostToDevice, st));
+  return search_dev_impl(h, nq, static_cast<const float*>(h->qdev), k, dev_D, dev_I, id_base, st);
+}
+
 static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
-                             int64_t id_base, cudaStream_t st, const uint64_t* bound) {
+                             int64_t id_base, cudaStream_t st, const uint64_t* bound, const float* host_q_inline) {
   SGIC_REQUIRE(k >= 1, "k must be >= 1");
   SGIC_REQUIRE(k <= kMaxK, "k > 1024 is not supported by this build");
   SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
@@ -1060,7 +1088,12 @@ static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     const uint32_t nq_here = static_cast<uint32_t>(std::min<int64_t>(NQ, nq - q0));
     ScanSmallParams p;
     p.db = h->db;
-    p.q = dev_q + static_cast<size_t>(q0) * h->d;
+    if (dev_q != nullptr) {
+      p.q = dev_q + static_cast<size_t>(q0) * h->d;
+    } else {
+      p.q = nullptr;
+      std::memcpy(p.q_inline, host_q_inline + static_cast<size_t>(q0) * h->d, static_cast<size_t>(nq_here) * h->d * 4);
+    }
     p.partial = static_cast<uint64_t*>(h->ws);
     p.n_rows = n_rows;
     p.d = static_cast<uint32_t>(h->d);
@@ -1308,6 +1341,7 @@ int sgic_index_destroy(sgic_index* h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->odev) cudaFree(h->odev);
   if (h->opin) cudaFreeHost(h->opin);
+  if (h->qpin) cudaFreeHost(h->qpin);
   if (h->vmm_base) vmm_destroy(h);
   else if (h->db) cudaFree(h->db);
   if (h->t0) cudaEventDestroy(h->t0);
@@ -1815,31 +1849,22 @@ int sgic_index_search(sgic_index* h, int64_t nq, const float* host_q, int64_t k,
   if (rc) return rc;
   if ((rc = order_begin(h, h->stream))) return rc;
   if ((rc = order_end(h, h->stream))) return rc;
-  // Small transfers skip the copy engines (their start-up latency, ~8 us each way, is on the critical path of a
-  // short search): the kernels read the queries out of the pinned host buffer themselves (K3 stages them once per
-  // CTA, the tensor-core path converts them in one pass) and the final writer stores the answer straight into it.
-  // Large ones go host -> pinned -> device and back through cudaMemcpyAsync.
-  const bool zc_in = qbytes <= kZeroCopyBytes, zc_out = dbytes + ibytes <= kZeroCopyBytes;
-  if (zc_in && zc_out) {  // two halves of one pinned buffer: answer first, queries behind it
-    const size_t q_off = (dbytes + ibytes + 255) & ~size_t(255);
-    if ((rc = ensure_buf(&h->opin, &h->opin_bytes, q_off + qbytes, true))) return rc;
-    float* pq = reinterpret_cast<float*>(static_cast<uint8_t*>(h->opin) + q_off);
-    std::memcpy(pq, host_q, qbytes);
+  // The answer of a small search is stored by the final writer (K3's last CTA / the merge kernel) straight into
+  // pinned host memory — no D2H copy engine transfer (~8 us of start-up latency) behind the kernel; large answers
+  // come back through cudaMemcpyAsync.  The queries go in through search_hostq_impl (kernel parameters or H2D).
+  if (dbytes + ibytes <= kZeroCopyBytes) {
     int64_t* pI = reinterpret_cast<int64_t*>(h->opin);
     float* pD = reinterpret_cast<float*>(static_cast<uint8_t*>(h->opin) + ibytes);
-    rc = search_dev_impl(h, nq, pq, k, pD, pI, 0, h->stream);
+    rc = search_hostq_impl(h, nq, host_q, false, k, pD, pI, 0, h->stream);
     if (rc) return rc;
     SGIC_CUDA(cudaStreamSynchronize(h->stream));
     std::memcpy(host_I, pI, ibytes);
     std::memcpy(host_D, pD, dbytes);
     return 0;
   }
-  // queries: host -> pinned -> device; results: device -> pinned -> host
-  std::memcpy(h->opin, host_q, qbytes);
-  SGIC_CUDA(cudaMemcpyAsync(h->qdev, h->opin, qbytes, cudaMemcpyHostToDevice, h->stream));
   int64_t* dI = reinterpret_cast<int64_t*>(h->odev);
   float* dD = reinterpret_cast<float*>(static_cast<uint8_t*>(h->odev) + ibytes);
-  rc = search_dev_impl(h, nq, static_cast<const float*>(h->qdev), k, dD, dI, 0, h->stream);
+  rc = search_hostq_impl(h, nq, host_q, false, k, dD, dI, 0, h->stream);
   if (rc) return rc;
   SGIC_CUDA(cudaMemcpyAsync(h->opin, h->odev, dbytes + ibytes, cudaMemcpyDeviceToHost, h->stream));
   SGIC_CUDA(cudaStreamSynchronize(h->stream));
@@ -2039,15 +2064,11 @@ int sgic_xchg_search(sgic_xchg* x, sgic_index* h, int64_t nq, const float* host_
   uint8_t* o = static_cast<uint8_t*>(h->odev);
   int64_t* lI = reinterpret_cast<int64_t*>(o + half);          // this rank's local answer
   float* lD = reinterpret_cast<float*>(o + half + cand * 8);
-  if (qbytes <= kZeroCopyBytes && cand * 12 <= kZeroCopyBytes) {
-    // small step: queries read in place from pinned host memory, merged answer stored into it by the merge kernel
-    const size_t q_off = (cand * 12 + 255) & ~size_t(255);
-    if ((rc = ensure_buf(&h->opin, &h->opin_bytes, q_off + qbytes, true))) return rc;
-    float* pq = reinterpret_cast<float*>(static_cast<uint8_t*>(h->opin) + q_off);
-    std::memcpy(pq, host_q, qbytes);
+  if (cand * 12 <= kZeroCopyBytes) {
+    // small step: the merged answer is stored into pinned host memory by the merge kernel itself (no D2H copy)
     int64_t* pI = reinterpret_cast<int64_t*>(h->opin);
     float* pD = reinterpret_cast<float*>(static_cast<uint8_t*>(h->opin) + cand * 8);
-    rc = search_dev_impl(h, nq, pq, k, lD, lI, id_base, h->stream);
+    rc = search_hostq_impl(h, nq, host_q, false, k, lD, lI, id_base, h->stream);
     if (rc) return rc;
     rc = sgic_xchg_merge_dev(x, nq, k, lD, lI, pD, pI, tie_by_position, h->stream);
     if (rc) return rc;
@@ -2056,11 +2077,9 @@ int sgic_xchg_search(sgic_xchg* x, sgic_index* h, int64_t nq, const float* host_
     std::memcpy(host_D, pD, cand * 4);
     return 0;
   }
-  std::memcpy(h->opin, host_q, qbytes);
-  SGIC_CUDA(cudaMemcpyAsync(h->qdev, h->opin, qbytes, cudaMemcpyHostToDevice, h->stream));
   int64_t* mI = reinterpret_cast<int64_t*>(o);                 // merged answer first: ids then scores, contiguous
   float* mD = reinterpret_cast<float*>(o + cand * 8);
-  rc = search_dev_impl(h, nq, static_cast<const float*>(h->qdev), k, lD, lI, id_base, h->stream);
+  rc = search_hostq_impl(h, nq, host_q, false, k, lD, lI, id_base, h->stream);
   if (rc) return rc;
   rc = sgic_xchg_merge_dev(x, nq, k, lD, lI, mD, mI, tie_by_position, h->stream);
   if (rc) return rc;

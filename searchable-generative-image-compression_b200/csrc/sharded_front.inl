@@ -224,13 +224,8 @@ static int front_shard_search(sgic_index* f, int g, int64_t nq, const float* q_p
   const size_t qbytes = static_cast<size_t>(nq) * s->d * 4, cand = static_cast<size_t>(nq) * k;
   const float* q_dev = nullptr;
   if (q_pinned) {
-    if (qbytes <= kZeroCopyBytes) {
-      q_dev = q_pinned;  // the kernels read the pinned host buffer themselves: no copy engine on the critical path
-    } else {
-      if ((rc = ensure_buf(&s->qdev, &s->qdev_bytes, qbytes, false))) return rc;
-      SGIC_CUDA(cudaMemcpyAsync(s->qdev, q_pinned, qbytes, cudaMemcpyHostToDevice, st));
-      q_dev = static_cast<const float*>(s->qdev);
-    }
+    // host queries: one or two ride in the kernel parameters of the streaming scan, larger batches are copied from
+    // the (shared, pinned) staging buffer by this GPU's copy engine — search_hostq_impl decides
   } else {
     SGIC_CUDA(cudaStreamWaitEvent(st, S->ev_q, 0));
     if (s->device == home->device || (S->direct[gi] && qbytes <= kZeroCopyBytes)) {
@@ -247,14 +242,16 @@ static int front_shard_search(sgic_index* f, int g, int64_t nq, const float* q_p
   const int64_t id_base = segs.size() == 1 ? segs[0].g0 - segs[0].l0 : 0;
   if (!multi && S->direct[gi]) {
     // the shard's final writer stores straight into the home GPU's gather slot
-    rc = search_dev_impl(s, nq, q_dev, k, dstD, dstI, id_base, st);
+    rc = q_pinned ? search_hostq_impl(s, nq, q_pinned, true, k, dstD, dstI, id_base, st)
+                  : search_dev_impl(s, nq, q_dev, k, dstD, dstI, id_base, st);
     if (rc) return rc;
   } else {
     const size_t half = (cand * 12 + 15) & ~size_t(15);  // local answer | remapped answer, each ids (8 B) then scores
     if ((rc = ensure_buf(&s->odev, &s->odev_bytes, 2 * half, false))) return rc;
     int64_t* lI = reinterpret_cast<int64_t*>(s->odev);
     float* lD = reinterpret_cast<float*>(static_cast<uint8_t*>(s->odev) + cand * 8);
-    rc = search_dev_impl(s, nq, q_dev, k, lD, lI, id_base, st);
+    rc = q_pinned ? search_hostq_impl(s, nq, q_pinned, true, k, lD, lI, id_base, st)
+                  : search_dev_impl(s, nq, q_dev, k, lD, lI, id_base, st);
     if (rc) return rc;
     float* oD = lD;
     int64_t* oI = lI;
