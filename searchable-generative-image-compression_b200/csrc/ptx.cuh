@@ -56,6 +56,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// The same for warps that have slack (consumers of an HBM-bound stream, epilogue warps behind the tensor pipe):
+// a failed try sleeps `ns` nanoseconds instead of polling again at once.  On a part that sits at its power cap in
+// every regime the issue slots a spinning warp burns are clock taken from everybody else.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  while (!mbar_try_wait(bar, parity)) {
+    if (ns) __nanosleep(ns);
+  }
+}
 
 // ---------------------------------------------------------------- L2 policies
 __device__ __forceinline__ uint64_t policy_evict_first() {

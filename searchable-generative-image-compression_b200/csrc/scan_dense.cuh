@@ -67,6 +67,7 @@ struct DenseParams {
   uint32_t idesc;          // UMMA instruction descriptor
   uint32_t db_evict_first; // single query tile: the database is streamed once -> evict_first
   uint32_t debug;          // timing experiments only (wrong results): 1 skip A loads, 2 skip B loads, 4 skip epilogue
+  uint32_t epi_wait_ns;    // epilogue warps sleep this long after a failed try on acc_full (0: poll)
 };
 
 // shared memory of the epilogue: thread-private lists (k <= 32); the reservoirs of larger k live in L2
@@ -636,7 +637,7 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
       else epi.load(p.partial, q0 + t, p.nq, p.n_lists, slot);
       for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
         const uint32_t as = tc & 1;
-        ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
+        ptx::mbar_wait_relaxed(&acc_full[as], (tc >> 1) & 1, p.epi_wait_ns);
         ptx::tc_fence_after();
         const uint32_t row0 = tile * BN;
         const uint32_t n_valid = min(static_cast<uint32_t>(BN), p.n_rows - row0);
@@ -675,7 +676,7 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams& p, uint32_t un
           const uint32_t soon = __ballot_sync(0xffffffffu, epi.cnt + 64u > epi.C && epi.cnt > epi.k);
           if (soon) epi.compact(soon);
         }
-        ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
+        ptx::mbar_wait_relaxed(&acc_full[as], (tc >> 1) & 1, p.epi_wait_ns);
         ptx::tc_fence_after();
         const uint32_t row0 = tile * BN;
         const uint32_t n_valid = min(static_cast<uint32_t>(BN), p.n_rows - row0);
@@ -836,6 +837,7 @@ struct DenseTParams {
                       // 8..15 of an accumulator are then never written; their thresholds are +inf)
   uint32_t n_slices, tiles_per_slice, n_tiles, n_lists;
   uint32_t kc, n_stages, idesc, db_evict_first, debug;
+  uint32_t epi_wait_ns;  // epilogue warps sleep this long after a failed try on acc_full (0: poll)
 };
 
 constexpr uint32_t kDtStageBytes = 256u * kDenseBK * 2u;  // 32 KB: 256 database rows x 128 B
@@ -970,7 +972,7 @@ scan_dense_t_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint32_t t0 = item * p.tiles_per_slice, t1 = min(t0 + p.tiles_per_slice, p.n_tiles);
       for (uint32_t tile = t0; tile < t1; ++tile, ++tc) {
         const uint32_t as = tc & 1;
-        ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
+        ptx::mbar_wait_relaxed(&acc_full[as], (tc >> 1) & 1, p.epi_wait_ns);
         ptx::tc_fence_after();
         if (!(p.debug & 4u)) {
 #pragma unroll 1
@@ -1308,6 +1310,7 @@ struct DenseBParams {
   uint32_t n_tiles;    // database tiles of 256 rows; pair u owns tiles u, u + n_pairs, ...
   uint32_t n_lists;
   uint32_t kc, idesc, debug;
+  uint32_t epi_wait_ns;  // epilogue warps sleep this long after a failed try on acc_full (0: poll)
 };
 
 constexpr int kD2bSlots = 8;   // resident database chunk slots (d <= 512)
@@ -1469,7 +1472,7 @@ scan_dense2b_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const bool q_valid = q0 + t < p.nq;
         const bool warp_valid = q0 + row0w < p.nq;
         const uint32_t as = tc & 1;
-        ptx::mbar_wait(&acc_full[as], (tc >> 1) & 1);
+        ptx::mbar_wait_relaxed(&acc_full[as], (tc >> 1) & 1, p.epi_wait_ns);
         ptx::tc_fence_after();
         if (warp_valid && !(p.debug & 4u)) {
           epi.res_warp = res_cta + (static_cast<size_t>(m) * kDenseBM + row0w) * p.res_cap;

@@ -34,6 +34,7 @@ struct ScanSmallParams {
   uint32_t n_stages;
   uint32_t stage_bytes;  // R * d * 2 rounded up to 128
   uint32_t evict_first;  // L2 policy for the database stream
+  uint32_t wait_ns;      // consumers sleep this long after a failed mbarrier try (0: poll)
   // fused final merge: the last CTA to finish merges every CTA's list and writes the answer
   uint32_t fused;        // 0: partial lists only (merge_keys_kernel follows)
   uint32_t* counter;     // zero on entry, reset to zero by the last CTA
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const __gri
 
     for (uint32_t it = 0;; ++it) {
       const uint32_t s = it % p.n_stages, use = it / p.n_stages;
-      ptx::mbar_wait(&full_bar[s], use & 1);
+      ptx::mbar_wait_relaxed(&full_bar[s], use & 1, p.wait_ns);
       const uint32_t tile = stage_tile[s];
       if (tile == kEndOfStream) break;
       const uint32_t row0 = tile * R;

@@ -169,7 +169,7 @@ struct sgic_index {
   int64_t shard_row_start = 0, shard_total_rows = -1;
   int shard_id = 0, shard_count = 1;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1, opt_trace = 0, opt_steal = 1, opt_t_n8 = 1, opt_t_max_nq = 88, opt_dense_seed = 1, opt_dense_slices = 0;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1, opt_trace = 0, opt_steal = 1, opt_t_n8 = 1, opt_t_max_nq = 88, opt_dense_seed = 1, opt_dense_slices = 0, opt_epi_wait_ns = 0, opt_scan_wait_ns = 0;
   int64_t stat_ingest_h2d_ns = 0, stat_ingest_k0_ns = 0, stat_ingest_k1_ns = 0;
   int64_t stat_ingest_parse_ns = 0, stat_ingest_pack_ns = 0, stat_ingest_gpu_ns = 0;
   int64_t stat_zl_device_frames = 0, stat_zl_host_rows = 0, stat_zl_fallback_slabs = 0;
@@ -802,6 +802,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
         bp.kc = (static_cast<uint32_t>(h->d) + kDenseBK - 1) / kDenseBK;
         bp.idesc = ptx::umma_idesc_f16(256, kDenseBN, h->dtype == SGIC_BF16 ? 1u : 0u);
         bp.debug = static_cast<uint32_t>(h->opt_debug);
+        bp.epi_wait_ns = static_cast<uint32_t>(h->opt_epi_wait_ns);
         static bool b_configured[64] = {false};
         if (!b_configured[h->device & 63]) {
           SGIC_CUDA(cudaFuncSetAttribute(scan_dense2b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -881,6 +882,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.idesc = ptx::umma_idesc_f16(q_tile, kDenseBN, h->dtype == SGIC_BF16 ? 1u : 0u);
     p.db_evict_first = (m_tiles == 1 && h->opt_evict_first) ? 1u : 0u;
     p.debug = static_cast<uint32_t>(h->opt_debug);
+    p.epi_wait_ns = static_cast<uint32_t>(h->opt_epi_wait_ns);
     h->ws_counter = nullptr;  // this launch overwrites the workspace: K3 must re-zero its "CTAs done" counter
     // empty lists where a CTA resumes its own slot; the by-slice schedule writes every list in full
     if (transposed || !by_slice) SGIC_CUDA(cudaMemsetAsync(h->ws, 0, partial_bytes, st));
@@ -906,6 +908,7 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
       tp_.idesc = ptx::umma_idesc_f16(128, n_mma, h->dtype == SGIC_BF16 ? 1u : 0u);
       tp_.db_evict_first = p.db_evict_first;
       tp_.debug = p.debug;
+      tp_.epi_wait_ns = p.epi_wait_ns;
       static bool t_configured[64] = {false};
       if (!t_configured[h->device & 63]) {
         SGIC_CUDA(cudaFuncSetAttribute(scan_dense_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1104,6 +1107,7 @@ static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.n_stages = stages;
     p.stage_bytes = stage_bytes;
     p.evict_first = h->opt_evict_first ? 1u : 0u;
+    p.wait_ns = static_cast<uint32_t>(h->opt_scan_wait_ns);
     p.fused = fused ? 1u : 0u;
     p.counter = counter;
     // equal round-robin shares for the first 7/8 of the tiles, the rest is claimed dynamically ("steal" = 0: all static)
@@ -2544,6 +2548,8 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "steal") h->opt_steal = value ? 1 : 0;
   else if (n == "t_n8") h->opt_t_n8 = value ? 1 : 0;
   else if (n == "t_max_nq") h->opt_t_max_nq = std::max<int64_t>(0, value);
+  else if (n == "epi_wait_ns") h->opt_epi_wait_ns = std::max<int64_t>(0, std::min<int64_t>(10000, value));
+  else if (n == "scan_wait_ns") h->opt_scan_wait_ns = std::max<int64_t>(0, std::min<int64_t>(10000, value));
   else if (n == "dense_slices") h->opt_dense_slices = std::max<int64_t>(0, value);
   else if (n == "dense_seed") h->opt_dense_seed = std::max<int64_t>(0, std::min<int64_t>(2, value));  // 2: force (tests)
   else if (n == "trace") h->opt_trace = value;  // device address of a [grid][4] u64 buffer (0 = off), see scan_small.cuh
