@@ -1311,25 +1311,20 @@ struct DenseBParams {
   uint32_t n_lists;
   uint32_t kc, idesc, debug;
   uint32_t epi_wait_ns;  // epilogue warps sleep this long after a failed try on acc_full (0: poll)
-  uint32_t n_stages;     // depth of the query chunk ring (kD2bStages .. kD2bMaxStages)
 };
 
 constexpr int kD2bSlots = 8;   // resident database chunk slots (d <= 512)
-constexpr int kD2bStages = 4;     // query chunk ring: at least this deep ...
-constexpr int kD2bMaxStages = 8;  // ... and as deep as shared memory allows (DenseBParams::n_stages): ncu showed the MMA
-                                  // issuer waiting 31 % of its time for query chunks behind a 4-stage ring (1.4 us of cover
-                                  // against an L2 latency of about 1 us under load)
+constexpr int kD2bStages = 4;  // query chunk ring
 
-__host__ __device__ __forceinline__ size_t dense_b_smem_bytes(uint32_t m_tiles, uint32_t n_stages = kD2bStages) {
-  return 1024 + static_cast<size_t>(kD2bSlots + n_stages) * (kDenseBM * kDenseBK * 2) +
-         static_cast<size_t>(m_tiles) * kDenseBM * 8 + 512;
+__host__ __device__ __forceinline__ size_t dense_b_smem_bytes(uint32_t m_tiles) {
+  return 1024 + static_cast<size_t>(kD2bSlots + kD2bStages) * (kDenseBM * kDenseBK * 2) +
+         static_cast<size_t>(m_tiles) * kDenseBM * 8 + 256;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDenseThreads, 1)
 scan_dense2b_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
                     const DenseBParams p) {
-  constexpr int BN = 256, NB = kD2bSlots;
-  const uint32_t NS = p.n_stages;
+  constexpr int BN = 256, NS = kD2bStages, NB = kD2bSlots;
   extern __shared__ uint8_t dense_smem_raw[];
   uint8_t* smem = dense_smem_raw + ((1024u - (ptx::smem_u32(dense_smem_raw) & 1023u)) & 1023u);
   uint8_t* b_res = smem;                                            // NB slots of 16 KB
@@ -1353,7 +1348,7 @@ scan_dense2b_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_q);
     ptx::prefetch_tmap(&tm_db);
-    for (uint32_t s = 0; s < NS; ++s) {
+    for (int s = 0; s < NS; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
     }
@@ -1406,7 +1401,7 @@ scan_dense2b_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             ptx2::tma_load_2d_2sm(stages + static_cast<size_t>(s) * kD2HalfBytes, &tm_q,
                                   static_cast<int32_t>(kc * kDenseBK), q_row, &full[s], pol_q);
             // database chunks whose slot saw its last use at a step <= g - NS can be replaced now
-            while (nb < total_b && g >= NS) {
+            while (nb < total_b && g >= static_cast<uint32_t>(NS)) {
               const uint32_t prev = nb - NB;
               const uint32_t last_use = ((prev / KC) * MT + (MT - 1)) * KC + prev % KC;
               if (last_use + NS > g) break;

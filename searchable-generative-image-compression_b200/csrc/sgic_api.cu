@@ -771,10 +771,6 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
       const size_t db_mb = (static_cast<size_t>(n_rows) * h->d * 2) >> 20;
       const bool eligible = pairs && h->d <= kD2MaxKc * kDenseBK && m_tiles >= 2 &&
                             dense_b_smem_bytes(m_tiles) <= kSmemBudget && ws_b <= (size_t(1) << 30);
-      // query chunk ring: as deep as shared memory allows ("stages" caps it for experiments)
-      uint32_t b_stages = kD2bStages;
-      while (b_stages < kD2bMaxStages && dense_b_smem_bytes(m_tiles, b_stages + 1) <= kSmemBudget) ++b_stages;
-      if (h->opt_stages >= kD2bStages) b_stages = std::min<uint32_t>(b_stages, static_cast<uint32_t>(h->opt_stages));
       if (eligible && (h->opt_dense_mode == 4 ||
                        (h->opt_dense_mode == 0 && db_mb >= static_cast<size_t>(h->opt_dense_b_min_mb)))) {
         const size_t pbytes = static_cast<size_t>(nqb) * units_b * static_cast<size_t>(k) * 8;
@@ -807,7 +803,6 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
         bp.idesc = ptx::umma_idesc_f16(256, kDenseBN, h->dtype == SGIC_BF16 ? 1u : 0u);
         bp.debug = static_cast<uint32_t>(h->opt_debug);
         bp.epi_wait_ns = static_cast<uint32_t>(h->opt_epi_wait_ns);
-        bp.n_stages = b_stages;
         static bool b_configured[64] = {false};
         if (!b_configured[h->device & 63]) {
           SGIC_CUDA(cudaFuncSetAttribute(scan_dense2b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -815,12 +810,12 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
           b_configured[h->device & 63] = true;
         }
         if (q0 == 0 && (rc = ring_mark(h, true, st))) return rc;
-        scan_dense2b_kernel<<<units_b * 2, kDenseThreads, dense_b_smem_bytes(m_tiles, b_stages), st>>>(tm_qb, tm_db, bp);
+        scan_dense2b_kernel<<<units_b * 2, kDenseThreads, dense_b_smem_bytes(m_tiles), st>>>(tm_qb, tm_db, bp);
         h->stat_launches++;
         SGIC_CUDA(cudaGetLastError());
         if (q0 == 0 && (rc = ring_mark(h, false, st))) return rc;
         h->stat_last_grid = units_b * 2;
-        h->stat_last_stages = b_stages;
+        h->stat_last_stages = kD2bStages;
         h->stat_last_kernel = 5;
         if (h->opt_timing == 1 && q0 == 0) SGIC_CUDA(cudaEventRecord(h->tm, st));
         rc = launch_merge_keys(h, static_cast<const uint64_t*>(h->ws), nqb, units_b, static_cast<uint32_t>(k),
