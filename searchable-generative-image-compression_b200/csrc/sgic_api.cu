@@ -2466,28 +2466,123 @@ int sgic_index_read(const char* path, int dtype, int device, int flags, sgic_ind
     return 3;
   }
   sgic_index* h = nullptr;
+  const bool dbg_load = std::getenv("SGIC_DEBUG_LOAD") != nullptr;
+  const auto t_load0 = std::chrono::steady_clock::now();
+  auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_load0).count(); };
   int rc = sgic_index_create(hd.d, dtype, device, hd.ntotal, flags, &h);
   if (rc) {
     std::fclose(f);
     return rc;
   }
-  const int64_t chunk = std::max<int64_t>(1, static_cast<int64_t>((64u << 20) / (hd.d * 4)));
-  std::vector<float> buf(static_cast<size_t>(std::min<int64_t>(chunk, std::max<int64_t>(hd.ntotal, 1))) * hd.d);
-  for (int64_t i0 = 0; i0 < hd.ntotal; i0 += chunk) {
-    const int64_t rows = std::min(chunk, hd.ntotal - i0);
-    const size_t cnt = static_cast<size_t>(rows) * hd.d;
-    if (std::fread(buf.data(), sizeof(float), cnt, f) != cnt) {
-      std::fclose(f);
-      sgic_index_destroy(h);
-      set_error(std::string("read error in ") + path + ": file shorter than its header says");
-      return 3;
+  if (dbg_load) std::fprintf(stderr, "[load] index created + %lld rows mapped: %.1f ms\n", static_cast<long long>(hd.ntotal), since());
+  // The fp32 rows come in through several readers (the reference re-reads this file in every query process,
+  // src/search.py:69,76): reader t preads chunk c = t, t + T, ... into one of its two pinned buffers, copies it to
+  // its own device staging buffer and packs it (K2) into the database rows the chunk stands for — all on the reader's
+  // stream, so the pread of one chunk overlaps the H2D copy + pack of the previous one.  The host copy that makes
+  // write_index bit-exact (SGIC_RETAIN_F32) is filled by the same readers.
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    const size_t row_bytes = static_cast<size_t>(hd.d) * 4;
+    const int64_t rows_per_chunk = std::max<int64_t>(1, static_cast<int64_t>((size_t(4) << 20) / row_bytes));
+    const int64_t n_chunks = (hd.ntotal + rows_per_chunk - 1) / rows_per_chunk;
+    const int T = static_cast<int>(std::min<int64_t>(4, std::max<int64_t>(1, n_chunks / 2)));
+    const bool retain = h->retain_ok;
+    bool retain_alloc = false;
+    if (retain) {
+      try {
+        h->retained.resize(static_cast<size_t>(hd.ntotal) * hd.d);
+        retain_alloc = true;
+      } catch (const std::bad_alloc&) {
+        h->retained.clear();
+        h->retain_ok = false;
+      }
     }
-    rc = sgic_index_add_f32(h, rows, buf.data());
-    if (rc) {
+    const int fd = fileno(f);
+    const size_t chunk_bytes = static_cast<size_t>(rows_per_chunk) * row_bytes;
+    std::vector<int> trc(static_cast<size_t>(T), 0);
+    std::vector<std::thread> readers;
+    const int dev = h->device;
+    for (int t = 0; t < T; ++t)
+      readers.emplace_back([&, t] {
+        cudaSetDevice(dev);
+        int& rc_t = trc[static_cast<size_t>(t)];
+        void* pin[2] = {nullptr, nullptr};
+        void* stage[2] = {nullptr, nullptr};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        cudaStream_t st = nullptr;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) rc_t = 2;
+        for (int b = 0; b < 2 && !rc_t; ++b)
+          if (cudaMallocHost(&pin[b], chunk_bytes) != cudaSuccess || cudaMalloc(&stage[b], chunk_bytes) != cudaSuccess ||
+              cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming) != cudaSuccess)
+            rc_t = 2;
+        if (dbg_load && t == 0) std::fprintf(stderr, "[load] reader 0 has its buffers: %.1f ms\n", since());
+        int b = 0;
+        for (int64_t c = t; c < n_chunks && !rc_t; c += T, b ^= 1) {
+          const int64_t row0 = c * rows_per_chunk, rows = std::min(rows_per_chunk, hd.ntotal - row0);
+          const size_t n = static_cast<size_t>(rows) * row_bytes;
+          if (cudaEventSynchronize(ev[b]) != cudaSuccess) {
+            rc_t = 2;
+            break;
+          }
+          size_t got = 0;
+          while (got < n) {
+            const ssize_t r = pread(fd, static_cast<uint8_t*>(pin[b]) + got, n - got,
+                                    static_cast<off_t>(sizeof(IxfiHeader) + static_cast<size_t>(row0) * row_bytes + got));
+            if (r <= 0) break;
+            got += static_cast<size_t>(r);
+          }
+          if (got != n) {
+            rc_t = 3;
+            break;
+          }
+          if (retain_alloc) std::memcpy(h->retained.data() + static_cast<size_t>(row0) * hd.d, pin[b], n);
+          if (cudaMemcpyAsync(stage[b], pin[b], n, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            rc_t = 2;
+            break;
+          }
+          // K2 on this reader's stream (launch_pack_f32 counts launches on the index: not from several threads)
+          const size_t n8 = static_cast<size_t>(rows) * hd.d / 8;
+          void* dst = static_cast<uint8_t*>(h->db) + static_cast<size_t>(row0) * hd.d * 2;
+          const unsigned grid = grid_for(n8, 256, h->sm_count);
+          if (h->dtype == SGIC_F16) pack_f32_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const float*>(stage[b]), dst, n8);
+          else pack_f32_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const float*>(stage[b]), dst, n8);
+          if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ev[b], st) != cudaSuccess) rc_t = 2;
+        }
+        if (st) cudaStreamSynchronize(st);
+        if (dbg_load && t == 0) std::fprintf(stderr, "[load] reader 0 drained: %.1f ms\n", since());
+        for (int i = 0; i < 2; ++i) {
+          if (ev[i]) cudaEventDestroy(ev[i]);
+          if (pin[i]) cudaFreeHost(pin[i]);
+          if (stage[i]) cudaFree(stage[i]);
+        }
+        if (st) cudaStreamDestroy(st);
+      });
+    for (auto& th : readers) th.join();
+    if (dbg_load) std::fprintf(stderr, "[load] %d readers done: %.1f ms\n", T, since());
+    (void)cudaGetLastError();
+    int bad = 0;
+    for (int t = 0; t < T; ++t) bad = std::max(bad, trc[static_cast<size_t>(t)]);
+    if (bad) {
       std::fclose(f);
-      sgic_index_destroy(h);
-      return rc;
+      // (unlock before destroying: the guard goes out of scope with this block — destroy below)
+      h->ntotal = 0;
     }
+    if (!bad) {
+      h->ntotal = hd.ntotal;
+      h->stat_launches += n_chunks;
+      drop_codes(h);
+    }
+    if (bad) {
+      // fall through to the error return outside the lock
+      rc = bad;
+    }
+  }
+  if (rc) {
+    sgic_index_destroy(h);
+    if (rc == 3) set_error(std::string("read error in ") + path + ": file shorter than its header says");
+    else set_error(std::string("loading ") + path + " onto the device failed");
+    return rc;
   }
   std::fclose(f);
   *out = h;
