@@ -181,20 +181,24 @@ namespace sgic {
 static size_t elt_rows_bytes(const sgic_index* h, int64_t rows) { return static_cast<size_t>(rows) * h->d * 2; }
 
 // Stream hand-over (call with the index mutex held).  order_begin(st): if the previous call enqueued on another
-// stream, `st` waits for it — for the index's own stream the event is recorded now (everything enqueued there so
-// far), for a caller's stream it was recorded right after that call's last enqueue (the handle may be gone by
-// now).  order_end(st): remember `st`; a foreign stream gets its event immediately.  Same stream again: no cost.
+// stream, an event is recorded on THAT stream now (everything enqueued there so far, which includes our work) and
+// `st` waits for it.  The previous stream may be a caller's stream that no longer exists: then the whole device is
+// synchronised instead, which is always safe.  order_end(st) only remembers the stream — calls that keep using one
+// stream (the common case: a search loop) pay nothing.
 static int order_begin(sgic_index* h, cudaStream_t st) {
   if (h->last_stream_valid && h->last_stream != st) {
-    if (h->last_stream == h->stream) SGIC_CUDA(cudaEventRecord(h->ev_order, h->stream));
-    SGIC_CUDA(cudaStreamWaitEvent(st, h->ev_order, 0));
+    if (cudaEventRecord(h->ev_order, h->last_stream) == cudaSuccess) {
+      SGIC_CUDA(cudaStreamWaitEvent(st, h->ev_order, 0));
+    } else {
+      (void)cudaGetLastError();
+      SGIC_CUDA(cudaDeviceSynchronize());
+    }
   }
   return 0;
 }
 static int order_end(sgic_index* h, cudaStream_t st) {
   h->last_stream = st;
   h->last_stream_valid = true;
-  if (st != h->stream) SGIC_CUDA(cudaEventRecord(h->ev_order, st));
   return 0;
 }
 
