@@ -712,6 +712,7 @@ def load_rate_extra(faiss, fill_index_random, dev, rows=5_000_000, d=512):
         t0 = time.perf_counter()
         faiss.write_shard(idx, str(tmp / "a.sgi2"))
         out["sgi2_write_s"] = time.perf_counter() - t0
+        os.sync()   # the write-back of 5 GB of dirty pages must not compete with the reads that are timed next
         t0 = time.perf_counter()
         back = faiss.read_index(str(tmp / "a.sgi2"), device=dev.index, retain_fp32=False)
         dt = time.perf_counter() - t0
@@ -725,6 +726,7 @@ def load_rate_extra(faiss, fill_index_random, dev, rows=5_000_000, d=512):
         sub.add(idx.reconstruct_n(0, small))
         faiss.write_index(sub, str(tmp / "a.index"))
         sub.close()
+        os.sync()
         t0 = time.perf_counter()
         back = faiss.read_index(str(tmp / "a.index"), device=dev.index, retain_fp32=False)
         dt = time.perf_counter() - t0
