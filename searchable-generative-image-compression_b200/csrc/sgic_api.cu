@@ -1263,7 +1263,7 @@ static int front_reset(sgic_index* f);
 extern "C" {
 
 const char* sgic_last_error(void) { return g_err.c_str(); }
-int sgic_version(void) { return 100; }
+int sgic_version(void) { return 200; }
 
 int sgic_index_create(int d, int dtype, int device, int64_t capacity_rows, int flags, sgic_index** out) {
   SGIC_REQUIRE(out != nullptr, "out is NULL");
