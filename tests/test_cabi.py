@@ -177,3 +177,34 @@ def test_deeply_nested_clip_meta_is_skipped_not_followed():
         except (RecursionError, ValueError):
             ref_ok = False
         assert ref_ok == (int(st) == 0)
+
+
+def _build_c_smoke(tmp_path):
+    """tests/c/cabi_smoke.c compiled as C99 against include/sgic.h and linked with libsgic.so — no Python, no C++."""
+    import subprocess
+    exe = tmp_path / "cabi_smoke"
+    pkg = _native.LIB_PATH.parent
+    cmd = ["gcc", "-std=c99", "-O2", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"),
+           str(ROOT / "tests" / "c" / "cabi_smoke.c"), "-L", str(pkg), "-lsgic", f"-Wl,-rpath,{pkg}", "-lm", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_program_links_against_the_abi_and_refuses_to_run_without_a_gpu(tmp_path):
+    import subprocess
+    import torch
+    exe = _build_c_smoke(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the GPU tier runs the program")
+    r = subprocess.run([str(exe), str(tmp_path / "x.index")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 77 and "no CPU fallback" in r.stderr          # loud refusal, not a silent CPU path
+
+
+@pytest.mark.gpu
+def test_c_program_runs_the_path_through_the_abi(tmp_path):
+    """create / add / search / write / read / sharded create from plain C: answers checked against a brute force in C."""
+    import subprocess
+    exe = _build_c_smoke(tmp_path)
+    r = subprocess.run([str(exe), str(tmp_path / "x.index")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "cabi_smoke ok" in r.stdout, r.stdout + r.stderr
