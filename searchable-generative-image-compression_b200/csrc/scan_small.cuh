@@ -58,6 +58,14 @@ struct ScanSmallParams {
   // search of one or two queries then needs no H2D copy at all (a copy engine costs ~8 us of start-up latency, and
   // 148 CTAs fetching 2 KB each from pinned host memory over PCIe were measured slower still: 32-byte reads)
   float q_inline[kScanInlineQ];
+  // Multi-GPU exchange folded into the scan (SURVEY.md §8e "optional fusion: peer-store epilogue + flag"): when x_n > 0
+  // the last CTA's merge stores the answer — global row numbers — into x_n destinations (gather slots in the home GPU's
+  // or every peer's HBM, mapped over NVLink) instead of (D, I), and then raises one system-scope release flag per
+  // destination to x_epoch.  The merge kernel on the other side spins on the flags: no push kernel, no event.
+  uint32_t x_n, x_epoch;
+  float* xD[16];
+  long long* xI[16];
+  uint32_t* xF[16];
 };
 
 // next pass's bound = key of the last answer slot of this pass (1 = "nothing left" if that slot is padding)
@@ -326,8 +334,22 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_small_kernel(const __gri
     long long* I = p.I;
     const size_t o0 = static_cast<size_t>(warp) * p.k;
     const long long base = p.id_base;
-    warp_multiway_merge<kMergeMaxLpl>(all + static_cast<size_t>(warp) * per_q, gridDim.x, p.k, p.k, lane,
-                                      [=](uint32_t r, uint64_t key) { store_answer(D, I, o0 + r, key, base); });
+    if (p.x_n == 0) {
+      warp_multiway_merge<kMergeMaxLpl>(all + static_cast<size_t>(warp) * per_q, gridDim.x, p.k, p.k, lane,
+                                        [=](uint32_t r, uint64_t key) { store_answer(D, I, o0 + r, key, base); });
+    } else {
+      const ScanSmallParams* pp = &p;  // grid-constant: lives in the constant bank
+      warp_multiway_merge<kMergeMaxLpl>(all + static_cast<size_t>(warp) * per_q, gridDim.x, p.k, p.k, lane,
+                                        [=](uint32_t r, uint64_t key) {
+                                          for (uint32_t j = 0; j < pp->x_n; ++j)
+                                            store_answer(pp->xD[j], pp->xI[j], o0 + r, key, base);
+                                        });
+      __threadfence_system();  // every lane that stored (lane 0, and the padding loop's lanes) orders its stores
+    }
+  }
+  if (p.x_n != 0) {
+    __syncthreads();  // all queries' answers are out (and fenced) before any flag goes up
+    if (tid < static_cast<int>(p.x_n)) st_release_sys(p.xF[tid], p.x_epoch);
   }
   if (tid == 0) {
     *p.counter = 0u;

@@ -947,11 +947,21 @@ static int search_dense_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
   return 0;
 }
 
+// Where a search's answer goes when it is one shard's part of a multi-GPU search: `n` gather slots (in the home GPU's
+// or every peer's memory) and their flags.  A search that can fold the push into its final writer (K3's last CTA) does
+// so and reports *pushed = true; otherwise it writes (dev_D, dev_I) as usual and the caller pushes.
+struct XDst {
+  uint32_t n = 0, epoch = 0;
+  float* D[16];
+  long long* I[16];
+  uint32_t* F[16];
+};
+
 // host_q_inline != nullptr (and dev_q == nullptr): the queries are taken from host memory and travel in the kernel
 // parameters (nq * d <= kScanInlineQ)
 static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
                              int64_t id_base, cudaStream_t st, const uint64_t* bound = nullptr,
-                             const float* host_q_inline = nullptr);
+                             const float* host_q_inline = nullptr, const XDst* xd = nullptr, bool* pushed = nullptr);
 
 // Smallest batch that goes to the tensor-core kernels ("dense_min_nq" overrides).  K3 owns lanes by 256-element
 // slabs of a row (8 elements per lane and chunk): at d = 512 / 768 / 1024 / 2048 every lane works and one query
@@ -970,7 +980,8 @@ static int64_t auto_dense_min_nq(const sgic_index* h) {
 // Searches `nq` device-resident fp32 queries; results to device buffers.  Regime choice: a few
 // queries -> K3 (CUDA-core streaming scan, HBM-bound); batches -> K4 (tcgen05 dense contraction).
 static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
-                           int64_t id_base, cudaStream_t st) {
+                           int64_t id_base, cudaStream_t st, const XDst* xd = nullptr, bool* pushed = nullptr) {
+  if (pushed) *pushed = false;
   SGIC_REQUIRE(k >= 1, "k must be >= 1");
   SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
   if (nq == 0) return 0;
@@ -1011,19 +1022,21 @@ static int search_dev_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_
   // tensor cores always (K3 with 4 queries is FMA-bound: 18.5 ms at 100M rows against 15.4 ms).
   const int64_t min_nq = auto_dense_min_nq(h);
   if (h->ntotal > 0 && nq >= min_nq) return search_dense_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st);
-  return search_small_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st);
+  return search_small_impl(h, nq, dev_q, k, dev_D, dev_I, id_base, st, nullptr, nullptr, xd, pushed);
 }
 
 // The same for queries in HOST memory.  One or two queries in the streaming regime ride in the kernel parameters (no
 // copy at all); anything else is staged through pinned memory (`pinned`: host_q already is pinned) and copied.
 static int search_hostq_impl(sgic_index* h, int64_t nq, const float* host_q, bool pinned, int64_t k, float* dev_D,
-                             int64_t* dev_I, int64_t id_base, cudaStream_t st) {
+                             int64_t* dev_I, int64_t id_base, cudaStream_t st, const XDst* xd = nullptr,
+                             bool* pushed = nullptr) {
+  if (pushed) *pushed = false;
   SGIC_REQUIRE(k >= 1, "k must be >= 1");
   SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
   if (nq == 0) return 0;
   const bool small = h->ntotal == 0 || nq < auto_dense_min_nq(h);
   if (small && k <= kMaxK && nq * h->d <= kScanInlineQ)
-    return search_small_impl(h, nq, nullptr, k, dev_D, dev_I, id_base, st, nullptr, host_q);
+    return search_small_impl(h, nq, nullptr, k, dev_D, dev_I, id_base, st, nullptr, host_q, xd, pushed);
   const size_t qbytes = static_cast<size_t>(nq) * h->d * 4;
   int rc = ensure_buf(&h->qdev, &h->qdev_bytes, qbytes, false);
   if (rc) return rc;
@@ -1034,11 +1047,13 @@ static int search_hostq_impl(sgic_index* h, int64_t nq, const float* host_q, boo
     src = h->qpin;
   }
   SGIC_CUDA(cudaMemcpyAsync(h->qdev, src, qbytes, cudaMemcpyHostToDevice, st));
-  return search_dev_impl(h, nq, static_cast<const float*>(h->qdev), k, dev_D, dev_I, id_base, st);
+  return search_dev_impl(h, nq, static_cast<const float*>(h->qdev), k, dev_D, dev_I, id_base, st, xd, pushed);
 }
 
 static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int64_t k, float* dev_D, int64_t* dev_I,
-                             int64_t id_base, cudaStream_t st, const uint64_t* bound, const float* host_q_inline) {
+                             int64_t id_base, cudaStream_t st, const uint64_t* bound, const float* host_q_inline,
+                             const XDst* xd, bool* pushed) {
+  if (pushed) *pushed = false;
   SGIC_REQUIRE(k >= 1, "k must be >= 1");
   SGIC_REQUIRE(k <= kMaxK, "k > 1024 is not supported by this build");
   SGIC_REQUIRE(nq >= 0, "nq must be >= 0");
@@ -1122,6 +1137,18 @@ static int search_small_impl(sgic_index* h, int64_t nq, const float* dev_q, int6
     p.I = reinterpret_cast<long long*>(dev_I + static_cast<size_t>(q0) * k);
     p.id_base = id_base;
     p.bound = bound;
+    p.x_n = 0;
+    p.x_epoch = 0;
+    if (xd != nullptr && xd->n > 0 && fused && nq <= NQ && n_rows > 0) {  // one launch answers the whole batch: fold the push
+      p.x_n = xd->n;
+      p.x_epoch = xd->epoch;
+      for (uint32_t j = 0; j < xd->n; ++j) {
+        p.xD[j] = xd->D[j];
+        p.xI[j] = xd->I[j];
+        p.xF[j] = xd->F[j];
+      }
+      if (pushed) *pushed = true;
+    }
     p.trace = reinterpret_cast<unsigned long long*>(static_cast<uintptr_t>(h->opt_trace));
     cudaError_t e;
     if (q0 == 0) {
@@ -2001,28 +2028,43 @@ int sgic_xchg_open(sgic_xchg* x, const uint8_t* handles) {
   return 0;
 }
 
-int sgic_xchg_merge_dev(sgic_xchg* x, int64_t nq, int64_t k, const float* dev_D_local, const int64_t* dev_I_local,
-                        float* dev_D, int64_t* dev_I, int tie_by_position, void* stream) {
-  SGIC_REQUIRE(x != nullptr && x->opened, "exchange is not open");
-  SGIC_REQUIRE(nq >= 1 && k >= 1 && nq * k <= x->max_cands, "nq * k exceeds the exchange buffer");
-  SGIC_REQUIRE(static_cast<int64_t>(x->world) * k < (1ll << 31), "too many candidates");
-  DeviceGuard g(x->device);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// one step of the exchange, in three parts so that a search can fold the push into its own final writer:
+//   xchg_begin  next epoch; where this rank's (nq, k) answer goes in every rank's buffer, and the flags to raise
+//   xchg_push   the push as a kernel of its own (the answer sits in local buffers)
+//   xchg_merge  merge of this rank's own buffer as soon as the `world` flags carry the epoch
+static void xchg_begin(sgic_xchg* x, XDst* xd) {
   const uint32_t epoch = ++x->epoch;
   const size_t par = epoch & 1u, W = static_cast<size_t>(x->world), MC = static_cast<size_t>(x->max_cands);
+  xd->n = static_cast<uint32_t>(x->world);
+  xd->epoch = epoch;
+  for (int r = 0; r < x->world; ++r) {
+    const size_t slot = par * W + static_cast<size_t>(x->rank);
+    xd->D[r] = reinterpret_cast<float*>(x->peer[r] + x->d_off) + slot * MC;
+    xd->I[r] = reinterpret_cast<long long*>(x->peer[r] + x->i_off) + slot * MC;
+    xd->F[r] = reinterpret_cast<uint32_t*>(x->peer[r] + slot * 128);
+  }
+}
+
+static int xchg_push(sgic_xchg* x, const XDst& xd, int64_t n, const float* dev_D_local, const int64_t* dev_I_local,
+                     cudaStream_t st) {
   XchgPushParams pp;
   pp.D = dev_D_local;
   pp.I = reinterpret_cast<const long long*>(dev_I_local);
-  pp.n = static_cast<uint32_t>(nq * k);
-  pp.epoch = epoch;
+  pp.n = static_cast<uint32_t>(n);
+  pp.epoch = xd.epoch;
   for (int r = 0; r < x->world; ++r) {
-    const size_t slot = par * W + static_cast<size_t>(x->rank);
-    pp.dstD[r] = reinterpret_cast<float*>(x->peer[r] + x->d_off) + slot * MC;
-    pp.dstI[r] = reinterpret_cast<long long*>(x->peer[r] + x->i_off) + slot * MC;
-    pp.dstFlag[r] = reinterpret_cast<uint32_t*>(x->peer[r] + slot * 128);
+    pp.dstD[r] = xd.D[r];
+    pp.dstI[r] = xd.I[r];
+    pp.dstFlag[r] = xd.F[r];
   }
   xchg_push_kernel<<<static_cast<unsigned>(x->world), 256, 0, st>>>(pp);
   SGIC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int xchg_merge(sgic_xchg* x, uint32_t epoch, int64_t nq, int64_t k, float* dev_D, int64_t* dev_I,
+                      int tie_by_position, cudaStream_t st) {
+  const size_t par = epoch & 1u, W = static_cast<size_t>(x->world), MC = static_cast<size_t>(x->max_cands);
   MergeListsParams mp;
   mp.D_lists = reinterpret_cast<const float*>(x->base + x->d_off) + par * W * MC;
   mp.I_lists = reinterpret_cast<const long long*>(x->base + x->i_off) + par * W * MC;
@@ -2051,14 +2093,31 @@ int sgic_xchg_merge_dev(sgic_xchg* x, int64_t nq, int64_t k, const float* dev_D_
   return 0;
 }
 
+int sgic_xchg_merge_dev(sgic_xchg* x, int64_t nq, int64_t k, const float* dev_D_local, const int64_t* dev_I_local,
+                        float* dev_D, int64_t* dev_I, int tie_by_position, void* stream) {
+  SGIC_REQUIRE(x != nullptr && x->opened, "exchange is not open");
+  SGIC_REQUIRE(nq >= 1 && k >= 1 && nq * k <= x->max_cands, "nq * k exceeds the exchange buffer");
+  SGIC_REQUIRE(static_cast<int64_t>(x->world) * k < (1ll << 31), "too many candidates");
+  DeviceGuard g(x->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  XDst xd;
+  xchg_begin(x, &xd);
+  int rc = xchg_push(x, xd, nq * k, dev_D_local, dev_I_local, st);
+  if (rc) return rc;
+  return xchg_merge(x, xd.epoch, nq, k, dev_D, dev_I, tie_by_position, st);
+}
+
 // One rank's whole search step with HOST buffers, in one call: pinned staging, H2D of the queries, the local scan
 // with global row numbers, the peer exchange + merge, D2H of the merged answer, one synchronise.  (The Python
 // host did the staging with torch calls before: ~70 us per step, more than the exchange itself.)
 int sgic_xchg_search(sgic_xchg* x, sgic_index* h, int64_t nq, const float* host_q, int64_t k, float* host_D,
                      int64_t* host_I, int64_t id_base, int tie_by_position) {
   SGIC_REQUIRE(x != nullptr && h != nullptr, "NULL argument");
+  SGIC_REQUIRE(x->opened, "exchange is not open");
   SGIC_REQUIRE(!is_front(h), "the peer exchange joins single-GPU indexes of different processes");
   SGIC_REQUIRE(k >= 1 && nq >= 1 && host_q && host_D && host_I, "bad arguments");
+  SGIC_REQUIRE(nq * k <= x->max_cands, "nq * k exceeds the exchange buffer");
+  SGIC_REQUIRE(static_cast<int64_t>(x->world) * k < (1ll << 31), "too many candidates");
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   const size_t qbytes = static_cast<size_t>(nq) * h->d * 4, cand = static_cast<size_t>(nq) * k;
@@ -2072,14 +2131,20 @@ int sgic_xchg_search(sgic_xchg* x, sgic_index* h, int64_t nq, const float* host_
   uint8_t* o = static_cast<uint8_t*>(h->odev);
   int64_t* lI = reinterpret_cast<int64_t*>(o + half);          // this rank's local answer
   float* lD = reinterpret_cast<float*>(o + half + cand * 8);
+  // the local scan: K3's last CTA stores the answer straight into every rank's buffer and raises the flags when it
+  // can (one or two queries); otherwise the answer lands in (lD, lI) and a push kernel carries it
+  XDst xd;
+  xchg_begin(x, &xd);
+  bool pushed = false;
+  static const bool fold = [] { const char* e = std::getenv("SGIC_XCHG_FOLD"); return !(e && e[0] == '0'); }();
+  rc = search_hostq_impl(h, nq, host_q, false, k, lD, lI, id_base, h->stream, fold ? &xd : nullptr, &pushed);
+  if (rc) return rc;
+  if (!pushed && (rc = xchg_push(x, xd, static_cast<int64_t>(cand), lD, lI, h->stream))) return rc;
   if (cand * 12 <= kZeroCopyBytes) {
     // small step: the merged answer is stored into pinned host memory by the merge kernel itself (no D2H copy)
     int64_t* pI = reinterpret_cast<int64_t*>(h->opin);
     float* pD = reinterpret_cast<float*>(static_cast<uint8_t*>(h->opin) + cand * 8);
-    rc = search_hostq_impl(h, nq, host_q, false, k, lD, lI, id_base, h->stream);
-    if (rc) return rc;
-    rc = sgic_xchg_merge_dev(x, nq, k, lD, lI, pD, pI, tie_by_position, h->stream);
-    if (rc) return rc;
+    if ((rc = xchg_merge(x, xd.epoch, nq, k, pD, pI, tie_by_position, h->stream))) return rc;
     SGIC_CUDA(cudaStreamSynchronize(h->stream));
     std::memcpy(host_I, pI, cand * 8);
     std::memcpy(host_D, pD, cand * 4);
@@ -2087,10 +2152,7 @@ int sgic_xchg_search(sgic_xchg* x, sgic_index* h, int64_t nq, const float* host_
   }
   int64_t* mI = reinterpret_cast<int64_t*>(o);                 // merged answer first: ids then scores, contiguous
   float* mD = reinterpret_cast<float*>(o + cand * 8);
-  rc = search_hostq_impl(h, nq, host_q, false, k, lD, lI, id_base, h->stream);
-  if (rc) return rc;
-  rc = sgic_xchg_merge_dev(x, nq, k, lD, lI, mD, mI, tie_by_position, h->stream);
-  if (rc) return rc;
+  if ((rc = xchg_merge(x, xd.epoch, nq, k, mD, mI, tie_by_position, h->stream))) return rc;
   SGIC_CUDA(cudaMemcpyAsync(h->opin, h->odev, cand * 12, cudaMemcpyDeviceToHost, h->stream));
   SGIC_CUDA(cudaStreamSynchronize(h->stream));
   std::memcpy(host_I, h->opin, cand * 8);
