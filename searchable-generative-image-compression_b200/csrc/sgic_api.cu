@@ -169,7 +169,7 @@ struct sgic_index {
   int64_t shard_row_start = 0, shard_total_rows = -1;
   int shard_id = 0, shard_count = 1;
   // options / stats
-  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1, opt_trace = 0, opt_steal = 1, opt_t_n8 = 1, opt_t_max_nq = 88, opt_dense_seed = 1, opt_dense_slices = 0, opt_epi_wait_ns = 0, opt_scan_wait_ns = 0;
+  int64_t opt_timing = 0, opt_evict_first = 1, opt_grid = 0, opt_stages = 0, opt_rb = 0, opt_fused = 1, opt_dense_min_nq = 0, opt_debug = 0, opt_dense_mode = 0, opt_device_zstd = 1, opt_dense_l2_mb = 0, opt_dense_b_min_mb = 90000, opt_dense_gthr = 1, opt_trace = 0, opt_steal = 1, opt_t_n8 = 1, opt_t_max_nq = 88, opt_dense_seed = 1, opt_dense_slices = 0, opt_epi_wait_ns = 0, opt_scan_wait_ns = 0, opt_fail_appends = 0;
   int64_t stat_ingest_h2d_ns = 0, stat_ingest_k0_ns = 0, stat_ingest_k1_ns = 0;
   int64_t stat_ingest_parse_ns = 0, stat_ingest_pack_ns = 0, stat_ingest_gpu_ns = 0;
   int64_t stat_zl_device_frames = 0, stat_zl_host_rows = 0, stat_zl_fallback_slabs = 0;
@@ -333,6 +333,11 @@ static void vmm_destroy(sgic_index* h) {
 
 // exact = true: an explicit reserve() — no geometric slack
 static int grow_database(sgic_index* h, int64_t rows, cudaStream_t st, bool exact) {
+  if (h->opt_fail_appends > 0) {  // fault injection for the tests of the error paths (option "fail_appends" = count)
+    --h->opt_fail_appends;
+    set_error("out of device memory (injected by the fail_appends option)");
+    return 3;
+  }
   if (rows <= h->capacity) return 0;
   const size_t row_bytes = static_cast<size_t>(h->d) * 2;
   if (vmm_init(h)) {
@@ -2701,6 +2706,7 @@ int sgic_index_set_option(sgic_index* h, const char* name, int64_t value) {
   else if (n == "fused") h->opt_fused = value;
   else if (n == "dense_min_nq") h->opt_dense_min_nq = value;
   else if (n == "debug") h->opt_debug = value;
+  else if (n == "fail_appends") h->opt_fail_appends = std::max<int64_t>(0, value);
   else if (n == "dense_mode") h->opt_dense_mode = value;
   else if (n == "device_zstd") h->opt_device_zstd = value;
   else if (n == "dense_l2_mb") h->opt_dense_l2_mb = std::max<int64_t>(0, value);

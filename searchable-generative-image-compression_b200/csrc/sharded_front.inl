@@ -19,7 +19,6 @@ class ShardPool {
  public:
   // devices[g]: the GPU worker g launches on; made current once, so the DeviceGuards inside the jobs are no-ops
   ShardPool(int n, const std::vector<int>& devices) : n_(n) {
-    for (int g = 1; g < n_; ++g) slots_.emplace_back(new Slot());
     for (int g = 1; g < n_; ++g)
       threads_.emplace_back([this, g, dev = devices[static_cast<size_t>(g)]] {
         cudaSetDevice(dev);
@@ -49,7 +48,6 @@ class ShardPool {
   }
 
  private:
-  struct Slot {};
   static void cpu_relax() {
 #if defined(__x86_64__)
     __builtin_ia32_pause();
@@ -79,7 +77,6 @@ class ShardPool {
     }
   }
   int n_;
-  std::vector<std::unique_ptr<Slot>> slots_;
   std::vector<std::thread> threads_;
   std::mutex mu_;
   std::condition_variable cv_;
@@ -436,6 +433,26 @@ static std::vector<FrontPiece> front_place(sgic_index* f, int64_t n) {
   return out;
 }
 
+// An append that failed on one shard must not leave rows behind on the others: rows outside every run would still be
+// scanned and come back under the row number of a neighbouring run.  Every shard is cut back to the row count it
+// had before the call (the rows' bytes stay in HBM beyond ntotal and are overwritten by the next append).
+static void front_rollback(sgic_index* f, const std::vector<int64_t>& before) {
+  for (size_t g = 0; g < f->shards.size(); ++g) {
+    sgic_index* s = f->shards[g];
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->ntotal <= before[g]) continue;
+    {
+      DeviceGuard dg(s->device);
+      cudaStreamSynchronize(s->stream);  // nothing of the failed call is still in flight when the caller retries
+      (void)cudaGetLastError();
+    }
+    const size_t keep = static_cast<size_t>(before[g]) * static_cast<size_t>(s->d);
+    if (s->retain_ok && s->retained.size() > keep) s->retained.resize(keep);
+    if (s->codes_ok && s->codes.size() > keep) s->codes.resize(keep);
+    s->ntotal = before[g];
+  }
+}
+
 // host rows: kind 0 = fp32 (add_f32), 1 = u8 codes (add_u8)
 static int front_add_host(sgic_index* f, int64_t n, const void* host, int kind) {
   SGIC_REQUIRE(n >= 0, "n must be >= 0");
@@ -455,7 +472,12 @@ static int front_add_host(sgic_index* f, int64_t n, const void* host, int kind) 
     sgic_index* s = f->shards[static_cast<size_t>(g)];
     return kind == 0 ? sgic_index_add_f32(s, p->n, reinterpret_cast<const float*>(src)) : sgic_index_add_u8(s, p->n, src);
   });
-  if (rc) return rc;
+  if (rc) {
+    const std::string msg = g_err;
+    front_rollback(f, before);
+    set_error(msg);
+    return rc;
+  }
   for (const auto& p : pieces) front_note_segment(f, p.g, f->ntotal + p.lo, before[static_cast<size_t>(p.g)], p.n);
   f->ntotal += n;
   return 0;
@@ -472,16 +494,19 @@ static int front_add_dev(sgic_index* f, int64_t n, const void* dev, int kind, cu
   cudaStream_t st = stream ? stream : home->stream;
   const std::vector<FrontPiece> pieces = front_place(f, n);
   const size_t row_bytes = static_cast<size_t>(f->d) * (kind == 0 ? 4 : kind == 1 ? 1 : 2);
+  for (const auto& p : pieces)
+    SGIC_REQUIRE(S->direct[static_cast<size_t>(p.g)],
+                 "device-resident appends need peer access from every shard to the home GPU");
+  std::vector<int64_t> before(f->shards.size(), 0);
+  for (size_t g = 0; g < f->shards.size(); ++g) before[g] = f->shards[g]->ntotal;
   {
     DeviceGuard dg(home->device);
     SGIC_CUDA(cudaEventRecord(S->ev_q, st));
   }
-  for (const auto& p : pieces) {
+  auto one_piece = [&](const FrontPiece& p) -> int {
     const size_t gi = static_cast<size_t>(p.g);
     sgic_index* s = f->shards[gi];
-    const int64_t before = s->ntotal;
     const uint8_t* src = static_cast<const uint8_t*>(dev) + static_cast<size_t>(p.lo) * row_bytes;
-    SGIC_REQUIRE(S->direct[gi], "device-resident appends need peer access from every shard to the home GPU");
     {
       DeviceGuard dg(s->device);
       SGIC_CUDA(cudaStreamWaitEvent(s->stream, S->ev_q, 0));
@@ -494,12 +519,20 @@ static int front_add_dev(sgic_index* f, int64_t n, const void* dev, int kind, cu
       DeviceGuard dg(s->device);
       SGIC_CUDA(cudaEventRecord(S->ev_in[gi], s->stream));
     }
-    {
-      DeviceGuard dg(home->device);
-      SGIC_CUDA(cudaStreamWaitEvent(st, S->ev_in[gi], 0));  // the caller may reuse / free its buffer in stream order
+    DeviceGuard dg(home->device);
+    SGIC_CUDA(cudaStreamWaitEvent(st, S->ev_in[gi], 0));  // the caller may reuse / free its buffer in stream order
+    return 0;
+  };
+  for (const auto& p : pieces) {
+    const int rc = one_piece(p);
+    if (rc) {
+      const std::string msg = g_err;
+      front_rollback(f, before);
+      set_error(msg);
+      return rc;
     }
-    front_note_segment(f, p.g, f->ntotal + p.lo, before, p.n);
   }
+  for (const auto& p : pieces) front_note_segment(f, p.g, f->ntotal + p.lo, before[static_cast<size_t>(p.g)], p.n);
   f->ntotal += n;
   return 0;
 }
@@ -525,7 +558,12 @@ static int front_add_c2df(sgic_index* f, const uint8_t* blob, const int64_t* off
     return sgic_index_add_c2df(f->shards[static_cast<size_t>(g)], blob, offsets + lo, hi - lo, status_out + lo,
                                &added[static_cast<size_t>(g)], per_threads);
   });
-  if (rc) return rc;
+  if (rc) {
+    const std::string msg = g_err;
+    front_rollback(f, before);
+    set_error(msg);
+    return rc;
+  }
   int64_t start = f->ntotal;
   for (int g = 0; g < G; ++g) {
     front_note_segment(f, g, start, before[static_cast<size_t>(g)], added[static_cast<size_t>(g)]);

@@ -220,3 +220,59 @@ def test_service_runs_on_a_multi_gpu_index(tmp_path):
     svc.close()
     for idx in (one, many, index):
         idx.close()
+
+
+def test_failed_append_leaves_no_rows_behind(tmp_path):
+    """An append that fails on ONE shard (out of memory, here injected) is undone on the others: the index keeps its
+    row count, its row numbers and its answers, and the same append succeeds afterwards."""
+    import torch
+    from sgic_b200 import c2df as c2, faiss_compat as faiss
+    from sgic_b200.index_build import quantize_u8_and_compress
+    rng = np.random.default_rng(31)
+    d = 64
+    xb = unit(rng, 60_000, d)
+    many = faiss.IndexFlatIP(d, devices=device_list(3), retain_codes=True)
+    one = faiss.IndexFlatIP(d, device=0)
+    many.add(xb[:20_000])
+    one.add(xb[:20_000])
+    xq = unit(rng, 9, d)
+    want = one.search(xq, 10)
+    # host rows, cut over the three shards: the middle one fails
+    many.shard(1).set_option("fail_appends", 1)
+    with pytest.raises(RuntimeError, match="shard 1"):
+        many.add(xb[20_000:50_000])
+    assert many.ntotal == 20_000 and [many.shard(g).ntotal for g in range(3)] == [one.ntotal // 3 + (g < one.ntotal % 3) for g in range(3)]
+    got = many.search(xq, 10)
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
+    # device rows on the home GPU: the last shard fails after the first two have taken their slices
+    home = torch.device("cuda", many.shard(0).device)
+    many.shard(2).set_option("fail_appends", 1)
+    with pytest.raises(RuntimeError):
+        many.add_torch(torch.from_numpy(xb[20_000:50_000]).to(home))
+    assert many.ntotal == 20_000
+    # .c2df files: shard 0 fails
+    blobs = []
+    for v in xb[50_000:56_000]:
+        stream, meta = quantize_u8_and_compress(v)
+        blobs.append(c2.pack_c2df({"clip_stream": stream, "clip_meta": meta}, {"version": 2}))
+    offs = np.zeros(len(blobs) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in blobs], out=offs[1:])
+    blob = np.frombuffer(b"".join(blobs), dtype=np.uint8)
+    many.shard(0).set_option("fail_appends", 1)
+    with pytest.raises(RuntimeError):
+        many.add_c2df(blob, offs)
+    assert many.ntotal == 20_000
+    got = many.search(xq, 10)
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
+    # the same appends go through afterwards, and the row numbers are the single-GPU ones
+    many.add(xb[20_000:50_000])
+    one.add(xb[20_000:50_000])
+    added, status = many.add_c2df(blob, offs)
+    assert added == 6000 and not status.any() and many.ntotal == 56_000
+    one.add(many.reconstruct_n(50_000, 6000))
+    for nq, k in ((1, 10), (9, 10)):
+        D1, I1 = one.search(xq[:nq], k)
+        Dm, Im = many.search(xq[:nq], k)
+        assert np.array_equal(I1, Im) and np.array_equal(D1, Dm)
+    one.close()
+    many.close()
