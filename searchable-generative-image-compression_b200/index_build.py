@@ -6,8 +6,10 @@
 glob, per-file ``[SKIP]`` on any decode error, both naming schemes written
 (``faiss.index`` + ``paths.json`` + ``meta.json`` and ``index.faiss`` + ``ids.txt``) — but the
 per-file Python loop is replaced by the batched C++ parser + device-side loader
-(``IndexFlatIP.add_c2df``).  ``build-images`` / ``download`` need CLIP weights / network
-and are out of scope.
+(``IndexFlatIP.add_c2df``).  ``build_index_from_image_dir`` (:207-241, the ``build-images``
+command) embeds an image directory with the CLIP encoder of ``query_encoders`` — a local
+checkpoint directory instead of an OpenCLIP download — and writes the same four files; the
+``download`` command and ``auto_download`` need the network and are out of scope.
 """
 from __future__ import annotations
 
@@ -27,7 +29,8 @@ from . import zstd
 from .c2df import unpack_c2df
 from .retrieval import decode_clip_from_c2df, load_index  # build.py carries its own copies (:26-43, :106-126)
 
-__all__ = ["build_index_from_c2df_dir", "quantize_u8_and_compress", "FaissDB", "load_index", "from_npy_dir", "pack_npy_dir"]
+__all__ = ["build_index_from_c2df_dir", "build_index_from_image_dir", "list_images", "encode_images_in_batches",
+           "quantize_u8_and_compress", "FaissDB", "load_index", "from_npy_dir", "pack_npy_dir"]
 
 
 def quantize_u8_and_compress(z_unit: np.ndarray, model_id: str = "ViT-B-32:laion2b_s34b_b79k"):
@@ -113,6 +116,102 @@ def build_index_from_c2df_dir(c2df_dir, index_dir, *, dtype="fp16", device=None,
     print(f"[OK] Index process completed!: N={index.ntotal}, dim={d}")
     if model_id:
         print(f"[INFO] Suggested CLIP model: {model_id}")
+
+
+def _device_index(device) -> int:
+    """The reference passes torch device strings ("cuda", "cuda:1"); the index wants a GPU number."""
+    if device is None:
+        return 0
+    if isinstance(device, int):
+        return device
+    name = str(device)
+    if name.startswith("cuda"):
+        return int(name.split(":", 1)[1]) if ":" in name else 0
+    raise RuntimeError(f"device {device!r}: the index lives in GPU memory (use \"cuda\" or \"cuda:N\")")
+
+
+def list_images(root, exts=None) -> List[Path]:
+    """Image files under ``root`` in ``rglob`` order (NOT sorted — src/build.py:171-180), suffix match is
+    case-insensitive and a missing leading dot in ``exts`` is added."""
+    if exts is None:
+        exts = {".jpg", ".jpeg", ".png", ".webp", ".bmp"}
+    exts = {e if e.startswith(".") else "." + e for e in {str(e).lower() for e in exts}}
+    return [p for p in Path(root).rglob("*") if p.is_file() and p.suffix.lower() in exts]
+
+
+def encode_images_in_batches(img_paths, encoder, batch_size: int = 32):
+    """src/build.py:182-205: unreadable images are reported with ``[SKIP]`` and left out, the rest go through the
+    image tower ``batch_size`` at a time; returns the fp32 unit rows on the host (``None`` if no image could be read).
+    ``encoder``: a :class:`~.query_encoders.ClipQueryEncoder` (the embedding itself runs on its device)."""
+    from PIL import Image
+    feats, cur = [], []
+
+    def flush():
+        if cur:
+            feats.append(encoder.encode_image(list(cur)).cpu().numpy().astype("float32"))
+            cur.clear()
+
+    for pth in img_paths:
+        try:
+            im = Image.open(pth).convert("RGB")
+        except Exception as e:
+            print(f"[SKIP] Can't read the image {pth}: {e}")
+            continue
+        cur.append(im)
+        if len(cur) == batch_size:
+            flush()
+    flush()
+    return np.concatenate(feats, 0).astype("float32") if feats else None
+
+
+def build_index_from_image_dir(image_dir, index_dir, model_id, device=None, batch_size: int = 32, exts=None,
+                               limit=None, random_pick: bool = False, seed=None, desired=None,
+                               auto_download: bool = False, *, encoder=None, **index_kwargs) -> None:
+    """``build-images`` (src/build.py:207-241): embed every image under ``image_dir`` and write ``faiss.index`` +
+    ``paths.json`` + ``meta.json`` and ``index.faiss`` + ``ids.txt``.
+
+    ``model_id`` is what ``meta.json`` records; the network comes from ``encoder`` (a ``ClipQueryEncoder``) or, when
+    that is not given, from ``model_id`` read as a local checkpoint directory — OpenCLIP's ``arch:pretrained`` names
+    need a download.  Selection follows the reference: ``desired`` (if positive) else ``limit`` images, the first ones
+    in listing order or ``random.Random(seed).sample`` with ``random_pick``.  As in the reference the path lists name
+    every SELECTED image, also one whose pixels could not be read (build.py:236).  The fp32 rows are kept on the host
+    as well, so the interchange files hold exactly the encoder's vectors."""
+    import random
+    image_dir, index_dir = Path(image_dir), Path(index_dir)
+    index_dir.mkdir(parents=True, exist_ok=True)
+    all_imgs = list_images(image_dir, exts=exts)
+    if desired is not None and auto_download and len(all_imgs) < desired:
+        raise RuntimeError(f"{len(all_imgs)} images under {image_dir}, {desired} wanted: downloading the shortfall "
+                           "(build.py:138-169) needs the network and is not part of this package")
+    if not all_imgs:
+        raise RuntimeError(f"There is no image in {image_dir}")
+    target_n = desired if (desired is not None and desired > 0) else limit
+    if target_n is not None and 0 < target_n <= len(all_imgs):
+        all_imgs = random.Random(seed).sample(all_imgs, target_n) if random_pick else all_imgs[:target_n]
+    print(f"[INFO] Using {len(all_imgs)} images to build the index")
+    if encoder is None:
+        from .query_encoders import ClipQueryEncoder
+        if model_id is None or not Path(str(model_id)).is_dir():
+            raise RuntimeError(f"model_id {model_id!r} is not a local CLIP checkpoint directory (OpenCLIP names need a "
+                               "download); pass encoder=ClipQueryEncoder(...)")
+        encoder = ClipQueryEncoder(model_id, device=_device_index(device))
+    X = encode_images_in_batches(all_imgs, encoder, batch_size=batch_size)
+    if X is None:
+        raise RuntimeError("Failed to build FAISS index!")
+    d = X.shape[1]
+    if device is not None and "device" not in index_kwargs and "devices" not in index_kwargs:
+        index_kwargs["device"] = _device_index(device)
+    index = faiss.IndexFlatIP(d, **index_kwargs)
+    index.add(X)
+    paths = [str(p) for p in all_imgs]
+    faiss.write_index(index, str(index_dir / "faiss.index"))
+    (index_dir / "paths.json").write_text(json.dumps(paths, ensure_ascii=False, indent=2), encoding="utf-8")
+    (index_dir / "meta.json").write_text(json.dumps({"dim": d, "model_id": model_id}, ensure_ascii=False, indent=2),
+                                         encoding="utf-8")
+    faiss.write_index(index, str(index_dir / "index.faiss"))
+    (index_dir / "ids.txt").write_text("\n".join(paths), encoding="utf-8")
+    print(f"[OK] Index process completed!: N={index.ntotal}, dim={d}")
+    index.close()
 
 
 class FaissDB:
@@ -235,9 +334,25 @@ def main(argv=None) -> None:
     sp = sub.add_parser("build", help="build the index from a directory of .c2df")
     sp.add_argument("--c2df_dir", type=Path, required=True)
     sp.add_argument("--index_dir", type=Path, required=True)
+    si = sub.add_parser("build-images", help="build the index from an image directory (CLIP checkpoint: a local directory)")
+    si.add_argument("--image_dir", type=Path, required=True)
+    si.add_argument("--index_dir", type=Path, required=True)
+    si.add_argument("--model_id", type=str, default=None, help="local CLIP checkpoint directory (Hugging Face layout)")
+    si.add_argument("--device", type=int, default=0)
+    si.add_argument("--batch_size", type=int, default=32)
+    si.add_argument("--exts", type=str, nargs="*", default=None)
+    si.add_argument("--limit", type=int, default=None)
+    si.add_argument("--random_pick", action="store_true")
+    si.add_argument("--seed", type=int, default=None)
+    si.add_argument("--desired", type=int, default=None)
     args = ap.parse_args(argv)
     try:
-        build_index_from_c2df_dir(args.c2df_dir, args.index_dir)
+        if args.cmd == "build-images":
+            build_index_from_image_dir(args.image_dir, args.index_dir, args.model_id, args.device, args.batch_size,
+                                       set(args.exts) if args.exts else None, args.limit, args.random_pick, args.seed,
+                                       args.desired)
+        else:
+            build_index_from_c2df_dir(args.c2df_dir, args.index_dir)
     except Exception as e:
         print(f"[ERROR] {e}")
         traceback.print_exc()

@@ -59,3 +59,80 @@ def test_device_resident_query_equals_the_host_route():
         assert [paths[i] for i in I[r].tolist()] == [p for p, _ in want]
     with pytest.raises(ValueError, match="dims"):
         enc.search(faiss.IndexFlatIP(128, device=0), z)
+
+
+def _image_corpus(root, n=11, size=40):
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    (root / "sub").mkdir(parents=True)
+    names = []
+    for i in range(n):
+        ext = (".png", ".JPG", ".bmp")[i % 3]
+        p = (root / "sub" if i % 4 == 0 else root) / f"im{i:03d}{ext}"
+        Image.fromarray(rng.integers(0, 256, (size, size + i, 3), dtype=np.uint8)).save(p, format={".png": "PNG", ".JPG": "JPEG", ".bmp": "BMP"}[ext])
+        names.append(p)
+    (root / "notes.txt").write_text("not an image")
+    (root / "broken.png").write_bytes(b"\x89PNG but not really")
+    return names
+
+
+def _tiny_encoder():
+    from transformers import CLIPImageProcessor
+    from sgic_b200.query_encoders import ClipQueryEncoder
+    proc = CLIPImageProcessor(size={"shortest_edge": 32}, crop_size={"height": 32, "width": 32})
+    return ClipQueryEncoder(tiny_clip(), device=0, image_processor=proc)
+
+
+def test_list_images_and_batched_embedding_follow_the_reference(tmp_path, capsys):
+    """src/build.py:171-205: rglob order, case-insensitive suffixes, unreadable files skipped with a message."""
+    from sgic_b200.index_build import encode_images_in_batches, list_images
+    names = _image_corpus(tmp_path)
+    got = list_images(tmp_path)
+    assert set(got) == set(names) | {tmp_path / "broken.png"} and got == [p for p in tmp_path.rglob("*") if p in set(got)]
+    assert list_images(tmp_path, exts={"PNG"}) == [p for p in got if p.suffix.lower() == ".png"]
+    enc = _tiny_encoder()
+    X = encode_images_in_batches(got, enc, batch_size=4)
+    assert "[SKIP] Can't read the image" in capsys.readouterr().out
+    assert X.shape == (len(names), 64) and X.dtype == np.float32
+    assert np.allclose(np.linalg.norm(X, axis=1), 1.0, atol=1e-5)
+    one = encode_images_in_batches([p for p in got if p.name != "broken.png"][:3], enc, batch_size=32)
+    assert np.allclose(one, X[:3], atol=1e-5)         # the batch size does not change a row
+    assert encode_images_in_batches([tmp_path / "broken.png"], enc) is None
+
+
+@pytest.mark.gpu
+def test_build_index_from_image_dir_writes_the_reference_layout(tmp_path):
+    """build-images (src/build.py:207-241): four files, both naming schemes; the IxFI bytes are the encoder's fp32
+    rows exactly; an image query finds its own file through load_index + do_search."""
+    import json
+    from PIL import Image
+    from oracle import c2df_ref
+    from sgic_b200 import faiss_compat as faiss
+    from sgic_b200.index_build import build_index_from_image_dir, encode_images_in_batches, list_images
+    from sgic_b200.retrieval import do_search, load_index
+    img_dir, out = tmp_path / "images", tmp_path / "index"
+    img_dir.mkdir()
+    names = _image_corpus(img_dir)
+    (img_dir / "broken.png").unlink()
+    enc = _tiny_encoder()
+    build_index_from_image_dir(img_dir, out, "tiny-random-clip", "cuda", batch_size=4, encoder=enc)
+    listed = [str(p) for p in list_images(img_dir)]
+    assert sorted(p.name for p in out.iterdir()) == ["faiss.index", "ids.txt", "index.faiss", "meta.json", "paths.json"]
+    assert json.loads((out / "paths.json").read_text(encoding="utf-8")) == listed
+    assert (out / "ids.txt").read_text(encoding="utf-8") == "\n".join(listed)
+    assert json.loads((out / "meta.json").read_text()) == {"dim": 64, "model_id": "tiny-random-clip"}
+    X = encode_images_in_batches(list_images(img_dir), enc, batch_size=4)
+    c2df_ref.write_ixfi(tmp_path / "want.index", X)
+    assert (out / "faiss.index").read_bytes() == (tmp_path / "want.index").read_bytes() == (out / "index.faiss").read_bytes()
+    index, paths, meta = load_index(out)
+    q = enc.encode_image([Image.open(names[3]).convert("RGB")]).cpu().numpy()
+    res = do_search(q, index, paths, topk=3)
+    assert res[0][0] == str(names[3]) and abs(res[0][1] - 1.0) < 2e-3
+    index.close()
+    # selection: the first `limit` images in listing order; `desired` with auto_download cannot be served offline
+    build_index_from_image_dir(img_dir, tmp_path / "few", None, 0, limit=4, encoder=enc)
+    assert json.loads((tmp_path / "few" / "paths.json").read_text()) == listed[:4]
+    with pytest.raises(RuntimeError, match="network"):
+        build_index_from_image_dir(img_dir, tmp_path / "x", None, 0, desired=500, auto_download=True, encoder=enc)
+    with pytest.raises(RuntimeError, match="There is no image"):
+        build_index_from_image_dir(tmp_path / "index", tmp_path / "y", None, 0, encoder=enc)
