@@ -30,7 +30,7 @@ from .c2df import unpack_c2df
 from .retrieval import decode_clip_from_c2df, load_index  # build.py carries its own copies (:26-43, :106-126)
 
 __all__ = ["build_index_from_c2df_dir", "build_index_from_image_dir", "list_images", "encode_images_in_batches",
-           "quantize_u8_and_compress", "FaissDB", "load_index", "from_npy_dir", "pack_npy_dir"]
+           "quantize_u8_and_compress", "ClipCodec", "FaissDB", "load_index", "from_npy_dir", "pack_npy_dir"]
 
 
 def quantize_u8_and_compress(z_unit: np.ndarray, model_id: str = "ViT-B-32:laion2b_s34b_b79k"):
@@ -40,6 +40,32 @@ def quantize_u8_and_compress(z_unit: np.ndarray, model_id: str = "ViT-B-32:laion
     meta = {"model_id": model_id, "dim": int(z_unit.shape[0]), "quant": "u8_symmetric_-1_1",
             "codec": "zstd", "zstd_level": 19}
     return zstd.compress(q.tobytes(), 19), meta
+
+
+class ClipCodec:
+    """The retrieval half of src/compress.py:57-86: image → unit CLIP vector → u8 codes + zstd → ``clip_stream`` /
+    ``clip_meta`` of a ``.c2df``.  ``encoder`` is a :class:`~.query_encoders.ClipQueryEncoder` (or a local checkpoint
+    directory for one); ``model_name`` is what ``clip_meta["model_id"]`` records (the reference writes
+    ``"<arch>:<pretrained>"``)."""
+
+    def __init__(self, encoder, model_name: str = "ViT-B-32:laion2b_s34b_b79k", device=0):
+        if not hasattr(encoder, "encode_image"):
+            from .query_encoders import ClipQueryEncoder
+            encoder = ClipQueryEncoder(encoder, device=_device_index(device))
+        self.encoder = encoder
+        self.device = encoder.device
+        self.model_name = model_name
+
+    def image_to_unit_vec(self, img_tensor_CHW) -> np.ndarray:
+        """(3, H, W) tensor in [-1, 1] → (D,) fp32 unit vector on the host (compress.py:67-74: through an 8-bit PIL
+        image, then the CLIP preprocessing)."""
+        from PIL import Image
+        x = img_tensor_CHW.detach().clamp(-1, 1).mul(0.5).add(0.5)
+        pil = Image.fromarray(x.mul(255).byte().permute(1, 2, 0).cpu().numpy())
+        return self.encoder.encode_image([pil]).squeeze(0).cpu().numpy().astype("float32")
+
+    def quantize_u8_and_compress(self, z_unit: np.ndarray):
+        return quantize_u8_and_compress(z_unit, self.model_name)
 
 
 def _skip_reason(path: Path, code: int) -> str:

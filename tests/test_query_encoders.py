@@ -136,3 +136,22 @@ def test_build_index_from_image_dir_writes_the_reference_layout(tmp_path):
         build_index_from_image_dir(img_dir, tmp_path / "x", None, 0, desired=500, auto_download=True, encoder=enc)
     with pytest.raises(RuntimeError, match="There is no image"):
         build_index_from_image_dir(tmp_path / "index", tmp_path / "y", None, 0, encoder=enc)
+
+
+def test_clip_codec_makes_the_retrieval_streams_of_a_c2df(tmp_path):
+    """compress.py:57-86 + :262-281: image tensor -> unit vector -> (clip_stream, clip_meta); decoding the file gives
+    the vector back within the u8 quantiser's step."""
+    import torch
+    from sgic_b200 import c2df
+    from sgic_b200.index_build import ClipCodec
+    from sgic_b200.retrieval import decode_clip_from_c2df
+    codec = ClipCodec(_tiny_encoder(), model_name="tiny:random")
+    img = torch.rand(3, 48, 40, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    z = codec.image_to_unit_vec(img)
+    assert z.shape == (64,) and z.dtype == np.float32 and abs(np.linalg.norm(z) - 1.0) < 1e-5
+    stream, meta = codec.quantize_u8_and_compress(z)
+    assert meta == {"model_id": "tiny:random", "dim": 64, "quant": "u8_symmetric_-1_1", "codec": "zstd", "zstd_level": 19}
+    blob = c2df.pack_c2df({"clip_stream": stream, "clip_meta": meta}, {"version": 2, "model_id": "tiny:random"})
+    (tmp_path / "img.c2df").write_bytes(blob)
+    back, header = decode_clip_from_c2df(tmp_path / "img.c2df")
+    assert header["model_id"] == "tiny:random" and float(back @ z) > 0.995
