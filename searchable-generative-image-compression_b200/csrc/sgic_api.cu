@@ -2398,12 +2398,14 @@ static int read_v2_body(FILE* f, const char* path, const Sgi2Header& hd, int dev
   sgic_index* h = nullptr;
   int rc = sgic_index_create(static_cast<int>(hd.d), static_cast<int>(hd.dtype), device, hd.ntotal, flags & ~SGIC_RETAIN_F32, &h);
   if (rc) return rc;
+  // (the index is destroyed only after the block that holds its mutex has been left)
+  std::string fail_msg;
+  int fail_code = 0;
   auto fail = [&](const std::string& msg, int code) {
-    sgic_index_destroy(h);
-    set_error(msg);
-    return code;
+    fail_msg = msg;
+    fail_code = code;
   };
-  {
+  [&] {
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
     // Several readers, each with its own pair of pinned chunks and its own stream: chunk c is pread() by reader
@@ -2476,6 +2478,11 @@ static int read_v2_body(FILE* f, const char* path, const Sgi2Header& hd, int dev
     h->shard_total_rows = hd.total_rows;
     h->shard_id = static_cast<int>(hd.shard);
     h->shard_count = static_cast<int>(hd.n_shards);
+  }();
+  if (fail_code) {
+    sgic_index_destroy(h);
+    set_error(fail_msg);
+    return fail_code;
   }
   *out = h;
   return 0;
