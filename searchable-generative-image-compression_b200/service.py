@@ -14,8 +14,10 @@ wire formats:
   ``meta/searched``, ``item`` × n, ``done`` | ``error``), and :func:`serve` speaks it over a TCP socket, one
   JSON request per line.
 
-The CLIP text / image encoders (src/search.py:93-105) are outside this path: text and image queries arrive as
-embeddings (``vec`` / ``vec_path``), ``.c2df`` queries are decoded here exactly as ``encode_c2df_query`` does.
+``.c2df`` queries are decoded here exactly as ``encode_c2df_query`` does.  Text and image queries arrive as
+embeddings (``vec`` / ``vec_path``) or — when the service was given an ``encoder``
+(:class:`~.query_encoders.ClipQueryEncoder`, src/search.py:93-105 on the index's GPU) — as the text itself / the path
+of an image, like the reference's ``query-text`` / ``query-image`` commands (src/search.py:153-162).
 """
 from __future__ import annotations
 
@@ -51,13 +53,15 @@ class SearchService:
     def __init__(self, index_dir=None, *, index=None, paths: Optional[Sequence[str]] = None, meta: Optional[Dict] = None,
                  max_batch: int = 256, max_wait_ms: float = 1.0,
                  preview_url: Optional[Callable[[str], Optional[str]]] = None,
-                 max_topk: int = 1024, allowed_roots: Optional[Sequence] = None):
+                 max_topk: int = 1024, allowed_roots: Optional[Sequence] = None, encoder=None):
         if index is None:
             from .retrieval import load_index
             index, paths, meta = load_index(index_dir)
         self.index, self.paths, self.meta = index, list(paths), dict(meta or {})
         self.max_batch, self.max_wait = int(max_batch), float(max_wait_ms) / 1e3
         self.preview_url = preview_url or (lambda p: None)
+        self.encoder = encoder                      # ClipQueryEncoder or None (then text / image queries need "vec")
+        self._enc_lock = threading.Lock()           # one encoder pass at a time (one model, one stream)
         # Untrusted callers (the TCP front end): topk is clamped to `max_topk`, and server-side paths are only
         # opened below one of `allowed_roots` (none configured: no path requests over the socket, inline vectors
         # only).  In-process callers are trusted like the reference's CLI is.
@@ -137,6 +141,28 @@ class SearchService:
         v = np.load(npy_path).astype("float32").reshape(1, -1)
         return self.search_vec(l2n(v).astype("float32"), topk)
 
+    def _need_encoder(self, kind: str):
+        if self.encoder is None:
+            raise NotImplementedError(f"{kind} query without an embedding: no CLIP encoder was configured "
+                                      "(send \"vec\" or \"vec_path\", or start the service with one)")
+        return self.encoder
+
+    def search_text(self, text: str, topk: int = 10) -> List[Tuple[str, float]]:
+        """``query-text`` (src/search.py:153-156, :93-97): embed on the GPU, then the batched search."""
+        enc = self._need_encoder("text")
+        with self._enc_lock:
+            z = enc.encode_text([text]).cpu().numpy()
+        return self.search_vec(z, topk)
+
+    def search_image(self, image_path, topk: int = 10) -> List[Tuple[str, float]]:
+        """``query-image`` (src/search.py:157-160, :100-105)."""
+        enc = self._need_encoder("image")
+        from PIL import Image
+        im = Image.open(image_path).convert("RGB")
+        with self._enc_lock:
+            z = enc.encode_image([im]).cpu().numpy()
+        return self.search_vec(z, topk)
+
     # ------------------------------------------------------------------ the reference's wire formats
     @staticmethod
     def cli_json(results: Iterable[Tuple[str, float]]) -> str:
@@ -193,9 +219,13 @@ class SearchService:
                 items = self.search_vec_file(self._checked_path(request["vec_path"], trusted), topk)
             elif kind == "c2df":
                 items = self.search_c2df(self._checked_path(request["path"], trusted), topk)
+            elif kind == "text":
+                items = self.search_text(str(request.get("text", "")), topk)
+            elif kind == "image":
+                self._need_encoder("image")
+                items = self.search_image(self._checked_path(request["path"], trusted), topk)
             else:
-                raise NotImplementedError(f"{kind} query without an embedding: the CLIP encoder is outside this path "
-                                          "(send \"vec\" or \"vec_path\")")
+                raise ValueError(f"unknown query type {kind!r}")
             ms = lambda: int((time.perf_counter() - t0) * 1000)
             yield {"type": "meta", "stage": "searched", "count": len(items), "elapsed_ms": ms()}
             for p, s in items:
@@ -250,9 +280,14 @@ def main(argv=None) -> None:
     ap.add_argument("--max_topk", type=int, default=1024, help="largest topk a socket client may ask for")
     ap.add_argument("--allow_root", type=Path, action="append", default=[],
                     help="directory whose files socket clients may name in \"path\" / \"vec_path\" (repeatable)")
+    ap.add_argument("--clip_dir", type=Path, default=None,
+                    help="local CLIP checkpoint directory: text / image queries are embedded on the index's GPU")
     a = ap.parse_args(argv)
     svc = SearchService(a.index_dir, max_batch=a.max_batch, max_wait_ms=a.max_wait_ms, max_topk=a.max_topk,
                         allowed_roots=a.allow_root)
+    if a.clip_dir is not None:
+        from .query_encoders import ClipQueryEncoder
+        svc.encoder = ClipQueryEncoder(a.clip_dir, device=svc.index.device)
     srv = serve(svc, a.host, a.port)
     print(json.dumps({"listening": list(srv.server_address), "ntotal": svc.index.ntotal, "d": svc.index.d}), flush=True)
     try:

@@ -146,3 +146,57 @@ def test_untrusted_requests_are_clamped_confined_and_told_little(svc, tmp_path):
     [t.join() for t in th]
     assert len(out[8]) == 400 and all(len(out[i]) == 3 for i in range(8))
     assert (1, 400) in idx.calls and all(k == 3 for nq, k in idx.calls if (nq, k) != (1, 400))
+
+
+class _CharTokenizer:
+    """Stand-in vocabulary for the randomly initialised CLIP of the tests (no checkpoint can be downloaded)."""
+
+    def __call__(self, texts, padding=None, truncation=None, return_tensors=None):
+        import torch
+        ids = torch.zeros((len(texts), 8), dtype=torch.long)
+        for r, t in enumerate(texts):
+            for c, ch in enumerate(t[:8]):
+                ids[r, c] = 1 + (ord(ch) % 90)
+        return {"input_ids": ids}
+
+
+def test_text_and_image_queries_are_embedded_by_the_service(tmp_path):
+    """query-text / query-image (src/search.py:153-162) through the resident service: the encoder of
+    query_encoders in front of the batched search; socket clients may only name images below an allowed root."""
+    from PIL import Image
+    from transformers import CLIPImageProcessor
+    from sgic_b200.query_encoders import ClipQueryEncoder
+    from test_query_encoders import tiny_clip
+    enc = ClipQueryEncoder(tiny_clip(), device=0, tokenizer=_CharTokenizer(),
+                           image_processor=CLIPImageProcessor(size={"shortest_edge": 32}, crop_size={"height": 32, "width": 32}))
+    texts = [f"{chr(97 + i)} thing {i}" for i in range(20)]
+    rng = np.random.default_rng(2)
+    (tmp_path / "served").mkdir()
+    imgs = []
+    for i in range(5):
+        p = tmp_path / "served" / f"q{i}.png"
+        Image.fromarray(rng.integers(0, 256, (36, 36, 3), dtype=np.uint8)).save(p)
+        imgs.append(p)
+    outside = tmp_path / "elsewhere.png"
+    Image.fromarray(rng.integers(0, 256, (36, 36, 3), dtype=np.uint8)).save(outside)
+    rows = np.concatenate([enc.encode_text(texts).cpu().numpy(),
+                           enc.encode_image([Image.open(p).convert("RGB") for p in imgs]).cpu().numpy()])
+    paths = [f"text{i}" for i in range(20)] + [str(p) for p in imgs]
+    s = SearchService(index=OracleIndex(rows), paths=paths, meta={"dim": 64}, max_wait_ms=1.0, encoder=enc,
+                      allowed_roots=[tmp_path / "served"])
+    try:
+        assert s.search_text(texts[7], topk=3)[0][0] == "text7"
+        assert s.search_image(imgs[2], topk=1)[0][0] == str(imgs[2])
+        ev = list(s.ndjson_events({"type": "text", "text": texts[3], "topk": 2}, trusted=False))
+        assert ev[0]["query"] == texts[3] and ev[2]["path"] == "text3" and ev[-1]["type"] == "done"
+        ev = list(s.ndjson_events({"type": "image", "path": str(imgs[4]), "topk": 1}, trusted=False))
+        assert ev[0]["filename"] == "q4.png" and ev[2]["path"] == str(imgs[4])
+        ev = list(s.ndjson_events({"type": "image", "path": str(outside)}, trusted=False))
+        assert ev[-1] == {"type": "error", "detail": "path not allowed"}
+        ev = list(s.ndjson_events({"type": "audio", "path": str(imgs[0])}, trusted=False))
+        assert ev[-1] == {"type": "error", "detail": "bad request"}
+        s.encoder = None
+        ev = list(s.ndjson_events({"type": "text", "text": "x"}, trusted=False))
+        assert ev[-1]["type"] == "error" and "embedding" in ev[-1]["detail"]
+    finally:
+        s.close()
