@@ -252,17 +252,6 @@ __global__ void __launch_bounds__(256, 1) xchg_push_kernel(const XchgPushParams 
   if (threadIdx.x == 0) st_release_sys(p.dstFlag[dst], p.epoch);
 }
 
-// raises the flags of `n` destinations after whatever ran before it on the stream stored their lists (used when the
-// final writer was not K3's last CTA, which raises them itself)
-struct XchgFlagParams {
-  uint32_t n, epoch;
-  uint32_t* flag[16];
-};
-__global__ void xchg_flag_kernel(const XchgFlagParams p) {
-  __threadfence_system();
-  if (threadIdx.x < p.n) st_release_sys(p.flag[threadIdx.x], p.epoch);
-}
-
 __global__ void __launch_bounds__(1024, 1) merge_lists_kernel(MergeListsParams p) {
   extern __shared__ __align__(16) uint64_t ml_smem[];
   const uint32_t q = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
