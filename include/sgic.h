@@ -60,6 +60,9 @@ enum {
   SGIC_C2DF_WRONG_D = 7,       /* row dimension differs from the index's d (np.concatenate
                                   would raise in build.py:91)                              */
   SGIC_C2DF_BAD_TYPE = 8,      /* filemaker.py:135  ValueError: unknown type code          */
+  SGIC_C2DF_BAD_ENTRY = 9,     /* filemaker.py:102-135,149: the header or an entry does not
+                                  load (json.JSONDecodeError, UnicodeDecodeError, numpy's
+                                  TypeError / ValueError for an array entry)               */
 };
 
 const char* sgic_last_error(void);

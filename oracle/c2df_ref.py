@@ -54,12 +54,49 @@ def zstd_compress(buf: bytes, level: int = 19) -> bytes:
     return out.raw[:r]
 
 
+def _load_entry(t: int, payload: bytes):
+    """filemaker.py:102-135: the value an entry stands for.  The reference builds it for EVERY entry of a file while it
+    walks, so an entry that does not load (bad UTF-8, bad JSON, an array whose bytes do not fit its shape, an
+    unknown type code, a payload shorter than its fixed size) makes the whole file unreadable."""
+    if t == 6:
+        return None
+    if t == 7:
+        return bool(struct.unpack_from("<B", payload, 0)[0])
+    if t == 2:
+        return struct.unpack_from("<q", payload, 0)[0]
+    if t == 3:
+        return struct.unpack_from("<d", payload, 0)[0]
+    if t in (0, 1, 4):
+        (n,) = struct.unpack_from("<I", payload, 0)
+        inner = payload[4:4 + n]
+        return inner if t == 0 else inner.decode("utf-8") if t == 1 else json.loads(inner.decode("utf-8"))
+    if t == 5:
+        off = 0
+        (dt_len,) = struct.unpack_from("<B", payload, off)
+        off += 1
+        dt = payload[off:off + dt_len].decode("utf-8")
+        off += dt_len
+        (ndim,) = struct.unpack_from("<B", payload, off)
+        off += 1
+        shape = []
+        for _ in range(ndim):
+            (d,) = struct.unpack_from("<I", payload, off)
+            off += 4
+            shape.append(int(d))
+        (data_len,) = struct.unpack_from("<I", payload, off)
+        off += 4
+        return np.frombuffer(payload[off:off + data_len], dtype=np.dtype(dt)).reshape(shape)
+    raise ValueError(f"unknown type code: {t}")
+
+
 def walk(data: bytes):
-    """Entries of a .c2df as {key: (type_code, raw_payload)} + header dict (filemaker.py:137-173)."""
+    """Entries of a .c2df as {key: (type_code, raw_payload)} + header dict (filemaker.py:137-173).  Every entry is
+    loaded on the way, as the reference does (the loaded values are dropped: callers here want the raw payloads)."""
     if data[:4] != b"C2DF":
         raise AssertionError("bad magic")
     off = 4
-    off += 2                                   # version: read and ignored (filemaker.py:147)
+    struct.unpack_from("<H", data, off)        # version: read and ignored (filemaker.py:147)
+    off += 2
     (hlen,) = struct.unpack_from("<I", data, off)
     off += 4
     header = json.loads(data[off:off + hlen].decode("utf-8")) if hlen > 0 else {}
@@ -83,8 +120,10 @@ def walk(data: bytes):
         else:
             (size,) = struct.unpack_from("<I", data, off)
             off += 4
-        out[key] = (t, data[off:off + size])
+        payload = data[off:off + size]         # slices clamp at the end of the data; unpack_from raises
         off += size
+        _load_entry(t, payload)
+        out[key] = (t, payload)
     return out, header
 
 

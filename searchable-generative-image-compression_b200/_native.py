@@ -90,6 +90,7 @@ C2DF_STATUS = {
     6: "Dimension didn't match",
     7: "vector dimension differs from the index dimension",
     8: "unknown type code",
+    9: "the header or an entry does not load (invalid JSON / UTF-8 / array entry)",
 }
 
 
