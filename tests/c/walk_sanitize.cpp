@@ -36,6 +36,13 @@ int main(int argc, char** argv) {
       sgic::Found fd;
       sgic::WalkMemo memo;
       int st = sgic::walk_one(exact.data(), exact.size(), &fd, (i & 1) ? &memo : nullptr);
+      if (st == 0 && fd.has_stream && fd.stream_is_bytes && fd.stream_len <= sgic::kZlMaxFrameBytes) {
+        // the frame classifier of the device-decode route reads the stream on the host as well; an exact-size copy again
+        std::vector<uint8_t> frame(fd.stream, fd.stream + fd.stream_len);
+        frame.shrink_to_fit();
+        sgic::zl::FrameInfo fi;
+        (void)sgic::zl::parse_frame(frame.data(), static_cast<uint32_t>(frame.size()), fi);
+      }
       long long dim = 0;
       if (st == 0 && fd.has_meta && fd.meta_type == 4 && sgic::clip_meta_dim(fd.meta, fd.meta_dim, &dim)) ++kept;
       ++total;
