@@ -289,3 +289,55 @@ def test_walker_is_memory_safe_on_hostile_files(golden, tmp_path):
     r = subprocess.run([str(exe), str(tmp_path / "blob.bin"), str(tmp_path / "offs.bin")], capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0 and "no sanitizer report" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+def test_header_json_grammar_equals_json_loads_on_random_texts():
+    """The header of a .c2df goes through ``json.loads(bytes.decode('utf-8'))`` in the reference (filemaker.py:149) and
+    any JSON value is accepted there, which makes it a clean probe of the walker's JSON / UTF-8 rules against the
+    interpreter's own parser: 6000 random texts over a JSON-heavy alphabet, plus mutations of valid documents."""
+    import json
+    import struct
+    from sgic_b200 import c2df
+    from sgic_b200.index_build import quantize_u8_and_compress
+    rng = np.random.default_rng(99)
+    v = rng.standard_normal(64).astype(np.float32)
+    v /= np.linalg.norm(v)
+    stream, meta = quantize_u8_and_compress(v)
+    body = c2df.pack_c2df({"clip_stream": stream, "clip_meta": meta}, {})
+    assert body[6:10] == struct.pack("<I", 2) and body[10:12] == b"{}"       # magic, version, hlen, header
+    tail = body[12:]
+    alphabet = [b"{", b"}", b"[", b"]", b",", b":", b'"', b"\\", b"a", b"u", b"0", b"1", b"9", b"-", b"+", b".", b"e", b"E",
+                b" ", b"\n", b"\t", b"true", b"false", b"null", b"NaN", b"Infinity", b'"k"', b'"\\u00e9"', b"\xc3\xa9",
+                b"\xe2\x82\xac", b"\xff", b"\x00", b"\x1f", b"/", b"b", b"n", b"\r", b"\\\"", b"12", b"0.5", b"1e5"]
+    valid_docs = [b'{"a": [1, 2.5, -3e-2, true, false, null], "b": {"c": "d\\n\\u00e9", "e": []}, "f": "\xc3\xa9"}',
+                  b'[[], {}, [[[1]]], "x", -0, 0.0, 1E+2, NaN, -Infinity]', b'"just a string"', b"  42  ", b"-1.5e-7"]
+    texts = []
+    for _ in range(4000):
+        texts.append(b"".join(alphabet[int(k)] for k in rng.integers(0, len(alphabet), int(rng.integers(1, 9)))))
+    for _ in range(2000):
+        d = bytearray(valid_docs[int(rng.integers(0, len(valid_docs)))])
+        for _ in range(int(rng.integers(1, 3))):
+            op, pos = int(rng.integers(0, 3)), int(rng.integers(0, len(d)))
+            tok = alphabet[int(rng.integers(0, len(alphabet)))]
+            if op == 0:
+                d[pos:pos + 1] = tok
+            elif op == 1:
+                d[pos:pos] = tok
+            else:
+                del d[pos:pos + int(rng.integers(1, 4))]
+        texts.append(bytes(d))
+    texts = [t for t in texts if t]                                           # hlen == 0 means "no header", not ""
+    want = []
+    for t in texts:
+        try:
+            json.loads(t.decode("utf-8"))
+            want.append(True)
+        except (ValueError, RecursionError):                                  # JSONDecodeError, UnicodeDecodeError
+            want.append(False)
+    files = [body[:6] + struct.pack("<I", len(t)) + t + tail for t in texts]
+    offs = np.zeros(len(files) + 1, dtype=np.int64)
+    np.cumsum([len(f) for f in files], out=offs[1:])
+    _, status, _ = _parse(np.frombuffer(b"".join(files), dtype=np.uint8), offs, 64, threads=2)
+    wrong = [(texts[i], want[i], int(status[i])) for i in range(len(texts)) if (status[i] == 0) != want[i]]
+    assert not wrong, wrong[:10]
+    assert 300 < sum(want) < len(want) - 300                                  # both verdicts are well represented
