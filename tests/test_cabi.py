@@ -341,3 +341,47 @@ def test_header_json_grammar_equals_json_loads_on_random_texts():
     wrong = [(texts[i], want[i], int(status[i])) for i in range(len(texts)) if (status[i] == 0) != want[i]]
     assert not wrong, wrong[:10]
     assert 300 < sum(want) < len(want) - 300                                  # both verdicts are well represented
+
+
+def test_dim_spellings_equal_python_int_on_random_texts():
+    """``int(meta.get("dim", 0))`` (src/search.py:30) over 12 000 random ``{"dim": …}`` texts — digits, signs,
+    underscores, whitespace and decimal digits of other scripts (raw and as \\u escapes), floats, literals, containers,
+    duplicate keys: the walker keeps a file exactly when Python's own ``json`` + ``int`` arrive at the stream's size."""
+    import struct
+    from oracle import c2df_ref
+    from sgic_b200.index_build import quantize_u8_and_compress
+    rng = np.random.default_rng(123)
+    v = rng.standard_normal(64).astype(np.float32)
+    v /= np.linalg.norm(v)
+    stream, _ = quantize_u8_and_compress(v)
+    alphabet = [b'"', b"6", b"4", b"0", b"_", b" ", b"+", b"-", b".", b"e", b"1", b"\\t", b"\\n", b"\\u0036", b"\\u0034",
+                b"\\u00a0", b"\\u2003", b"\\uff16", b"\\uff14", b"\\u0666", b"\\u0664", b"\xef\xbc\x96", b"\xef\xbc\x94",
+                b"\xc2\xa0", b"true", b"false", b"null", b"64", b'"64"', b"6.4e1", b"[", b"]", b",", b"\\u001f", b"\\u000c",
+                b"\\u000b", b"\\u0085", b"\\u1680", b"\\u3000", b"\\ud835\\udfd4", b"\xf0\x9d\x9f\x94", b"E", b"00"]
+
+    def lp(b):
+        return struct.pack("<I", len(b)) + b
+
+    def entry(key, t, payload):
+        return struct.pack("<H", len(key)) + key + struct.pack("<B", t) + struct.pack("<I", len(payload)) + payload
+
+    files, want, texts = [], [], []
+    for _ in range(12_000):
+        soup = b"".join(alphabet[int(k)] for k in rng.integers(0, len(alphabet), int(rng.integers(1, 8))))
+        text = (b'{"dim":"x","dim":' if rng.integers(0, 4) == 0 else b'{"dim":') + soup + b"}"
+        f = (b"C2DF" + struct.pack("<H", 1) + struct.pack("<I", 2) + b"{}" + struct.pack("<I", 2) +
+             entry(b"clip_stream", 0, lp(stream)) + entry(b"clip_meta", 4, lp(text)))
+        try:
+            q, _ = c2df_ref.decode_clip(f)
+            ok = q.size == 64
+        except Exception:
+            ok = False
+        files.append(f)
+        want.append(ok)
+        texts.append(text)
+    offs = np.zeros(len(files) + 1, dtype=np.int64)
+    np.cumsum([len(f) for f in files], out=offs[1:])
+    _, status, _ = _parse(np.frombuffer(b"".join(files), dtype=np.uint8), offs, 64, threads=2)
+    wrong = [(texts[i], want[i], int(status[i])) for i in range(len(texts)) if (status[i] == 0) != want[i]]
+    assert not wrong, wrong[:10]
+    assert sum(want) > 60
