@@ -568,8 +568,8 @@ bool clip_meta_dim(const char* s, const JsonDim& cap, long long* dim) {
 }
 
 // numpy's itemsize for the dtype strings np.dtype() understands among the ones an array's dtype.str / dtype.name can
-// be (filemaker.py:25,128-129); 0 = "data type not understood" (TypeError in the reference).  Structured, datetime
-// and object dtypes are not recognised: a file carrying such an array is skipped.
+// be (filemaker.py:25,128-129); 0 = "data type not understood" (TypeError in the reference).  Structured, sub-array
+// ("4i4"), datetime and object dtypes are not recognised: a file carrying such an array is skipped.
 size_t np_itemsize(const uint8_t* p, size_t n) {
   // array-protocol type strings first ("<i4", "|u1", "<f4": what dtype.str gives and the reference writes)
   size_t i = 0;
