@@ -17,7 +17,7 @@ import json
 import sys
 import traceback
 from pathlib import Path
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -164,6 +164,17 @@ def _load_vec(path: Path, d: int) -> np.ndarray:
     return l2n(v).astype("float32")
 
 
+def resolve_clip_dir(arg, meta) -> Optional[Path]:
+    """Where the CLIP checkpoint of a text / image query comes from: ``--clip_dir``, else ``$SGIC_CLIP_DIR``, else
+    ``meta["model_id"]`` when that names a local directory (the reference picks its model from ``meta["model_id"]``,
+    src/search.py:151-152 — an OpenCLIP name there, which needs a download).  With the environment variable set, the
+    reference's own command line (``query-text --index_dir D --text T --topk K``, webapp.py:246-248) works unchanged."""
+    for cand in (arg, os.environ.get("SGIC_CLIP_DIR"), (meta or {}).get("model_id")):
+        if cand and Path(str(cand)).is_dir():
+            return Path(str(cand))
+    return None
+
+
 def main(argv=None) -> None:
     ap = argparse.ArgumentParser(description="query-text / query-image / query-c2df")
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -183,11 +194,12 @@ def main(argv=None) -> None:
     args = ap.parse_args(argv)
     try:
         index, paths, _meta = load_index(args.index_dir)
+        clip_dir = resolve_clip_dir(getattr(args, "clip_dir", None), _meta) if args.cmd != "query-c2df" else None
         if args.cmd == "query-c2df":
             q = encode_c2df_query(args.c2df)
-        elif args.cmd in ("query-text", "query-image") and args.vec is None and args.clip_dir is not None:
+        elif args.cmd in ("query-text", "query-image") and args.vec is None and clip_dir is not None:
             from .query_encoders import ClipQueryEncoder
-            enc = ClipQueryEncoder(args.clip_dir, device=index.device)
+            enc = ClipQueryEncoder(clip_dir, device=index.device)
             if args.cmd == "query-text":
                 z = enc.encode_text([args.text])
             else:
@@ -200,7 +212,7 @@ def main(argv=None) -> None:
             if args.vec is None:
                 raise NotImplementedError(
                     f"{args.cmd}: no CLIP weights can be fetched offline; pass a local checkpoint with --clip_dir DIR "
-                    "or the embedding with --vec file.npy")
+                    "(or $SGIC_CLIP_DIR) or the embedding with --vec file.npy")
             q = _load_vec(args.vec, index.d)
         else:
             raise ValueError(f"Unknown behavior: {args.cmd}")

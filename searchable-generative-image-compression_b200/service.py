@@ -285,9 +285,11 @@ def main(argv=None) -> None:
     a = ap.parse_args(argv)
     svc = SearchService(a.index_dir, max_batch=a.max_batch, max_wait_ms=a.max_wait_ms, max_topk=a.max_topk,
                         allowed_roots=a.allow_root)
-    if a.clip_dir is not None:
+    from .retrieval import resolve_clip_dir
+    clip_dir = resolve_clip_dir(a.clip_dir, svc.meta)
+    if clip_dir is not None:
         from .query_encoders import ClipQueryEncoder
-        svc.encoder = ClipQueryEncoder(a.clip_dir, device=svc.index.device)
+        svc.encoder = ClipQueryEncoder(clip_dir, device=svc.index.device)
     srv = serve(svc, a.host, a.port)
     print(json.dumps({"listening": list(srv.server_address), "ntotal": svc.index.ntotal, "d": svc.index.d}), flush=True)
     try:

@@ -155,3 +155,20 @@ def test_clip_codec_makes_the_retrieval_streams_of_a_c2df(tmp_path):
     (tmp_path / "img.c2df").write_bytes(blob)
     back, header = decode_clip_from_c2df(tmp_path / "img.c2df")
     assert header["model_id"] == "tiny:random" and float(back @ z) > 0.995
+
+
+def test_clip_checkpoint_resolution_order(tmp_path, monkeypatch):
+    """--clip_dir, then $SGIC_CLIP_DIR, then meta["model_id"] when it is a directory (src/search.py:151-152 takes the
+    model from meta["model_id"]); OpenCLIP names and missing directories resolve to nothing."""
+    from sgic_b200.retrieval import resolve_clip_dir
+    a, b, c = tmp_path / "a", tmp_path / "b", tmp_path / "c"
+    for d in (a, b, c):
+        d.mkdir()
+    monkeypatch.delenv("SGIC_CLIP_DIR", raising=False)
+    assert resolve_clip_dir(None, {"model_id": "ViT-B-32:laion2b_s34b_b79k"}) is None
+    assert resolve_clip_dir(None, None) is None
+    assert resolve_clip_dir(None, {"model_id": str(c)}) == c
+    monkeypatch.setenv("SGIC_CLIP_DIR", str(b))
+    assert resolve_clip_dir(None, {"model_id": str(c)}) == b
+    assert resolve_clip_dir(a, {"model_id": str(c)}) == a
+    assert resolve_clip_dir(tmp_path / "missing", {"model_id": None}) == b
